@@ -1,0 +1,221 @@
+"""Seeded synthetic audio and seeded random-init merged checkpoints (TEST INFRASTRUCTURE).
+
+Everything is generated with ``torch.Generator`` on the CPU so the build container
+(where the reference runs and the goldens are made) and the GPU box (same image,
+same torch build) see identical bytes.
+
+Audio  : SURVEY.md section 8(d) "noise/tone" recipe.
+Weights: "random-init of the named architecture" (BASELINE.json), in the merged
+         layout ``sub_models.<i>.base.*`` / ``sub_models.<i>.head.{2,3,6,7,10}.*``
+         written by MM:154-159.  BN running statistics are *calibrated* on seeded
+         synthetic images (SURVEY.md section 7 hard part 1) so activations keep unit
+         scale through the 20 convolutions and the logits spread like a trained
+         model's instead of collapsing to a constant.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, List
+
+import torch
+import torch.nn.functional as F
+
+from . import restatement as R
+
+AUDIO_SEED = 20251018
+WEIGHT_SEED = 0
+CAL_FIRST = 1_000_000      # global index of the first calibration segment
+N_CAL = 32
+TARGET = 0.25               # |logit| the read-out is fitted to on the calibration corpus
+RIDGE = 10.0
+
+
+# --------------------------------------------------------------------------------------
+# audio
+# --------------------------------------------------------------------------------------
+def synth_segments(n: int, first: int = 0, seed: int = AUDIO_SEED) -> torch.Tensor:
+    """[n,128000] fp32 in [-1,1]: a_n*N(0,1) + a_t*sin(2 pi f t + phi), clipped.
+
+    Segment i (global index first+i) has its own generator seeded with seed ^ i, so any
+    shard can be produced independently.  10% pure noise, 10% pure tone.
+    """
+    out = torch.empty(n, R.WINDOW_SAMPLES, dtype=torch.float32)
+    t = torch.arange(R.WINDOW_SAMPLES, dtype=torch.float64) / R.SAMPLE_RATE
+    for k in range(n):
+        g = torch.Generator().manual_seed(seed ^ (first + k))
+        u = torch.rand(6, generator=g, dtype=torch.float64)
+        a_n = math.exp(math.log(1e-3) + float(u[0]) * (math.log(0.2) - math.log(1e-3)))
+        a_t = 0.5 * float(u[1])
+        f = math.exp(math.log(50.0) + float(u[2]) * (math.log(11000.0) - math.log(50.0)))
+        phi = 2 * math.pi * float(u[3])
+        kind = float(u[4])
+        if kind < 0.1:
+            a_t = 0.0
+        elif kind < 0.2:
+            a_n = 1e-3          # "pure tone": only the minimum noise floor
+            a_t = max(a_t, 0.05)
+        noise = torch.randn(R.WINDOW_SAMPLES, generator=g, dtype=torch.float32)
+        tone = torch.sin(2 * math.pi * f * t + phi).to(torch.float32)
+        out[k] = torch.clamp(a_n * noise + a_t * tone, -1.0, 1.0)
+    return out
+
+
+def synth_clip(n_samples: int, seed: int, silent_spans=()) -> torch.Tensor:
+    """A longer clip for slicing tests; ``silent_spans`` are (start, stop) sample ranges zeroed."""
+    g = torch.Generator().manual_seed(seed)
+    x = 0.1 * torch.randn(n_samples, generator=g, dtype=torch.float32)
+    t = torch.arange(n_samples, dtype=torch.float64) / R.SAMPLE_RATE
+    x = x + (0.3 * torch.sin(2 * math.pi * 440.0 * t)).float()
+    for a, b in silent_spans:
+        x[a:b] = 0.0
+    return torch.clamp(x, -1, 1)
+
+
+# --------------------------------------------------------------------------------------
+# weights
+# --------------------------------------------------------------------------------------
+def _layer_plan():
+    """(kind, name, ...) in the order timm/torchvision ResNet-18 registers its modules."""
+    plan = [("conv", "conv1", 64, 3, 7), ("bn", "bn1", 64)]
+    for li, (cin, cout) in enumerate(((64, 64), (64, 128), (128, 256), (256, 512)), start=1):
+        for b in range(2):
+            p = f"layer{li}.{b}"
+            c0 = cin if b == 0 else cout
+            plan += [("conv", f"{p}.conv1", cout, c0, 3), ("bn", f"{p}.bn1", cout),
+                     ("conv", f"{p}.conv2", cout, cout, 3), ("bn", f"{p}.bn2", cout)]
+            if b == 0 and li > 1:
+                plan += [("conv", f"{p}.downsample.0", cout, c0, 1), ("bn", f"{p}.downsample.1", cout)]
+    return plan
+
+
+def _rand_bn(sd, key, c, g):
+    sd[key + ".weight"] = 0.5 + torch.rand(c, generator=g)
+    sd[key + ".bias"] = 0.1 * torch.randn(c, generator=g)
+    sd[key + ".running_mean"] = 0.1 * torch.randn(c, generator=g)
+    sd[key + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+    sd[key + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.int64)
+
+
+def _rand_linear(sd, key, fin, fout, g):
+    bound = 1.0 / math.sqrt(fin)                         # nn.Linear default init range
+    sd[key + ".weight"] = (2 * torch.rand(fout, fin, generator=g) - 1) * bound
+    sd[key + ".bias"] = (2 * torch.rand(fout, generator=g) - 1) * bound
+
+
+def random_head_state(g: torch.Generator) -> "OrderedDict[str, torch.Tensor]":
+    """One BinaryClassifier's state_dict (136 keys: 120 base + 16 head), fp32, module order."""
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for item in _layer_plan():
+        if item[0] == "conv":
+            _, name, cout, cin, k = item
+            std = math.sqrt(2.0 / (cout * k * k))        # kaiming_normal_(fan_out, relu)
+            sd[f"base.{name}.weight"] = std * torch.randn(cout, cin, k, k, generator=g)
+        else:
+            _rand_bn(sd, f"base.{item[1]}", item[2], g)
+    _rand_linear(sd, "head.2", 512, 512, g)
+    _rand_bn(sd, "head.3", 512, g)
+    _rand_linear(sd, "head.6", 512, 256, g)
+    _rand_bn(sd, "head.7", 256, g)
+    _rand_linear(sd, "head.10", 256, 2, g)
+    return sd
+
+
+def _calibrate(sd: Dict[str, torch.Tensor], images: torch.Tensor, head_index: int = 0) -> None:
+    """Set every BN's running stats to the statistics its input has on ``images``.
+
+    Done layer by layer in forward order (so later layers see calibrated inputs).  The
+    final Linear(256,2) is then ridge-fitted on the calibration corpus (see below) so the
+    logits are bimodal with a margin on in-distribution inputs, like a trained detector's,
+    instead of hugging zero where any rounding flips the decision (hard part 1).
+    """
+    def stat(x, key, dims):
+        sd[key + ".running_mean"] = x.mean(dim=dims).clone()
+        sd[key + ".running_var"] = x.var(dim=dims, unbiased=False).clone() + 1e-3
+
+    with torch.no_grad():
+        p = "base."
+        x = F.conv2d(images, sd[p + "conv1.weight"], None, stride=2, padding=3)
+        stat(x, p + "bn1", (0, 2, 3))
+        x = F.relu(R._bn(x, sd, p + "bn1"))
+        x = F.max_pool2d(x, 3, 2, 1)
+        for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
+            for b in range(2):
+                q = f"{p}layer{li}.{b}"
+                s = stride if b == 0 else 1
+                o = F.conv2d(x, sd[q + ".conv1.weight"], None, stride=s, padding=1)
+                stat(o, q + ".bn1", (0, 2, 3))
+                o = F.relu(R._bn(o, sd, q + ".bn1"))
+                o = F.conv2d(o, sd[q + ".conv2.weight"], None, stride=1, padding=1)
+                stat(o, q + ".bn2", (0, 2, 3))
+                o = R._bn(o, sd, q + ".bn2")
+                if (q + ".downsample.0.weight") in sd:
+                    idn = F.conv2d(x, sd[q + ".downsample.0.weight"], None, stride=s)
+                    stat(idn, q + ".downsample.1", (0, 2, 3))
+                    idn = R._bn(idn, sd, q + ".downsample.1")
+                else:
+                    idn = x
+                x = F.relu(o + idn)
+        v = x.mean(dim=(2, 3))
+        v = F.linear(v, sd["head.2.weight"], sd["head.2.bias"])
+        stat(v, "head.3", (0,))
+        v = F.relu(R._bn(v, sd, "head.3"))
+        v = F.linear(v, sd["head.6.weight"], sd["head.6.bias"])
+        stat(v, "head.7", (0,))
+        v = F.relu(R._bn(v, sd, "head.7"))
+        # "Trained-like" read-out: ridge-fit the last Linear so that on the calibration corpus
+        # the Synthetic logit is +-TARGET according to an input attribute this head "detects"
+        # (mean level of one 64-row strip of the image = 16 mel bands); the Real logit follows an
+        # attribute common to all heads (strip 7).
+        def strip_sign(k):
+            a = images[:, 0, 64 * k:64 * k + 64, :].mean(dim=(1, 2))
+            return torch.where(a > a.median(), TARGET, -TARGET)
+        y_syn = strip_sign(head_index % 7)       # what THIS head detects
+        y_real = strip_sign(7)                   # shared by all heads, so mean_i(real_i) keeps its margin
+        Y = torch.stack([y_real, y_syn], dim=1).double()
+        X = torch.cat([v, torch.ones(v.shape[0], 1)], dim=1).double()
+        A = X.T @ X + RIDGE * torch.eye(X.shape[1], dtype=torch.float64)
+        A[-1, -1] -= RIDGE
+        Wb = torch.linalg.solve(A, X.T @ Y).float()
+        sd["head.10.weight"] = Wb[:-1].T.contiguous()
+        sd["head.10.bias"] = Wb[-1].contiguous()
+
+
+def calibration_images(n: int = N_CAL) -> torch.Tensor:
+    """[n,3,512,512] images of seeded synthetic segments through the oracle front end."""
+    x = synth_segments(n, first=CAL_FIRST)
+    img = R.waveform_to_image(x)
+    return img.unsqueeze(1).repeat(1, 3, 1, 1)
+
+
+_CAL_CACHE = {}
+
+
+def merged_state_dict(n_heads: int, seed: int = WEIGHT_SEED, calibrate: bool = True,
+                      n_cal: int = N_CAL) -> "OrderedDict[str, torch.Tensor]":
+    """Merged ModularMultiHeadClassifier.state_dict() with keys ``sub_models.<i>.*`` (MM:154-159)."""
+    imgs = None
+    if calibrate:
+        if n_cal not in _CAL_CACHE:
+            _CAL_CACHE[n_cal] = calibration_images(n_cal)
+        imgs = _CAL_CACHE[n_cal]
+    merged: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for i in range(n_heads):
+        g = torch.Generator().manual_seed(seed * 1000 + i)
+        sd = random_head_state(g)
+        if calibrate:
+            _calibrate(sd, imgs, head_index=i)
+        for k, v in sd.items():
+            merged[f"sub_models.{i}.{k}"] = v.contiguous()
+    return merged
+
+
+def class_names(n_heads: int) -> List[str]:
+    return [f"Synthetic{chr(ord('A') + i)}" for i in range(n_heads)] + ["Real"]
+
+
+def save_merged_checkpoint(path: str, n_heads: int, seed: int = WEIGHT_SEED, calibrate: bool = True):
+    """Write the file MM:154-159 writes: {'state_dict', 'metadata': {'class_names'}}."""
+    sd = merged_state_dict(n_heads, seed, calibrate)
+    torch.save({"state_dict": sd, "metadata": {"class_names": class_names(n_heads)}}, path)
+    return sd

@@ -1,0 +1,152 @@
+"""The CPU oracle (oracle/restatement.py) against golden vectors produced by the reference itself.
+
+Goldens: tests/golden/*.npz, written by oracle/make_golden.py from
+/root/reference/modular/source/inference_runner.py (functions cited per test).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures as FX
+from oracle import restatement as R
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+# ---------------------------------------------------------------- slicing (IR:176-190), bit exact
+def _clips():
+    short = FX.synth_clip(50000, seed=15)
+    return {
+        "ragged": FX.synth_clip(5 * 128000 + 777, seed=11),
+        "silent_mid": FX.synth_clip(6 * 128000, seed=12, silent_spans=[(128000, 3 * 128000)]),
+        "exact_one": FX.synth_clip(128000, seed=13),
+        "short_padded": R.pad_to_window(short),
+        "all_silent": torch.zeros(3 * 128000),
+        "quiet_edge": FX.synth_clip(2 * 128000, seed=14) * 0.0 + 9.9e-4,
+    }
+
+
+@pytest.mark.parametrize("tag,overlap,thr", [("cli", 0.0, 1e-3), ("dflt", 0.85, 1e-4)])
+def test_slicing_matches_reference(golden_dir, tag, overlap, thr):
+    g = _load(golden_dir, "slicing.npz")
+    for name, wf in _clips().items():
+        assert int(g[f"{name}.{tag}.n_samples"]) == wf.shape[0]
+        starts, kept = R.slice_waveform(wf, 32000, 4.0, overlap, thr)
+        mine = np.array([s for s, k in zip(starts, kept) if k], dtype=np.int64)
+        np.testing.assert_array_equal(mine, g[f"{name}.{tag}.starts"], err_msg=f"{name}.{tag}")
+        np.testing.assert_array_equal(mine / 32000, g[f"{name}.{tag}.stamps"])
+
+
+def test_window_hop_float_quirk():
+    # IR:181: int((1-0.85)*128000) == 19200 although the float product is 19200.000000000004
+    assert R.window_and_hop(32000, 4.0, 0.85) == (128000, 19200)
+    assert R.window_and_hop(32000, 4.0, 0.0) == (128000, 128000)
+
+
+def test_short_clip_is_padded_to_one_window(golden_dir):
+    g = _load(golden_dir, "slicing.npz")
+    assert g["short_padded.cli.starts"].tolist() == [0]
+    assert g["all_silent.cli.starts"].tolist() == []          # IR:264-273 empty-result case
+    assert g["quiet_edge.cli.starts"].tolist() == []          # 9.9e-4 < 1e-3 dropped by the CLI gate
+    assert g["quiet_edge.dflt.starts"].tolist() != []         # ... but kept by the dataclass default 1e-4
+
+
+# ---------------------------------------------------------------- front end (IR:157-174)
+def _golden_pcm(g):
+    x = torch.cat([FX.synth_segments(1, first=int(i)) for i in g["seg_ids"]])
+    np.testing.assert_array_equal(x.double().sum(1).numpy(), g["pcm_checksum"])   # same bytes as the golden run
+    return x
+
+
+def test_frontend_constants(golden_dir):
+    g = _load(golden_dir, "frontend.npz")
+    fb = R.mel_filterbank()
+    assert int((fb != 0).sum()) == int(g["fb_nnz"]) == 1515
+    np.testing.assert_array_equal(fb.sum(0).numpy(), g["fb_colsum"])
+    assert float(R.hann_window().sum()) == float(g["window_sum"]) == 1024.0
+    nz = (fb != 0).any(dim=1).nonzero().flatten()
+    assert int(nz.min()) == 2 and int(nz.max()) == 768
+
+
+def test_logmel_bit_identical_to_reference(golden_dir):
+    g = _load(golden_dir, "frontend.npz")
+    x = _golden_pcm(g)
+    db = R.logmel_db(x)
+    np.testing.assert_array_equal(db.numpy(), g["logmel_db"])
+    _, mu, sd = R.standardise(db)
+    np.testing.assert_array_equal(mu.numpy(), g["mu"])
+    np.testing.assert_array_equal(sd.numpy(), g["sigma"])
+
+
+def test_image_bit_identical_to_reference(golden_dir):
+    g = _load(golden_dir, "frontend.npz")
+    img = R.waveform_to_image(_golden_pcm(g)).numpy()
+    np.testing.assert_array_equal(img[:2], g["image_full"])
+    np.testing.assert_array_equal(img[:, ::7, ::5], g["image_sub"])
+    np.testing.assert_array_equal(img.astype(np.float64).sum(axis=(1, 2)), g["image_sum"])
+
+
+def test_framing_is_reflect_padding(golden_dir):
+    x = FX.synth_segments(1, first=3)
+    fr = R.frames(x)[0]
+    assert fr.shape == (251, 2048)
+    for f in (0, 1, 2, 125, 248, 249, 250):
+        idx = [R.reflect_pad_index(f * 512 + n) for n in (0, 1, 1023, 1024, 2047)]
+        np.testing.assert_array_equal(fr[f, [0, 1, 1023, 1024, 2047]].numpy(), x[0, idx].numpy())
+
+
+def test_fp32_reference_noise_floor_vs_fp64(golden_dir):
+    """How far the reference's own fp32 result sits from exact arithmetic: bounds what parity can mean."""
+    g = _load(golden_dir, "frontend.npz")
+    x = _golden_pcm(g)
+    db64 = R.logmel_db(x.double(), torch.float64)
+    err = (torch.from_numpy(g["logmel_db"]).double() - db64).abs()
+    tol = 1e-4 * torch.clamp(db64.abs(), min=1.0)
+    assert float((err / tol).max()) < 1.0
+
+
+# ---------------------------------------------------------------- ensemble (IR:28-73, 194-214, 328-334)
+@pytest.mark.parametrize("tag", ["n2", "n5"])
+def test_ensemble_matches_reference(golden_dir, tag):
+    g = _load(golden_dir, f"ensemble_{tag}.npz")
+    n = int(g["n_heads"])
+    sd = FX.merged_state_dict(n)
+    assert R.head_indices(sd) == list(range(n))
+    x = torch.cat([FX.synth_segments(1, first=int(i)) for i in g["seg_ids"]])
+    img = R.waveform_to_image(x).unsqueeze(1).repeat(1, 3, 1, 1)
+    ph = R.per_head_logits(img, sd)
+    merged = R.merge_logits(ph)
+    # same torch build -> bit identical; allow a few ulp for a different BLAS thread split
+    np.testing.assert_allclose(ph.numpy(), g["per_head_logits"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(merged.numpy(), g["merged_logits"], rtol=0, atol=2e-6)
+    labels, probs = R.interpret(merged, 0.5)
+    np.testing.assert_allclose(probs, g["probs"], rtol=0, atol=1e-6)
+    names = [str(s) for s in g["class_names"]]
+    mine = [R.label_name(int(l), n, names[:-1], names[-1]) for l in labels]
+    assert mine == [str(s) for s in g["labels"]]
+    pct, _ = R.clip_aggregate(probs, np.zeros(len(labels), np.int64), 1)
+    np.testing.assert_allclose(pct[0] * 100, g["percentages"], rtol=0, atol=1e-4)
+
+
+def test_decision_rule_cases():
+    # IR:207-213: Real needs real>=thr AND every synthetic < thr; else argmax even if all syn < thr
+    z = torch.tensor([[-1.0, -2.0, 3.0],      # Real
+                      [-1.0, -2.0, -3.0],     # nothing above thr -> argmax syn = 0
+                      [2.0, 3.0, 5.0],        # syn above thr -> argmax = 1
+                      [0.0, -1.0, 0.0]])      # sigmoid(0)=0.5: syn 0.5 is NOT < thr -> synthetic 0
+    labels, _ = R.interpret(z, 0.5)
+    assert labels.tolist() == [2, 0, 1, 0]
+    assert R.label_name(2, 2, ["A", "B"], "Real") == "Real"
+    assert R.label_name(1, 2, ["A"], "Real") == "Synthetic_2"
+
+
+def test_checkpoint_layout_counts():
+    sd = FX.merged_state_dict(2, calibrate=False)
+    assert len(sd) == 272                                      # 136 keys/head
+    f32 = {k: v for k, v in sd.items() if k.startswith("sub_models.0.") and v.dtype == torch.float32}
+    assert sum(v.numel() for v in f32.values()) == 11_583_682            # params + BN running stats
+    assert sum(v.numel() for k, v in f32.items() if "running" not in k) == 11_572_546
