@@ -1,0 +1,129 @@
+/*
+ * sad_b200.h -- C ABI of the B200-native inference hot path of Synthetic-Audio-Detection.
+ *
+ * The reference (pure Python) has no FFI of its own; its boundary for this path is the module-level
+ * API of modular/source/inference_runner.py and model_merger.py.  The Python mirror of that API
+ * (synthetic-audio-detection_b200/inference_runner.py) binds THIS header through ctypes; every entry
+ * point below names the reference function (file:line under /root/reference/modular/source) whose
+ * arithmetic it replaces.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SAD_E* code otherwise; sad_last_error(ctx) has text;
+ *   - "dev" pointers are CUDA device pointers on the context's device, "host" pointers are CPU memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); calls are
+ *     stream-ordered and do not synchronise unless stated;
+ *   - the caller owns every buffer it passes; the library owns its context, weights and workspace;
+ *   - there is no CPU fallback: without a CUDA device sad_create fails with SAD_ENODEVICE.
+ */
+#ifndef SAD_B200_H_
+#define SAD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAD_OK 0
+#define SAD_EINVAL (-1)    /* bad argument                                   */
+#define SAD_ENODEVICE (-2) /* no usable sm_100 CUDA device                   */
+#define SAD_ECUDA (-3)     /* a CUDA runtime / driver call failed            */
+#define SAD_ESTATE (-4)    /* call order violated (e.g. weights not loaded)  */
+
+/* Fixed geometry of the path (inference_runner.py:258-259). */
+#define SAD_SAMPLE_RATE 32000
+#define SAD_SEGMENT_SAMPLES 128000 /* int(4.0 * 32000)                       */
+#define SAD_N_FFT 2048
+#define SAD_HOP 512
+#define SAD_N_FRAMES 251
+#define SAD_N_FREQS 1025
+#define SAD_N_MELS 128
+#define SAD_IMAGE 512
+
+typedef struct sad_ctx sad_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* One context per GPU.  `n_heads` = number of sub-models of the merged ensemble
+ * (ModularMultiHeadClassifier, inference_runner.py:53-73); `max_batch` = segments processed per
+ * internal pass (workspace is sized for it; larger batches are chunked).                        */
+int sad_create(sad_ctx** out, int device, int n_heads, int max_batch);
+int sad_destroy(sad_ctx* ctx);
+const char* sad_last_error(const sad_ctx* ctx);
+const char* sad_version(void);
+
+/* ---- weights: replaces load_merged_model's per-head rebuild (inference_runner.py:101-114) ----- */
+/* The library describes the fp32 tensors it needs for ONE BinaryClassifier (inference_runner.py:28-51),
+ * in state_dict order without the int64 num_batches_tracked entries: name i is the key suffix after
+ * "sub_models.<h>." (e.g. "base.layer1.0.conv1.weight", "head.3.running_var").                    */
+int sad_weight_count(void);
+const char* sad_weight_name(int i);
+long long sad_weight_numel(int i);
+/* host_tensors[i] points at sad_weight_numel(i) contiguous fp32 values.  Eval-mode BatchNorm is folded
+ * into the preceding conv / Linear in fp64 and the conv weights are rounded once to bf16.          */
+int sad_load_weights(sad_ctx* ctx, int head, const float* const* host_tensors, int n_tensors);
+
+/* Optional: upload the Hann window [2048] and mel filterbank [1025*128, row = FFT bin] computed by the
+ * caller (torch / torchaudio) so the constants are bit-identical to the reference's
+ * (torchaudio MelSpectrogram, inference_runner.py:158-166).  Defaults are computed internally.     */
+int sad_set_frontend_constants(sad_ctx* ctx, const float* host_window, const float* host_mel_fb);
+
+/* ---- front end: replaces waveform_to_spectrogram (inference_runner.py:157-174) ---------------- */
+/* pcm [B,128000] fp32 -> log-mel dB [B,128,251] fp32 (after AmplitudeToDB top_db=80, :167-170) and
+ * per-segment (mean, unbiased std) [B,2] used by the standardisation at :171.  Either output may be NULL. */
+int sad_frontend_logmel(sad_ctx* ctx, const float* pcm_dev, int B, float* logmel_db_dev, float* mu_sigma_dev,
+                        void* stream);
+/* pcm [B,128000] -> standardised, 512x512 bilinear-resized image [B,512,512] fp32; the reference's three
+ * channels are identical copies of it (:172-173).                                                  */
+int sad_frontend_image(sad_ctx* ctx, const float* pcm_dev, int B, float* image_dev, void* stream);
+
+/* ---- slicing gate: replaces the silence test of slice_waveform (inference_runner.py:184-188) --- */
+/* For window w starting at w*hop: keep[w] = !(max|x| < silence_threshold).  n_windows as computed by
+ * sad_slice_count.                                                                                 */
+long long sad_slice_count(long long n_samples, long long window, long long hop);
+int sad_slice_gate(sad_ctx* ctx, const float* wf_dev, long long n_samples, long long window, long long hop,
+                   float silence_threshold, uint8_t* keep_dev, void* stream);
+/* Gather kept windows into a dense [n_kept,window] batch: dst[i] = wf[starts[i] : starts[i]+window]. */
+int sad_gather_windows(sad_ctx* ctx, const float* wf_dev, const long long* starts_dev, int n_kept,
+                       long long window, float* dst_dev, void* stream);
+
+/* ---- ensemble: replaces ModularMultiHeadClassifier.forward (inference_runner.py:62-73) over
+ *      BinaryClassifier.forward (:49-51) and interpret_multihead_logits (:194-214) -------------- */
+/* Fused path, pcm [B,128000] fp32 in, per segment out:
+ *   logits [B,N+1] = [syn_1..syn_N, mean_i(real_i)],  probs = sigmoid(logits),
+ *   labels [B] int32: N means Real, 0..N-1 the arg-max synthetic head (rule at :207-213).
+ * Any output pointer may be NULL.                                                                  */
+int sad_forward(sad_ctx* ctx, const float* pcm_dev, int B, float threshold, float* logits_dev, float* probs_dev,
+                int32_t* labels_dev, void* stream);
+/* nn.Module.forward drop-in: x [B,3,512,512] fp32 NCHW (any image, channels need not be equal). */
+int sad_forward_images(sad_ctx* ctx, const float* x_nchw_dev, int B, float threshold, float* logits_dev,
+                       float* probs_dev, int32_t* labels_dev, void* stream);
+/* End-to-end with HOST buffers: pinned staging, H2D of pcm, compute, D2H of the results, chunked and
+ * double-buffered on internal streams; synchronises before returning.                              */
+int sad_forward_host(sad_ctx* ctx, const float* pcm_host, int B, float threshold, float* logits_host,
+                     float* probs_host, int32_t* labels_host);
+
+/* ---- clip aggregation: replaces inference_runner.py:328-334 ------------------------------------ */
+/* clip_id [B] int32 (any order, values in [0,n_clips)); clip_probs [n_clips,N+1] = mean over the clip's
+ * segments of probs; clip_label = rule :207-213 applied to the clip mean (-1 for a clip with no segment). */
+int sad_clip_reduce(sad_ctx* ctx, const float* probs_dev, const int32_t* clip_id_dev, int B, int n_clips,
+                    float threshold, float* clip_probs_dev, int32_t* clip_label_dev, void* stream);
+
+/* ---- introspection (tests, bench) --------------------------------------------------------------- */
+int sad_n_heads(const sad_ctx* ctx);
+int sad_max_batch(const sad_ctx* ctx);
+/* Number of kernels this library has launched on the context since creation. */
+long long sad_launch_count(const sad_ctx* ctx);
+/* Run ONE convolution layer of one head on caller buffers (NHWC bf16): layer = index into the 20 convs in
+ * state_dict order (0 = stem conv1 is not available here; 1..19).  `in` [B,Hi,Wi,Cin], `residual`
+ * [B,Ho,Wo,Cout] or NULL, `out` [B,Ho,Wo,Cout].  Used by the per-layer parity tests.                */
+int sad_debug_conv(sad_ctx* ctx, int head, int layer, const void* in_dev, const void* residual_dev, void* out_dev,
+                   int B, int relu, void* stream);
+/* Copy an internal activation of the last sad_forward* chunk to the caller (tests only).
+ * which: 0 = image bf16 [B,512,512]; 1 = pooled stem out bf16 [H*B,128,128,64]; 2 = layer4 out bf16
+ * [H*B,16,16,512]; 3 = per-head logits fp32 [H*B,2].  Returns the number of bytes written.         */
+long long sad_debug_read(sad_ctx* ctx, int which, void* dst_dev, long long capacity_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAD_B200_H_ */

@@ -1,0 +1,71 @@
+"""ctypes binding of libsad_b200.so (include/sad_b200.h).  Fails loudly when the library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsad_b200.so")
+
+SAD_OK, SAD_EINVAL, SAD_ENODEVICE, SAD_ECUDA, SAD_ESTATE = 0, -1, -2, -3, -4
+_CODES = {SAD_EINVAL: "SAD_EINVAL", SAD_ENODEVICE: "SAD_ENODEVICE", SAD_ECUDA: "SAD_ECUDA", SAD_ESTATE: "SAD_ESTATE"}
+
+_vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+# name -> (restype, argtypes): every symbol include/sad_b200.h declares
+SIGNATURES = {
+    "sad_create": (_i, [C.POINTER(_vp), _i, _i, _i]),
+    "sad_destroy": (_i, [_vp]),
+    "sad_last_error": (C.c_char_p, [_vp]),
+    "sad_version": (C.c_char_p, []),
+    "sad_weight_count": (_i, []),
+    "sad_weight_name": (C.c_char_p, [_i]),
+    "sad_weight_numel": (_ll, [_i]),
+    "sad_load_weights": (_i, [_vp, _i, C.POINTER(_vp), _i]),
+    "sad_set_frontend_constants": (_i, [_vp, _vp, _vp]),
+    "sad_frontend_logmel": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "sad_frontend_image": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "sad_slice_count": (_ll, [_ll, _ll, _ll]),
+    "sad_slice_gate": (_i, [_vp, _vp, _ll, _ll, _ll, _f, _vp, _vp]),
+    "sad_gather_windows": (_i, [_vp, _vp, _vp, _i, _ll, _vp, _vp]),
+    "sad_forward": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
+    "sad_forward_images": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
+    "sad_forward_host": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp]),
+    "sad_clip_reduce": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    "sad_n_heads": (_i, [_vp]),
+    "sad_max_batch": (_i, [_vp]),
+    "sad_launch_count": (_ll, [_vp]),
+    "sad_debug_conv": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "sad_debug_read": (_ll, [_vp, _i, _vp, _ll, _vp]),
+}
+
+_lib = None
+
+
+class SadError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """dlopen the library (no GPU needed for this) and declare the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SadError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` (nvcc, sm_100a). "
+            "There is no CPU or PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(ctx, code: int, what: str):
+    if code >= 0:
+        return code
+    msg = load().sad_last_error(ctx)
+    raise SadError(f"{what}: {_CODES.get(code, code)}: {msg.decode() if msg else ''}")

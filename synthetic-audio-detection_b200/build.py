@@ -1,0 +1,46 @@
+"""Build libsad_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so must travel with the repo)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libsad_b200.so")
+SOURCES = ["api.cu", "conv_umma.cu", "frontend.cu", "head.cu"]
+HEADERS = ["conv_umma.h", "frontend.h", "head.h", "ptx.cuh", "fft2048.cuh", os.path.join("..", "..", "include", "sad_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile if sources are newer than the library; returns the library path."""
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+def build_fft_host_check() -> str:
+    """CPU test helper that exercises the FFT pass bodies (see csrc/fft_host_check.cpp)."""
+    out = os.path.join(HERE, "fft_host_check.bin")
+    src = os.path.join(CSRC, "fft_host_check.cpp")
+    if not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out) or \
+            os.path.getmtime(os.path.join(CSRC, "fft2048.cuh")) > os.path.getmtime(out):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-o", out, src], check=True)
+    return out
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,902 @@
+// C-ABI of the B200-native inference hot path (include/sad_b200.h): context, weight folding / packing,
+// TMA tensor maps, the per-chunk launch plan and the host-buffer end-to-end path.
+//
+// Reference being replaced: modular/source/inference_runner.py -- load_merged_model (:77-123) for the weight
+// side, waveform_to_spectrogram (:157-174) + ModularMultiHeadClassifier.forward (:62-73) +
+// interpret_multihead_logits (:194-214) for the per-segment path, :328-334 for the clip mean.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sad_b200.h"
+#include "conv_umma.h"
+#include "frontend.h"
+#include "head.h"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+// ------------------------------------------------------------------------------------------------
+// network description (ResNet-18 trunk as timm builds it: conv1/bn1/act1/maxpool/layer1..4)
+// ------------------------------------------------------------------------------------------------
+struct ConvSpec {
+    std::string conv, bn;
+    int cin, cout, k, stride, pad, hin, hout;
+};
+
+std::vector<ConvSpec> build_convs() {
+    std::vector<ConvSpec> v;
+    v.push_back({"base.conv1", "base.bn1", 3, 64, 7, 2, 3, 512, 256});
+    const int chans[4] = {64, 128, 256, 512};
+    int cin = 64, h = 128;
+    for (int li = 0; li < 4; ++li) {
+        const int cout = chans[li];
+        for (int b = 0; b < 2; ++b) {
+            const std::string p = "base.layer" + std::to_string(li + 1) + "." + std::to_string(b);
+            const int stride = (b == 0 && li > 0) ? 2 : 1;
+            const int c0 = b == 0 ? cin : cout;
+            const int hin = h, hout = h / stride;
+            v.push_back({p + ".conv1", p + ".bn1", c0, cout, 3, stride, 1, hin, hout});
+            v.push_back({p + ".conv2", p + ".bn2", cout, cout, 3, 1, 1, hout, hout});
+            if (b == 0 && li > 0) v.push_back({p + ".downsample.0", p + ".downsample.1", c0, cout, 1, 2, 0, hin, hout});
+            h = hout;
+        }
+        cin = cout;
+    }
+    return v;   // 20 entries, state_dict order
+}
+
+struct TensorSpec {
+    std::string name;
+    long long numel;
+};
+
+std::vector<TensorSpec> build_tensor_list(const std::vector<ConvSpec>& convs) {
+    std::vector<TensorSpec> t;
+    auto bn = [&](const std::string& p, int c) {
+        t.push_back({p + ".weight", c});
+        t.push_back({p + ".bias", c});
+        t.push_back({p + ".running_mean", c});
+        t.push_back({p + ".running_var", c});
+    };
+    for (const auto& c : convs) {
+        t.push_back({c.conv + ".weight", 1LL * c.cout * c.cin * c.k * c.k});
+        bn(c.bn, c.cout);
+    }
+    t.push_back({"head.2.weight", 512 * 512});
+    t.push_back({"head.2.bias", 512});
+    bn("head.3", 512);
+    t.push_back({"head.6.weight", 256 * 512});
+    t.push_back({"head.6.bias", 256});
+    bn("head.7", 256);
+    t.push_back({"head.10.weight", 2 * 256});
+    t.push_back({"head.10.bias", 2});
+    return t;   // 20*5 + 14 = 114
+}
+
+const std::vector<ConvSpec>& convs() {
+    static const std::vector<ConvSpec> v = build_convs();
+    return v;
+}
+const std::vector<TensorSpec>& tensors() {
+    static const std::vector<TensorSpec> v = build_tensor_list(convs());
+    return v;
+}
+
+// launch plan over the activation buffers: X (block input / output), Y, T (mid), D (downsample branch)
+enum Buf { BX = 0, BY = 1, BT = 2, BD = 3, BNONE = -1 };
+struct Step {
+    int conv;
+    int in, res, out;
+    int relu;
+};
+std::vector<Step> build_plan() {
+    std::vector<Step> p;
+    int ci = 1;
+    for (int li = 0; li < 4; ++li) {
+        if (li == 0) {
+            p.push_back({ci + 0, BX, BNONE, BT, 1});
+            p.push_back({ci + 1, BT, BX, BY, 1});
+            ci += 2;
+        } else {
+            p.push_back({ci + 0, BX, BNONE, BT, 1});
+            p.push_back({ci + 2, BX, BNONE, BD, 0});
+            p.push_back({ci + 1, BT, BD, BY, 1});
+            ci += 3;
+        }
+        p.push_back({ci + 0, BY, BNONE, BT, 1});
+        p.push_back({ci + 1, BT, BY, BX, 1});
+        ci += 2;
+    }
+    return p;   // 19 steps; the trunk output ends in X
+}
+
+constexpr double kBnEps = 1e-5;
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct sad_ctx {
+    int device = 0, H = 0, Bc = 0, num_sms = 0;
+    char err[512] = {0};
+    long long launches = 0;
+    std::vector<char> loaded;
+
+    // weights
+    bf16* d_w[20] = {nullptr};          // [H][Cout][taps*Cin]; index 0 unused (stem has its own two packings)
+    float* d_bias[20] = {nullptr};      // [H][Cout]
+    bf16* d_w_stem1 = nullptr;          // [H][64][64]   1-channel (summed) stem, K = 49 -> 64
+    bf16* d_w_stem3 = nullptr;          // [H][64][192]  3-channel stem, K = 147 -> 192
+    float *d_w1t = nullptr, *d_b1 = nullptr, *d_w2t = nullptr, *d_b2 = nullptr, *d_w3 = nullptr, *d_b3 = nullptr;
+
+    // front-end constants
+    float* d_window = nullptr;
+    sad::MelTable* d_mel = nullptr;
+    sad::ResizeTable* d_resize = nullptr;
+
+    // workspace (per chunk)
+    float* d_db = nullptr;              // [Bc][128][251]
+    unsigned* d_segmax = nullptr;       // [Bc]
+    float* d_musig = nullptr;           // [Bc][2]
+    bf16* d_img = nullptr;              // [Bc][512][512]
+    bf16* d_A1 = nullptr;               // [Bc][65536][64]
+    bf16* d_A3 = nullptr;               // [Bc][65536][192] (allocated on first sad_forward_images)
+    bf16* d_stem = nullptr;             // [H*Bc][256][256][64]
+    bf16* d_buf[4] = {nullptr};         // X, Y, T, D
+    float* d_head_logits = nullptr;     // [H*Bc][2]
+    int last_B = 0;
+
+    // launch descriptors with tensor maps bound to the workspace
+    sad::ConvLaunch stem1, stem3;
+    std::vector<sad::ConvLaunch> plan_launch;
+    std::vector<Step> plan;
+    bool stem3_ready = false;
+
+    // end-to-end path
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr};
+    float* h_stage[2] = {nullptr, nullptr};
+    float* d_pcm[2] = {nullptr, nullptr};
+    float* d_res_logits = nullptr;
+    float* d_res_probs = nullptr;
+    int32_t* d_res_labels = nullptr;
+    long long res_capacity = 0;
+};
+
+namespace {
+
+int fail(sad_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU_OK(ctx, expr)                                                                                  \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(ctx, SAD_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                        \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t n) {
+    return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+}
+
+// ---- tensor maps -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn(char* err, int errlen) {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+        snprintf(err, errlen, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+        return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+}  // namespace
+
+namespace sad {
+
+bool encode_act_map(CUtensorMap* m, const void* base, int C, int W, int H, long long N, long long sx, long long sy,
+                    long long sn, int box_w, int box_h, char* err, int errlen) {
+    EncodeTiledFn fn = encode_fn(err, errlen);
+    if (!fn) return false;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                          static_cast<cuuint64_t>(N)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(sx) * 2, static_cast<cuuint64_t>(sy) * 2,
+                             static_cast<cuuint64_t>(sn) * 2};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(err, errlen, "cuTensorMapEncodeTiled(act C=%d W=%d H=%d N=%lld box=%dx%d) -> CUresult %d", C, W, H, N,
+                 box_w, box_h, static_cast<int>(r));
+        return false;
+    }
+    return true;
+}
+
+bool encode_weight_map(CUtensorMap* m, const void* base, long long K, long long rows, int box_rows, char* err,
+                       int errlen) {
+    EncodeTiledFn fn = encode_fn(err, errlen);
+    if (!fn) return false;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(err, errlen, "cuTensorMapEncodeTiled(weights K=%lld rows=%lld box=%d) -> CUresult %d", K, rows,
+                 box_rows, static_cast<int>(r));
+        return false;
+    }
+    return true;
+}
+
+}  // namespace sad
+
+namespace {
+
+// Fill one ConvLaunch for conv `ci` reading `in` (NHWC [n_imgs][hin][hin][cin]) and writing `out`.
+bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const bf16* res, bf16* out, long long n_imgs,
+                 int relu) {
+    const ConvSpec& s = convs()[ci];
+    memset(L, 0, sizeof(*L));
+    const int Wo = s.hout, Hi = s.hin, C = s.cin;
+    const int rows = 128 / Wo;
+    if (s.stride == 1) {
+        if (!sad::encode_act_map(&L->a_map[0], in, C, Hi, Hi, n_imgs, C, 1LL * Hi * C, 1LL * Hi * Hi * C, Wo, rows, c->err,
+                                 sizeof(c->err)))
+            return false;
+        for (int i = 1; i < 4; ++i) L->a_map[i] = L->a_map[0];
+    } else {
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px)
+                if (!sad::encode_act_map(&L->a_map[py * 2 + px], in + (1LL * py * Hi + px) * C, C, Hi / 2, Hi / 2, n_imgs,
+                                         2LL * C, 2LL * Hi * C, 1LL * Hi * Hi * C, Wo, rows, c->err, sizeof(c->err)))
+                    return false;
+    }
+    const int n_tile = sad::conv_n_tile(s.cout);
+    const long long K = 1LL * s.k * s.k * s.cin;
+    if (!sad::encode_weight_map(&L->b_map, c->d_w[ci], K, 1LL * c->H * s.cout, n_tile, c->err, sizeof(c->err)))
+        return false;
+    L->bias = c->d_bias[ci];
+    L->residual = res;
+    L->out = out;
+    L->Cin = s.cin;
+    L->Cout = s.cout;
+    L->ksize = s.k;
+    L->stride = s.stride;
+    L->pad = s.pad;
+    L->m_tiles_per_img = Wo * Wo / 128;
+    L->rows_per_tile = rows;
+    L->n_tile = n_tile;
+    L->n_tiles = s.cout / n_tile;
+    L->relu = relu;
+    L->shared_input = 0;
+    return true;
+}
+
+// The stem runs as a 1x1 "convolution" over the im2col matrix A [n][65536 px][Kpad] viewed as [n][512][128][Kpad].
+bool make_stem_launch(sad_ctx* c, sad::ConvLaunch* L, const bf16* A, const bf16* w, int Kpad) {
+    memset(L, 0, sizeof(*L));
+    if (!sad::encode_act_map(&L->a_map[0], A, Kpad, 128, 512, c->Bc, Kpad, 128LL * Kpad, 65536LL * Kpad, 128, 1, c->err,
+                             sizeof(c->err)))
+        return false;
+    for (int i = 1; i < 4; ++i) L->a_map[i] = L->a_map[0];
+    if (!sad::encode_weight_map(&L->b_map, w, Kpad, 1LL * c->H * 64, 64, c->err, sizeof(c->err))) return false;
+    L->bias = c->d_bias[0];
+    L->residual = nullptr;
+    L->out = c->d_stem;
+    L->Cin = Kpad;
+    L->Cout = 64;
+    L->ksize = 1;
+    L->stride = 1;
+    L->pad = 0;
+    L->m_tiles_per_img = 512;
+    L->rows_per_tile = 1;
+    L->n_tile = 64;
+    L->n_tiles = 1;
+    L->relu = 1;
+    L->shared_input = 1;
+    return true;
+}
+
+void set_batch(sad::ConvLaunch* L, int B, int H) {
+    L->imgs_per_head = B;
+    L->total_tiles = H * B * L->m_tiles_per_img * L->n_tiles;
+}
+
+// ---- default front-end constants (overridable through sad_set_frontend_constants) -------------------
+void default_window(std::vector<float>& w) {
+    w.resize(2048);
+    for (int n = 0; n < 2048; ++n) w[n] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * M_PI * n / 2048.0));
+}
+// torchaudio.functional.melscale_fbanks(1025, 20, 12000, 128, 32000, norm='slaney', mel_scale='htk'), in fp32
+// where torchaudio computes in fp32.
+void default_mel_fb(std::vector<float>& fb) {
+    const int nf = 1025, nm = 128;
+    fb.assign(static_cast<size_t>(nf) * nm, 0.f);
+    std::vector<float> all(nf), fpts(nm + 2);
+    for (int i = 0; i < nf; ++i) all[i] = static_cast<float>(16000.0 * i / (nf - 1));
+    const double m_min = 2595.0 * std::log10(1.0 + 20.0 / 700.0), m_max = 2595.0 * std::log10(1.0 + 12000.0 / 700.0);
+    for (int i = 0; i < nm + 2; ++i) {
+        const float m = static_cast<float>(m_min + (m_max - m_min) * i / (nm + 1));
+        fpts[i] = 700.0f * (std::pow(10.0f, m / 2595.0f) - 1.0f);
+    }
+    for (int k = 0; k < nf; ++k)
+        for (int m = 0; m < nm; ++m) {
+            const float down = (all[k] - fpts[m]) / (fpts[m + 1] - fpts[m]);
+            const float up = (fpts[m + 2] - all[k]) / (fpts[m + 2] - fpts[m + 1]);
+            const float v = std::fmax(0.f, std::fmin(down, up));
+            fb[static_cast<size_t>(k) * nm + m] = v * (2.0f / (fpts[m + 2] - fpts[m]));
+        }
+}
+
+int upload_mel(sad_ctx* c, const float* fb) {
+    sad::MelTable t;
+    memset(&t, 0, sizeof(t));
+    int off = 0;
+    for (int m = 0; m < 128; ++m) {
+        int first = -1, last = -1;
+        for (int k = 0; k < 1025; ++k)
+            if (fb[static_cast<size_t>(k) * 128 + m] != 0.f) {
+                if (first < 0) first = k;
+                last = k;
+            }
+        if (first < 0) {
+            t.start[m] = 0;
+            t.count[m] = 0;
+            t.off[m] = off;
+            continue;
+        }
+        if (last > 768) return fail(c, SAD_EINVAL, "mel filter %d has weight on FFT bin %d > 768", m, last);
+        const int cnt = last - first + 1;
+        if (off + cnt > 1536) return fail(c, SAD_EINVAL, "mel filterbank has more than 1536 banded taps");
+        t.start[m] = first;
+        t.count[m] = cnt;
+        t.off[m] = off;
+        for (int k = 0; k < cnt; ++k) t.w[off + k] = fb[static_cast<size_t>(first + k) * 128 + m];
+        off += cnt;
+    }
+    t.n_weights = off;
+    CU_OK(c, cudaMemcpy(c->d_mel, &t, sizeof(t), cudaMemcpyHostToDevice));
+    return SAD_OK;
+}
+
+// ATen _compute_indices_min_size_weights_aa for bilinear (support 1 when up-sampling), fp32 arithmetic.
+void resize_axis(int in, int* idx, float* w) {
+    const float scale = static_cast<float>(in) / 512.0f;
+    for (int i = 0; i < 512; ++i) {
+        const float center = scale * (static_cast<float>(i) + 0.5f);
+        int lo = static_cast<int>(center - 1.0f + 0.5f);
+        if (lo < 0) lo = 0;
+        int hi = static_cast<int>(center + 1.0f + 0.5f);
+        if (hi > in) hi = in;
+        float ws[2] = {0.f, 0.f}, tot = 0.f;
+        for (int j = 0; j < hi - lo && j < 2; ++j) {
+            float t = std::fabs(static_cast<float>(j + lo) - center + 0.5f);
+            ws[j] = t < 1.0f ? 1.0f - t : 0.f;
+            tot += ws[j];
+        }
+        idx[i] = lo;
+        w[2 * i] = ws[0] / tot;
+        w[2 * i + 1] = ws[1] / tot;
+    }
+}
+
+// ---- weight folding ---------------------------------------------------------------------------------
+inline bf16 to_bf16(double v) { return __float2bfloat16_rn(static_cast<float>(v)); }
+
+void bn_scale_shift(const float* g, const float* b, const float* m, const float* v, int n, std::vector<double>& s,
+                    std::vector<double>& t) {
+    s.resize(n);
+    t.resize(n);
+    for (int i = 0; i < n; ++i) {
+        s[i] = static_cast<double>(g[i]) / std::sqrt(static_cast<double>(v[i]) + kBnEps);
+        t[i] = static_cast<double>(b[i]) - static_cast<double>(m[i]) * s[i];
+    }
+}
+
+int run_chunk(sad_ctx* c, const float* pcm, const float* x_nchw, int B, float thr, float* logits, float* probs,
+              int32_t* labels, cudaStream_t st);
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* sad_version(void) { return "sad_b200 0.1 (sm_100a)"; }
+
+int sad_weight_count(void) { return static_cast<int>(tensors().size()); }
+const char* sad_weight_name(int i) {
+    if (i < 0 || i >= sad_weight_count()) return nullptr;
+    return tensors()[i].name.c_str();
+}
+long long sad_weight_numel(int i) {
+    if (i < 0 || i >= sad_weight_count()) return -1;
+    return tensors()[i].numel;
+}
+
+const char* sad_last_error(const sad_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+int sad_n_heads(const sad_ctx* ctx) { return ctx ? ctx->H : 0; }
+int sad_max_batch(const sad_ctx* ctx) { return ctx ? ctx->Bc : 0; }
+long long sad_launch_count(const sad_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+long long sad_slice_count(long long n_samples, long long window, long long hop) {
+    // len(range(0, n_samples - window + 1, hop)), inference_runner.py:184
+    if (hop <= 0 || window <= 0) return -1;
+    const long long stop = n_samples - window + 1;
+    if (stop <= 0) return 0;
+    return (stop + hop - 1) / hop;
+}
+
+int sad_create(sad_ctx** out, int device, int n_heads, int max_batch) {
+    if (!out) return SAD_EINVAL;
+    *out = nullptr;
+    if (n_heads < 1 || n_heads > 31 || max_batch < 1 || max_batch > 4096) return SAD_EINVAL;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0 || device < 0 || device >= n_dev) {
+        cudaGetLastError();
+        return SAD_ENODEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SAD_ENODEVICE;
+    if (prop.major != 10) return SAD_ENODEVICE;   // tcgen05 / TMEM path only: there is no fallback
+    sad_ctx* c = new sad_ctx();
+    c->device = device;
+    c->H = n_heads;
+    c->Bc = max_batch;
+    c->num_sms = prop.multiProcessorCount;
+    c->loaded.assign(n_heads, 0);
+    *out = c;   // returned even on failure so the caller can read sad_last_error, then sad_destroy
+    CU_OK(c, cudaSetDevice(device));
+
+    const long long H = n_heads, Bc = max_batch, HB = H * Bc;
+    for (int i = 1; i < 20; ++i) {
+        const ConvSpec& s = convs()[i];
+        CU_OK(c, dalloc(&c->d_w[i], H * s.cout * s.k * s.k * s.cin));
+        CU_OK(c, dalloc(&c->d_bias[i], H * s.cout));
+    }
+    CU_OK(c, dalloc(&c->d_bias[0], H * 64));
+    CU_OK(c, dalloc(&c->d_w_stem1, H * 64 * 64));
+    CU_OK(c, dalloc(&c->d_w_stem3, H * 64 * 192));
+    CU_OK(c, dalloc(&c->d_w1t, H * 512 * 512));
+    CU_OK(c, dalloc(&c->d_b1, H * 512));
+    CU_OK(c, dalloc(&c->d_w2t, H * 512 * 256));
+    CU_OK(c, dalloc(&c->d_b2, H * 256));
+    CU_OK(c, dalloc(&c->d_w3, H * 2 * 256));
+    CU_OK(c, dalloc(&c->d_b3, H * 2));
+
+    CU_OK(c, dalloc(&c->d_window, 2048));
+    CU_OK(c, dalloc(&c->d_mel, 1));
+    CU_OK(c, dalloc(&c->d_resize, 1));
+    {
+        std::vector<float> w, fb;
+        default_window(w);
+        default_mel_fb(fb);
+        CU_OK(c, cudaMemcpy(c->d_window, w.data(), 2048 * sizeof(float), cudaMemcpyHostToDevice));
+        int r = upload_mel(c, fb.data());
+        if (r != SAD_OK) return r;
+        sad::ResizeTable rt;
+        resize_axis(251, rt.w_idx, rt.w_w);
+        resize_axis(128, rt.h_idx, rt.h_w);
+        CU_OK(c, cudaMemcpy(c->d_resize, &rt, sizeof(rt), cudaMemcpyHostToDevice));
+    }
+
+    CU_OK(c, dalloc(&c->d_db, Bc * 128 * 251));
+    CU_OK(c, dalloc(&c->d_segmax, Bc));
+    CU_OK(c, dalloc(&c->d_musig, Bc * 2));
+    CU_OK(c, dalloc(&c->d_img, Bc * 512 * 512));
+    CU_OK(c, dalloc(&c->d_A1, Bc * 65536 * 64));
+    CU_OK(c, dalloc(&c->d_stem, HB * 65536 * 64));
+    for (int i = 0; i < 3; ++i) CU_OK(c, dalloc(&c->d_buf[i], HB * 128 * 128 * 64));
+    CU_OK(c, dalloc(&c->d_buf[BD], HB * 64 * 64 * 128));
+    CU_OK(c, dalloc(&c->d_head_logits, HB * 2));
+
+    // launch plan bound to the workspace
+    if (!make_stem_launch(c, &c->stem1, c->d_A1, c->d_w_stem1, 64)) return SAD_ECUDA;
+    c->plan = build_plan();
+    c->plan_launch.resize(c->plan.size());
+    for (size_t i = 0; i < c->plan.size(); ++i) {
+        const Step& s = c->plan[i];
+        if (!make_launch(c, &c->plan_launch[i], s.conv, c->d_buf[s.in], s.res == BNONE ? nullptr : c->d_buf[s.res],
+                         c->d_buf[s.out], HB, s.relu))
+            return SAD_ECUDA;
+    }
+
+    CU_OK(c, cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    CU_OK(c, cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU_OK(c, cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        CU_OK(c, cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
+    }
+    return SAD_OK;
+}
+
+int sad_destroy(sad_ctx* c) {
+    if (!c) return SAD_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 20; ++i) {
+        cudaFree(c->d_w[i]);
+        cudaFree(c->d_bias[i]);
+    }
+    void* ptrs[] = {c->d_w_stem1, c->d_w_stem3, c->d_w1t, c->d_b1, c->d_w2t, c->d_b2, c->d_w3, c->d_b3, c->d_window,
+                    c->d_mel, c->d_resize, c->d_db, c->d_segmax, c->d_musig, c->d_img, c->d_A1, c->d_A3, c->d_stem,
+                    c->d_buf[0], c->d_buf[1], c->d_buf[2], c->d_buf[3], c->d_head_logits, c->d_pcm[0], c->d_pcm[1],
+                    c->d_res_logits, c->d_res_probs, c->d_res_labels};
+    for (void* p : ptrs) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
+    }
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    if (c->s_comp) cudaStreamDestroy(c->s_comp);
+    cudaGetLastError();
+    delete c;
+    return SAD_OK;
+}
+
+int sad_set_frontend_constants(sad_ctx* c, const float* host_window, const float* host_mel_fb) {
+    if (!c) return SAD_EINVAL;
+    CU_OK(c, cudaSetDevice(c->device));
+    if (host_window) CU_OK(c, cudaMemcpy(c->d_window, host_window, 2048 * sizeof(float), cudaMemcpyHostToDevice));
+    if (host_mel_fb) return upload_mel(c, host_mel_fb);
+    return SAD_OK;
+}
+
+int sad_load_weights(sad_ctx* c, int head, const float* const* T, int n_tensors) {
+    if (!c) return SAD_EINVAL;
+    if (head < 0 || head >= c->H) return fail(c, SAD_EINVAL, "head %d out of range [0,%d)", head, c->H);
+    if (n_tensors != sad_weight_count())
+        return fail(c, SAD_EINVAL, "expected %d tensors, got %d", sad_weight_count(), n_tensors);
+    for (int i = 0; i < n_tensors; ++i)
+        if (!T[i]) return fail(c, SAD_EINVAL, "tensor %d (%s) is null", i, sad_weight_name(i));
+    CU_OK(c, cudaSetDevice(c->device));
+    std::vector<double> s, t;
+    int ti = 0;
+    for (int ci = 0; ci < 20; ++ci) {
+        const ConvSpec& cs = convs()[ci];
+        const float* w = T[ti];
+        bn_scale_shift(T[ti + 1], T[ti + 2], T[ti + 3], T[ti + 4], cs.cout, s, t);
+        ti += 5;
+        std::vector<float> bias(cs.cout);
+        for (int o = 0; o < cs.cout; ++o) bias[o] = static_cast<float>(t[o]);
+        CU_OK(c, cudaMemcpy(c->d_bias[ci] + static_cast<size_t>(head) * cs.cout, bias.data(), cs.cout * sizeof(float),
+                            cudaMemcpyHostToDevice));
+        const int kk = cs.k * cs.k;
+        if (ci == 0) {
+            // stem, two packings: channel-summed K=49 (the reference's three input channels are identical,
+            // inference_runner.py:173) and the general 3-channel K=147.
+            std::vector<bf16> p1(64 * 64, to_bf16(0.0)), p3(64 * 192, to_bf16(0.0));
+            for (int o = 0; o < 64; ++o)
+                for (int tap = 0; tap < 49; ++tap) {
+                    double sum = 0.0;
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const double v = static_cast<double>(w[(o * 3 + ch) * 49 + tap]) * s[o];
+                        sum += v;
+                        p3[o * 192 + tap * 3 + ch] = to_bf16(v);
+                    }
+                    p1[o * 64 + tap] = to_bf16(sum);
+                }
+            CU_OK(c, cudaMemcpy(c->d_w_stem1 + static_cast<size_t>(head) * 64 * 64, p1.data(), p1.size() * sizeof(bf16),
+                                cudaMemcpyHostToDevice));
+            CU_OK(c, cudaMemcpy(c->d_w_stem3 + static_cast<size_t>(head) * 64 * 192, p3.data(),
+                                p3.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+        } else {
+            const size_t K = static_cast<size_t>(kk) * cs.cin;
+            std::vector<bf16> p(static_cast<size_t>(cs.cout) * K);
+            for (int o = 0; o < cs.cout; ++o)
+                for (int ch = 0; ch < cs.cin; ++ch)
+                    for (int tap = 0; tap < kk; ++tap)
+                        p[o * K + static_cast<size_t>(tap) * cs.cin + ch] =
+                            to_bf16(static_cast<double>(w[(static_cast<size_t>(o) * cs.cin + ch) * kk + tap]) * s[o]);
+            CU_OK(c, cudaMemcpy(c->d_w[ci] + static_cast<size_t>(head) * cs.cout * K, p.data(), p.size() * sizeof(bf16),
+                                cudaMemcpyHostToDevice));
+        }
+    }
+    // head: Linear(512,512)+BN1d, Linear(512,256)+BN1d, Linear(256,2)
+    {
+        const float *w1 = T[ti], *b1 = T[ti + 1];
+        bn_scale_shift(T[ti + 2], T[ti + 3], T[ti + 4], T[ti + 5], 512, s, t);
+        ti += 6;
+        std::vector<float> wt(512 * 512), bb(512);
+        for (int o = 0; o < 512; ++o) {
+            bb[o] = static_cast<float>(static_cast<double>(b1[o]) * s[o] + t[o]);
+            for (int i = 0; i < 512; ++i) wt[i * 512 + o] = static_cast<float>(static_cast<double>(w1[o * 512 + i]) * s[o]);
+        }
+        CU_OK(c, cudaMemcpy(c->d_w1t + static_cast<size_t>(head) * 512 * 512, wt.data(), wt.size() * sizeof(float),
+                            cudaMemcpyHostToDevice));
+        CU_OK(c, cudaMemcpy(c->d_b1 + head * 512, bb.data(), 512 * sizeof(float), cudaMemcpyHostToDevice));
+        const float *w2 = T[ti], *b2 = T[ti + 1];
+        bn_scale_shift(T[ti + 2], T[ti + 3], T[ti + 4], T[ti + 5], 256, s, t);
+        ti += 6;
+        std::vector<float> wt2(512 * 256), bb2(256);
+        for (int o = 0; o < 256; ++o) {
+            bb2[o] = static_cast<float>(static_cast<double>(b2[o]) * s[o] + t[o]);
+            for (int i = 0; i < 512; ++i) wt2[i * 256 + o] = static_cast<float>(static_cast<double>(w2[o * 512 + i]) * s[o]);
+        }
+        CU_OK(c, cudaMemcpy(c->d_w2t + static_cast<size_t>(head) * 512 * 256, wt2.data(), wt2.size() * sizeof(float),
+                            cudaMemcpyHostToDevice));
+        CU_OK(c, cudaMemcpy(c->d_b2 + head * 256, bb2.data(), 256 * sizeof(float), cudaMemcpyHostToDevice));
+        CU_OK(c, cudaMemcpy(c->d_w3 + head * 512, T[ti], 512 * sizeof(float), cudaMemcpyHostToDevice));
+        CU_OK(c, cudaMemcpy(c->d_b3 + head * 2, T[ti + 1], 2 * sizeof(float), cudaMemcpyHostToDevice));
+        ti += 2;
+    }
+    c->loaded[head] = 1;
+    return SAD_OK;
+}
+
+int sad_frontend_logmel(sad_ctx* c, const float* pcm, int B, float* logmel_db, float* mu_sigma, void* stream) {
+    if (!c || !pcm || B < 0) return SAD_EINVAL;
+    CU_OK(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int b0 = 0; b0 < B; b0 += c->Bc) {
+        const int nb = B - b0 < c->Bc ? B - b0 : c->Bc;
+        CU_OK(c, sad::frontend_logmel_launch(pcm + static_cast<size_t>(b0) * SAD_SEGMENT_SAMPLES, nb, c->d_window, c->d_mel,
+                                             c->d_db, c->d_segmax,
+                                             logmel_db ? logmel_db + static_cast<size_t>(b0) * 128 * 251 : nullptr,
+                                             c->d_musig, st, &c->launches));
+        if (mu_sigma)
+            CU_OK(c, cudaMemcpyAsync(mu_sigma + 2 * static_cast<size_t>(b0), c->d_musig, 2 * nb * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, st));
+    }
+    return SAD_OK;
+}
+
+int sad_frontend_image(sad_ctx* c, const float* pcm, int B, float* image, void* stream) {
+    if (!c || !pcm || !image || B < 0) return SAD_EINVAL;
+    CU_OK(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int b0 = 0; b0 < B; b0 += c->Bc) {
+        const int nb = B - b0 < c->Bc ? B - b0 : c->Bc;
+        CU_OK(c, sad::frontend_logmel_launch(pcm + static_cast<size_t>(b0) * SAD_SEGMENT_SAMPLES, nb, c->d_window, c->d_mel,
+                                             c->d_db, c->d_segmax, nullptr, c->d_musig, st, &c->launches));
+        CU_OK(c, sad::image_launch_f32(c->d_db, c->d_musig, c->d_resize, image + static_cast<size_t>(b0) * 512 * 512, nb, st,
+                                       &c->launches));
+    }
+    return SAD_OK;
+}
+
+int sad_slice_gate(sad_ctx* c, const float* wf, long long n_samples, long long window, long long hop, float thr,
+                   uint8_t* keep, void* stream) {
+    if (!c || !wf || !keep) return SAD_EINVAL;
+    const long long n = sad_slice_count(n_samples, window, hop);
+    if (n < 0) return fail(c, SAD_EINVAL, "bad window/hop");
+    CU_OK(c, cudaSetDevice(c->device));
+    CU_OK(c, sad::slice_gate_launch(wf, n, window, hop, thr, keep, static_cast<cudaStream_t>(stream), &c->launches));
+    return SAD_OK;
+}
+
+int sad_gather_windows(sad_ctx* c, const float* wf, const long long* starts, int n_kept, long long window, float* dst,
+                       void* stream) {
+    if (!c || !wf || !starts || !dst || n_kept < 0) return SAD_EINVAL;
+    CU_OK(c, cudaSetDevice(c->device));
+    CU_OK(c, sad::gather_windows_launch(wf, starts, n_kept, window, dst, static_cast<cudaStream_t>(stream), &c->launches));
+    return SAD_OK;
+}
+
+int sad_forward(sad_ctx* c, const float* pcm, int B, float thr, float* logits, float* probs, int32_t* labels,
+                void* stream) {
+    if (!c || !pcm || B < 0) return SAD_EINVAL;
+    CU_OK(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n1 = c->H + 1;
+    for (int b0 = 0; b0 < B; b0 += c->Bc) {
+        const int nb = B - b0 < c->Bc ? B - b0 : c->Bc;
+        int r = run_chunk(c, pcm + static_cast<size_t>(b0) * SAD_SEGMENT_SAMPLES, nullptr, nb, thr,
+                          logits ? logits + static_cast<size_t>(b0) * n1 : nullptr,
+                          probs ? probs + static_cast<size_t>(b0) * n1 : nullptr, labels ? labels + b0 : nullptr, st);
+        if (r != SAD_OK) return r;
+    }
+    return SAD_OK;
+}
+
+int sad_forward_images(sad_ctx* c, const float* x, int B, float thr, float* logits, float* probs, int32_t* labels,
+                       void* stream) {
+    if (!c || !x || B < 0) return SAD_EINVAL;
+    CU_OK(c, cudaSetDevice(c->device));
+    if (!c->stem3_ready) {
+        CU_OK(c, dalloc(&c->d_A3, static_cast<size_t>(c->Bc) * 65536 * 192));
+        if (!make_stem_launch(c, &c->stem3, c->d_A3, c->d_w_stem3, 192)) return SAD_ECUDA;
+        c->stem3_ready = true;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n1 = c->H + 1;
+    for (int b0 = 0; b0 < B; b0 += c->Bc) {
+        const int nb = B - b0 < c->Bc ? B - b0 : c->Bc;
+        int r = run_chunk(c, nullptr, x + static_cast<size_t>(b0) * 3 * 512 * 512, nb, thr,
+                          logits ? logits + static_cast<size_t>(b0) * n1 : nullptr,
+                          probs ? probs + static_cast<size_t>(b0) * n1 : nullptr, labels ? labels + b0 : nullptr, st);
+        if (r != SAD_OK) return r;
+    }
+    return SAD_OK;
+}
+
+int sad_forward_host(sad_ctx* c, const float* pcm_host, int B, float thr, float* logits_host, float* probs_host,
+                     int32_t* labels_host) {
+    if (!c || !pcm_host || B < 0) return SAD_EINVAL;
+    CU_OK(c, cudaSetDevice(c->device));
+    const size_t seg = SAD_SEGMENT_SAMPLES;
+    const int n1 = c->H + 1;
+    if (!c->d_pcm[0]) {
+        for (int i = 0; i < 2; ++i) {
+            CU_OK(c, dalloc(&c->d_pcm[i], static_cast<size_t>(c->Bc) * seg));
+            CU_OK(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_stage[i]), static_cast<size_t>(c->Bc) * seg * sizeof(float)));
+        }
+    }
+    if (B > c->res_capacity) {
+        cudaFree(c->d_res_logits);
+        cudaFree(c->d_res_probs);
+        cudaFree(c->d_res_labels);
+        c->d_res_logits = c->d_res_probs = nullptr;
+        c->d_res_labels = nullptr;
+        c->res_capacity = 0;
+        CU_OK(c, dalloc(&c->d_res_logits, static_cast<size_t>(B) * n1));
+        CU_OK(c, dalloc(&c->d_res_probs, static_cast<size_t>(B) * n1));
+        CU_OK(c, dalloc(&c->d_res_labels, static_cast<size_t>(B)));
+        c->res_capacity = B;
+    }
+    // is the caller's buffer page-locked?  then DMA straight from it, otherwise stage through pinned memory
+    cudaPointerAttributes attr;
+    bool pinned = cudaPointerGetAttributes(&attr, pcm_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    int it = 0;
+    for (int b0 = 0; b0 < B; b0 += c->Bc, ++it) {
+        const int nb = B - b0 < c->Bc ? B - b0 : c->Bc;
+        const int j = it & 1;
+        const float* src = pcm_host + static_cast<size_t>(b0) * seg;
+        if (!pinned) {
+            if (it >= 2) CU_OK(c, cudaEventSynchronize(c->ev_h2d[j]));   // staging buffer j drained
+            memcpy(c->h_stage[j], src, static_cast<size_t>(nb) * seg * sizeof(float));
+            src = c->h_stage[j];
+        }
+        if (it >= 2) CU_OK(c, cudaStreamWaitEvent(c->s_copy, c->ev_comp[j], 0));   // device pcm buffer j consumed
+        CU_OK(c, cudaMemcpyAsync(c->d_pcm[j], src, static_cast<size_t>(nb) * seg * sizeof(float), cudaMemcpyHostToDevice,
+                                 c->s_copy));
+        CU_OK(c, cudaEventRecord(c->ev_h2d[j], c->s_copy));
+        CU_OK(c, cudaStreamWaitEvent(c->s_comp, c->ev_h2d[j], 0));
+        int r = run_chunk(c, c->d_pcm[j], nullptr, nb, thr, c->d_res_logits + static_cast<size_t>(b0) * n1,
+                          c->d_res_probs + static_cast<size_t>(b0) * n1, c->d_res_labels + b0, c->s_comp);
+        if (r != SAD_OK) return r;
+        CU_OK(c, cudaEventRecord(c->ev_comp[j], c->s_comp));
+    }
+    if (logits_host)
+        CU_OK(c, cudaMemcpyAsync(logits_host, c->d_res_logits, static_cast<size_t>(B) * n1 * sizeof(float),
+                                 cudaMemcpyDeviceToHost, c->s_comp));
+    if (probs_host)
+        CU_OK(c, cudaMemcpyAsync(probs_host, c->d_res_probs, static_cast<size_t>(B) * n1 * sizeof(float),
+                                 cudaMemcpyDeviceToHost, c->s_comp));
+    if (labels_host)
+        CU_OK(c, cudaMemcpyAsync(labels_host, c->d_res_labels, static_cast<size_t>(B) * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, c->s_comp));
+    CU_OK(c, cudaStreamSynchronize(c->s_comp));
+    CU_OK(c, cudaStreamSynchronize(c->s_copy));
+    return SAD_OK;
+}
+
+int sad_clip_reduce(sad_ctx* c, const float* probs, const int32_t* clip_id, int B, int n_clips, float thr,
+                    float* clip_probs, int32_t* clip_label, void* stream) {
+    if (!c || !probs || !clip_id || !clip_probs || !clip_label || B < 0 || n_clips < 0) return SAD_EINVAL;
+    CU_OK(c, cudaSetDevice(c->device));
+    CU_OK(c, sad::clip_reduce_launch(probs, clip_id, B, n_clips, c->H, thr, clip_probs, clip_label,
+                                     static_cast<cudaStream_t>(stream), &c->launches));
+    return SAD_OK;
+}
+
+int sad_debug_conv(sad_ctx* c, int head, int layer, const void* in, const void* residual, void* out, int B, int relu,
+                   void* stream) {
+    if (!c || !in || !out || B < 1) return SAD_EINVAL;
+    if (layer < 1 || layer >= 20) return fail(c, SAD_EINVAL, "layer %d out of range [1,20)", layer);
+    if (head < 0 || head >= c->H) return fail(c, SAD_EINVAL, "head out of range");
+    if (!c->loaded[head]) return fail(c, SAD_ESTATE, "weights of head %d not loaded", head);
+    CU_OK(c, cudaSetDevice(c->device));
+    sad::ConvLaunch L;
+    if (!make_launch(c, &L, layer, static_cast<const bf16*>(in), static_cast<const bf16*>(residual), static_cast<bf16*>(out),
+                     B, relu))
+        return SAD_ECUDA;
+    // single head: offset the weight / bias views to `head` by re-encoding the weight map on that slice
+    const ConvSpec& s = convs()[layer];
+    const long long K = 1LL * s.k * s.k * s.cin;
+    if (!sad::encode_weight_map(&L.b_map, c->d_w[layer] + static_cast<size_t>(head) * s.cout * K, K, s.cout, L.n_tile, c->err,
+                                sizeof(c->err)))
+        return SAD_ECUDA;
+    L.bias = c->d_bias[layer] + static_cast<size_t>(head) * s.cout;
+    set_batch(&L, B, 1);
+    CU_OK(c, sad::conv_umma_launch(L, c->num_sms, static_cast<cudaStream_t>(stream)));
+    c->launches += 1;
+    return SAD_OK;
+}
+
+long long sad_debug_read(sad_ctx* c, int which, void* dst, long long capacity, void* stream) {
+    if (!c || !dst) return SAD_EINVAL;
+    const long long B = c->last_B, H = c->H;
+    const void* src = nullptr;
+    long long bytes = 0;
+    switch (which) {
+        case 0: src = c->d_img; bytes = B * 512 * 512 * 2; break;
+        case 1: src = c->d_stem; bytes = 0; break;
+        case 2: src = c->d_buf[BX]; bytes = H * B * 16 * 16 * 512 * 2; break;
+        case 3: src = c->d_head_logits; bytes = H * B * 2 * 4; break;
+        case 4: src = c->d_db; bytes = B * 128 * 251 * 4; break;
+        default: return fail(c, SAD_EINVAL, "unknown buffer id %d", which);
+    }
+    if (which == 1) return fail(c, SAD_EINVAL, "pooled stem output is overwritten by the trunk; use sad_debug_conv");
+    if (bytes > capacity) return fail(c, SAD_EINVAL, "need %lld bytes, capacity %lld", bytes, capacity);
+    if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+        return fail(c, SAD_ECUDA, "debug copy failed");
+    return bytes;
+}
+
+}  // extern "C"
+
+namespace {
+
+// One chunk (B <= Bc) through the whole pipeline on stream `st`.  Exactly one of pcm / x_nchw is non-null.
+int run_chunk(sad_ctx* c, const float* pcm, const float* x_nchw, int B, float thr, float* logits, float* probs,
+              int32_t* labels, cudaStream_t st) {
+    for (int h = 0; h < c->H; ++h)
+        if (!c->loaded[h]) return fail(c, SAD_ESTATE, "weights of head %d not loaded", h);
+    if (B == 0) return SAD_OK;
+    const int H = c->H;
+    c->last_B = B;
+    sad::ConvLaunch stem;
+    if (pcm) {
+        CU_OK(c, sad::frontend_logmel_launch(pcm, B, c->d_window, c->d_mel, c->d_db, c->d_segmax, nullptr, c->d_musig, st,
+                                             &c->launches));
+        CU_OK(c, sad::image_launch_bf16(c->d_db, c->d_musig, c->d_resize, c->d_img, B, st, &c->launches));
+        CU_OK(c, sad::im2col_stem1_launch(c->d_img, c->d_A1, B, st, &c->launches));
+        stem = c->stem1;
+    } else {
+        CU_OK(c, sad::im2col_stem3_launch(x_nchw, c->d_A3, B, st, &c->launches));
+        stem = c->stem3;
+    }
+    set_batch(&stem, B, H);
+    CU_OK(c, sad::conv_umma_launch(stem, c->num_sms, st));
+    c->launches += 1;
+    CU_OK(c, sad::maxpool_launch(c->d_stem, c->d_buf[BX], 1LL * H * B, st, &c->launches));
+    for (size_t i = 0; i < c->plan.size(); ++i) {
+        sad::ConvLaunch L = c->plan_launch[i];
+        set_batch(&L, B, H);
+        CU_OK(c, sad::conv_umma_launch(L, c->num_sms, st));
+        c->launches += 1;
+    }
+    sad::HeadWeights hw{c->d_w1t, c->d_b1, c->d_w2t, c->d_b2, c->d_w3, c->d_b3};
+    CU_OK(c, sad::head_mlp_launch(c->d_buf[BX], hw, B, H, c->d_head_logits, st, &c->launches));
+    CU_OK(c, sad::merge_decide_launch(c->d_head_logits, B, H, thr, logits, probs, labels, st, &c->launches));
+    return SAD_OK;
+}
+
+}  // namespace

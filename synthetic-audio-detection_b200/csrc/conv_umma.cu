@@ -1,0 +1,252 @@
+// K3: implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// One launch = one convolution layer for ALL heads of the ensemble (grouped over heads):
+//   out[img, oy, ox, co] = act( sum_{ky,kx,ci} in[img, oy*s+ky-p, ox*s+kx-p, ci] * w[head, co, ky, kx, ci]
+//                               + bias[head, co] + residual[img, oy, ox, co] )
+// with eval-mode BatchNorm already folded into w/bias (api.cu), activations NHWC bf16, fp32 accumulation.
+// Replaces, per layer, the conv2d + batch_norm (+ add) + relu sequence that timm's ResNet runs inside
+// BinaryClassifier.forward (reference modular/source/inference_runner.py:49-51).
+//
+// GEMM view:  M = 128 output pixels (a block of 128/Wo full output rows of one image),
+//             N = N_TILE output channels, K = taps * Cin walked in blocks of 64 channels of one tap.
+//   A tile (128 px x 64 ch, K-major, 128 B rows): ONE 4-D TMA box {64 ch, Wo, 128/Wo rows, 1 image} shifted by
+//       the tap offset; out-of-bounds rows/columns (the conv zero padding) are zero-filled by TMA.
+//       Stride-2 layers read through one of four "parity" tensor maps (a strided view of the input with
+//       W/2 x H/2 pixels) so the box stays dense.
+//   B tile (N_TILE x 64, K-major): 2-D TMA box from the packed weights [heads*Cout][taps*Cin].
+//   Both land in SWIZZLE_128B layout and are consumed by tcgen05.mma (UMMA 128 x N_TILE x 16) straight from
+//   shared memory; the fp32 accumulator lives in TMEM (double-buffered: 2 x N_TILE columns).
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over a static tile schedule):
+//   warp 0 : TMA producer (one elected lane)      -- full/empty mbarrier ring of kStages stages
+//   warp 1 : TMEM allocator + UMMA issuer (one lane), tcgen05.commit releases smem stages / signals epilogue
+//   warps 2-5 : epilogue: tcgen05.ld -> +bias (+residual) -> ReLU -> bf16 -> global (NHWC)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "conv_umma.h"
+#include "ptx.cuh"
+
+namespace sad {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
+
+template <int N_TILE>
+struct Cfg {
+    static constexpr int kBBytes = N_TILE * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+    static constexpr int kTmemCols = 2 * N_TILE < 32 ? 32 : 2 * N_TILE;   // 128 / 256 / 512: powers of two
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int N_TILE>
+__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvLaunch p) {
+    using C = Cfg<N_TILE>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* tiles = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint64_t* full_bar = bars;                      // [kStages]
+    uint64_t* empty_bar = bars + C::kStages;        // [kStages]
+    uint64_t* tmem_full = bars + 2 * C::kStages;    // [2]
+    uint64_t* tmem_empty = tmem_full + 2;           // [2]
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
+        tma_prefetch_desc(&p.b_map);
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_base_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    const int taps = p.ksize * p.ksize;
+    const int cblocks = p.Cin / kBlockK;
+    const int ksteps = taps * cblocks;
+    const int tiles_per_head = p.imgs_per_head * p.m_tiles_per_img * p.n_tiles;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int head = tile / tiles_per_head;
+                int r = tile - head * tiles_per_head;
+                const int n_t = r % p.n_tiles;
+                r /= p.n_tiles;
+                const int m_t = r % p.m_tiles_per_img;
+                const int img = r / p.m_tiles_per_img;
+                const int img_in = p.shared_input ? img : head * p.imgs_per_head + img;
+                const int oy0 = m_t * p.rows_per_tile;
+                const int wrow = head * p.Cout + n_t * N_TILE;
+                for (int tap = 0; tap < taps; ++tap) {
+                    const int offy = tap / p.ksize - p.pad;
+                    const int offx = tap % p.ksize - p.pad;
+                    int map = 0, x0 = offx, y0 = oy0 + offy;
+                    if (p.stride == 2) {   // parity view: input pixel (2*h2+py, 2*w2+px)
+                        map = ((offy & 1) << 1) | (offx & 1);
+                        x0 = offx >> 1;    // arithmetic shift: floor(-1/2) = -1
+                        y0 = oy0 + (offy >> 1);
+                    }
+                    for (int cb = 0; cb < cblocks; ++cb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* a_dst = tiles + stage * C::kStageBytes;
+                        uint8_t* b_dst = a_dst + kABytes;
+                        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+                        tma_load_4d(a_dst, &p.a_map[map], &full_bar[stage], cb * kBlockK, x0, y0, img_in);
+                        tma_load_2d(b_dst, &p.b_map, &full_bar[stage], tap * p.Cin + cb * kBlockK, wrow);
+                        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ UMMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, N_TILE);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * N_TILE;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(tiles + stage * C::kStageBytes);
+                    const uint64_t adesc = umma_desc_sw128(a_addr);
+                    const uint64_t bdesc = umma_desc_sw128(a_addr + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in >>4 units
+                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);   // frees this smem stage once the MMAs have read it
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);         // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;          // pixel inside the 128-pixel tile
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int head = tile / tiles_per_head;
+            int r = tile - head * tiles_per_head;
+            const int n_t = r % p.n_tiles;
+            r /= p.n_tiles;
+            const int m_t = r % p.m_tiles_per_img;
+            const int img = r / p.m_tiles_per_img;
+            const int acc = it & 1;
+            const long long pix =
+                (static_cast<long long>(head) * p.imgs_per_head + img) * (p.m_tiles_per_img * kBlockM) +
+                m_t * kBlockM + row;
+            const int co0 = n_t * N_TILE;
+            const float* bias = p.bias + head * p.Cout + co0;
+            __nv_bfloat16* out = p.out + pix * p.Cout + co0;
+            const __nv_bfloat16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * N_TILE;
+#pragma unroll 1
+            for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                tmem_ld_wait();
+                uint4 rv[4];
+                if (res) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(res + c0) + q);
+                }
+                uint4 ov[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t packed[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = q * 8 + j * 2;
+                        float x0 = __uint_as_float(v[c]) + __ldg(bias + c0 + c);
+                        float x1 = __uint_as_float(v[c + 1]) + __ldg(bias + c0 + c + 1);
+                        if (res) {
+                            const uint32_t rr = reinterpret_cast<const uint32_t*>(&rv[q])[j];
+                            x0 += __uint_as_float(rr << 16);
+                            x1 += __uint_as_float(rr & 0xFFFF0000u);
+                        }
+                        if (p.relu) {
+                            x0 = fmaxf(x0, 0.f);
+                            x1 = fmaxf(x1, 0.f);
+                        }
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(x0, x1);
+                        packed[j] = *reinterpret_cast<uint32_t*>(&b2);
+                    }
+                    ov[q] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(out + c0)[q] = ov[q];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+template <int N_TILE>
+cudaError_t launch_t(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
+    using C = Cfg<N_TILE>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             C::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+    conv_umma_kernel<N_TILE><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int conv_n_tile(int Cout) { return Cout >= 256 ? 256 : Cout; }
+
+cudaError_t conv_umma_launch(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
+    switch (p.n_tile) {
+        case 64: return launch_t<64>(p, num_sms, stream);
+        case 128: return launch_t<128>(p, num_sms, stream);
+        case 256: return launch_t<256>(p, num_sms, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace sad

@@ -1,0 +1,39 @@
+// Host-visible launch description of the tcgen05 implicit-GEMM convolution (conv_umma.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace sad {
+
+struct alignas(64) ConvLaunch {
+    CUtensorMap a_map[4];   // input views; stride 1 uses [0] (all four equal), stride 2 uses parity (py*2+px)
+    CUtensorMap b_map;      // packed weights [heads*Cout][taps*Cin] bf16, K-major
+    const float* bias;      // [heads*Cout] fp32 (folded BN shift)
+    const __nv_bfloat16* residual;   // NHWC [heads*imgs][Ho*Wo][Cout] or nullptr
+    __nv_bfloat16* out;     // NHWC [heads*imgs][Ho*Wo][Cout]
+    int Cin, Cout;
+    int ksize, stride, pad;
+    int imgs_per_head;      // B
+    int m_tiles_per_img;    // Ho*Wo / 128
+    int rows_per_tile;      // 128 / Wo
+    int n_tiles;            // Cout / n_tile
+    int n_tile;             // 64, 128 or 256
+    int total_tiles;        // heads * imgs * m_tiles_per_img * n_tiles
+    int relu;
+    int shared_input;       // 1: every head reads image `img` (stem); 0: head h reads image h*B+img
+};
+
+int conv_n_tile(int Cout);
+cudaError_t conv_umma_launch(const ConvLaunch& p, int num_sms, cudaStream_t stream);
+
+// Tensor-map construction (api.cu): resolves cuTensorMapEncodeTiled through the runtime so that the
+// library does not link against libcuda and still loads on a machine without a driver.
+// 4-D NHWC bf16 activation view: dims {C, W, H, N}; element (c,x,y,n) at base + c + x*sx + y*sy + n*sn (elements).
+bool encode_act_map(CUtensorMap* m, const void* base, int C, int W, int H, long long N, long long sx, long long sy,
+                    long long sn, int box_w, int box_h, char* err, int errlen);
+// 2-D weight view: dims {K, rows}; box {64, box_rows}.
+bool encode_weight_map(CUtensorMap* m, const void* base, long long K, long long rows, int box_rows, char* err,
+                       int errlen);
+
+}  // namespace sad

@@ -1,0 +1,178 @@
+// K4 / K5: global average pool + per-head MLP (BatchNorm1d folded) + merge + sigmoid/threshold decision,
+// and the per-clip mean.  fp32 throughout (the tolerance budget is spent on the bf16 convolutions).
+// Replaces BinaryClassifier.head (reference modular/source/inference_runner.py:36-48, eval mode),
+// ModularMultiHeadClassifier.forward's merge (:62-73), interpret_multihead_logits (:194-214) and the clip
+// mean (:328-334).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "head.h"
+
+namespace sad {
+
+namespace {
+
+// grid (B, H), 256 threads.  feats: NHWC bf16 [H*B][256 px][512]; weights transposed [in][out] fp32.
+__global__ void __launch_bounds__(256) head_mlp_kernel(const __nv_bfloat16* __restrict__ feats, HeadWeights hw, int B,
+                                                       float* __restrict__ head_logits) {
+    __shared__ float pooled[512];
+    __shared__ float h1[512];
+    __shared__ float h2[256];
+    __shared__ float red[2][8];
+    const int b = blockIdx.x, h = blockIdx.y, t = threadIdx.x;
+    const size_t n = static_cast<size_t>(h) * B + b;
+    const __nv_bfloat162* f = reinterpret_cast<const __nv_bfloat162*>(feats + n * 256 * 512);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+    for (int p = 0; p < 256; ++p) {
+        const float2 v = __bfloat1622float2(f[p * 256 + t]);
+        s0 += v.x;
+        s1 += v.y;
+    }
+    pooled[2 * t] = s0 * (1.0f / 256.0f);
+    pooled[2 * t + 1] = s1 * (1.0f / 256.0f);
+    __syncthreads();
+
+    const float* w1 = hw.w1t + static_cast<size_t>(h) * 512 * 512;
+    float a0 = hw.b1[h * 512 + t], a1 = hw.b1[h * 512 + t + 256];
+#pragma unroll 4
+    for (int i = 0; i < 512; ++i) {
+        const float x = pooled[i];
+        a0 = fmaf(x, __ldg(w1 + i * 512 + t), a0);
+        a1 = fmaf(x, __ldg(w1 + i * 512 + t + 256), a1);
+    }
+    h1[t] = fmaxf(a0, 0.f);
+    h1[t + 256] = fmaxf(a1, 0.f);
+    __syncthreads();
+
+    const float* w2 = hw.w2t + static_cast<size_t>(h) * 512 * 256;
+    float c = hw.b2[h * 256 + t];
+#pragma unroll 4
+    for (int i = 0; i < 512; ++i) c = fmaf(h1[i], __ldg(w2 + i * 256 + t), c);
+    h2[t] = fmaxf(c, 0.f);
+    __syncthreads();
+
+    const float* w3 = hw.w3 + static_cast<size_t>(h) * 2 * 256;   // [2][256] as in nn.Linear
+    float z0 = h2[t] * w3[t], z1 = h2[t] * w3[256 + t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        z0 += __shfl_xor_sync(0xffffffffu, z0, o);
+        z1 += __shfl_xor_sync(0xffffffffu, z1, o);
+    }
+    if ((t & 31) == 0) {
+        red[0][t >> 5] = z0;
+        red[1][t >> 5] = z1;
+    }
+    __syncthreads();
+    if (t < 2) {
+        float z = hw.b3[h * 2 + t];
+        for (int i = 0; i < 8; ++i) z += red[t][i];
+        head_logits[n * 2 + t] = z;   // index 0 = Real, 1 = Synthetic
+    }
+}
+
+// One warp per segment; lane i holds head i's (real, synthetic) logits.  N <= 31.
+__global__ void __launch_bounds__(256) merge_decide_kernel(const float* __restrict__ head_logits, int B, int N, float thr,
+                                                           float* __restrict__ logits, float* __restrict__ probs,
+                                                           int* __restrict__ labels) {
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    float real = 0.f, syn = 0.f;
+    if (lane < N) {
+        real = head_logits[(static_cast<size_t>(lane) * B + b) * 2];
+        syn = head_logits[(static_cast<size_t>(lane) * B + b) * 2 + 1];
+    }
+    float acc = 0.f;
+    for (int i = 0; i < N; ++i) acc += __shfl_sync(0xffffffffu, real, i);   // sequential order, like torch.mean
+    const float real_mean = acc / static_cast<float>(N);
+    const float z = lane < N ? syn : real_mean;                               // column `lane` of [syn.., real_mean]
+    const float s = 1.0f / (1.0f + expf(-z));
+    if (lane <= N) {
+        if (logits) logits[static_cast<size_t>(b) * (N + 1) + lane] = z;
+        if (probs) probs[static_cast<size_t>(b) * (N + 1) + lane] = s;
+    }
+    // decision: gather the N+1 probabilities into every lane's registers is overkill; use ballots
+    const unsigned below = __ballot_sync(0xffffffffu, lane < N && s < thr);
+    const bool all_below = below == ((N >= 32) ? 0xffffffffu : ((1u << N) - 1u));
+    const float s_real = __shfl_sync(0xffffffffu, s, N);
+    float best = lane < N ? s : -1.f;
+    int arg = lane < N ? lane : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob > best || (ob == best && oa < arg)) {
+            best = ob;
+            arg = oa;
+        }
+    }
+    if (lane == 0 && labels) labels[b] = (s_real >= thr && all_below) ? N : arg;
+}
+
+// One warp per clip over SORTED clip ids: binary-search the run, sum rows sequentially per column (numpy's
+// order for np.mean(axis=0)), divide, decide.
+__global__ void __launch_bounds__(256) clip_reduce_kernel(const float* __restrict__ probs, const int* __restrict__ clip_id,
+                                                          int B, int n_clips, int N, float thr,
+                                                          float* __restrict__ clip_probs, int* __restrict__ clip_label) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= n_clips) return;
+    int lo = 0, hi = B;
+    while (lo < hi) {   // first index with clip_id >= c
+        const int mid = (lo + hi) >> 1;
+        if (clip_id[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    const int first = lo;
+    hi = B;
+    while (lo < hi) {   // first index with clip_id > c
+        const int mid = (lo + hi) >> 1;
+        if (clip_id[mid] <= c) lo = mid + 1; else hi = mid;
+    }
+    const int last = lo;
+    const int cnt = last - first;
+    float acc = 0.f;
+    if (lane <= N)
+        for (int r = first; r < last; ++r) acc += probs[static_cast<size_t>(r) * (N + 1) + lane];
+    const float mean = cnt > 0 ? acc / static_cast<float>(cnt) : 0.f;
+    if (lane <= N) clip_probs[static_cast<size_t>(c) * (N + 1) + lane] = mean;
+    const unsigned below = __ballot_sync(0xffffffffu, lane < N && mean < thr);
+    const bool all_below = below == ((1u << N) - 1u);
+    const float s_real = __shfl_sync(0xffffffffu, mean, N);
+    float best = lane < N ? mean : -1.f;
+    int arg = lane < N ? lane : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob > best || (ob == best && oa < arg)) {
+            best = ob;
+            arg = oa;
+        }
+    }
+    if (lane == 0) clip_label[c] = cnt == 0 ? -1 : ((s_real >= thr && all_below) ? N : arg);
+}
+
+}  // namespace
+
+cudaError_t head_mlp_launch(const __nv_bfloat16* feats, const HeadWeights& hw, int B, int H, float* head_logits,
+                            cudaStream_t stream, long long* launches) {
+    head_mlp_kernel<<<dim3(B, H), 256, 0, stream>>>(feats, hw, B, head_logits);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t merge_decide_launch(const float* head_logits, int B, int N, float thr, float* logits, float* probs, int* labels,
+                                cudaStream_t stream, long long* launches) {
+    merge_decide_kernel<<<(B + 7) / 8, 256, 0, stream>>>(head_logits, B, N, thr, logits, probs, labels);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t clip_reduce_launch(const float* probs, const int* clip_id, int B, int n_clips, int N, float thr,
+                               float* clip_probs, int* clip_label, cudaStream_t stream, long long* launches) {
+    if (n_clips <= 0) return cudaSuccess;
+    clip_reduce_kernel<<<(n_clips + 7) / 8, 256, 0, stream>>>(probs, clip_id, B, n_clips, N, thr, clip_probs, clip_label);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace sad

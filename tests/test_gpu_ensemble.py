@@ -1,0 +1,97 @@
+"""GPU parity: the whole path (PCM -> decisions) through the C ABI vs the fp32 oracle and the reference goldens.
+
+Tolerances (BASELINE.json north_star): merged logits within 2e-2 absolute (bf16 convolutions), identical
+Real/Synthetic decision on >= 99.9% of segments.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bf16_emulation as E
+from oracle import fixtures as FX
+from oracle import restatement as R
+from tests import gpu_common as G
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 2e-2
+
+
+@pytest.mark.parametrize("tag", ["n2", "n5"])
+def test_fused_forward_vs_reference_golden(tag):
+    g = G.golden(f"ensemble_{tag}.npz")
+    n = int(g["n_heads"])
+    e = G.engine(n)
+    x = G.segs(g["seg_ids"]).cuda()
+    logits, probs, labels = e.forward_pcm(x, 0.5)
+    torch.cuda.synchronize()
+    d = np.abs(logits.cpu().numpy() - g["merged_logits"])
+    print(f"{tag}: max |logit diff| vs reference golden {d.max():.4f}")
+    assert d.max() <= LOGIT_TOL
+    np.testing.assert_allclose(probs.cpu().numpy(), g["probs"], rtol=0, atol=LOGIT_TOL / 4 + 1e-6)
+    names = [str(s) for s in g["class_names"]]
+    mine = [R.label_name(int(l), n, names[:-1], names[-1]) for l in labels.cpu().numpy()]
+    want = [str(s) for s in g["labels"]]
+    margin = np.abs(g["merged_logits"]).min(axis=1)
+    for a, b, m in zip(mine, want, margin):
+        assert a == b or m <= LOGIT_TOL, (a, b, m)
+
+
+def test_images_entry_matches_fused_entry():
+    """sad_forward_images (nn.Module.forward drop-in, 3-channel stem) on the oracle's images vs the oracle."""
+    sd = G.merged_sd(2)
+    x = FX.synth_segments(4, first=40)
+    img3 = R.waveform_to_image(x).unsqueeze(1).repeat(1, 3, 1, 1).contiguous()
+    want = R.ensemble_forward(img3, sd).numpy()
+    e = G.engine(2)
+    lo, _, _ = e.forward_images(img3.cuda(), 0.5)
+    d = np.abs(lo.cpu().numpy() - want)
+    print("forward_images: max |logit diff|", d.max())
+    assert d.max() <= LOGIT_TOL
+    # a genuinely 3-channel image (channels differ) exercises the K=147 packing
+    g = torch.Generator().manual_seed(5)
+    rgb = torch.randn(2, 3, 512, 512, generator=g)
+    want = R.ensemble_forward(rgb, sd).numpy()
+    lo, _, _ = e.forward_images(rgb.cuda(), 0.5)
+    d = np.abs(lo.cpu().numpy() - want)
+    print("forward_images rgb: max |logit diff|", d.max())
+    assert d.max() <= 2 * LOGIT_TOL        # out-of-distribution input: BN statistics were calibrated on log-mels
+
+
+def test_decisions_and_logits_on_corpus():
+    """In-distribution corpus (the fixture's calibration segments) + held-out segments, N=2."""
+    sd = G.merged_sd(2)
+    e = G.engine(2)
+    x = torch.cat([FX.synth_segments(FX.N_CAL, first=FX.CAL_FIRST), FX.synth_segments(32, first=300)])
+    img3 = R.waveform_to_image(x).unsqueeze(1).repeat(1, 3, 1, 1)
+    want = torch.cat([R.ensemble_forward(img3[i:i + 16], sd) for i in range(0, x.shape[0], 16)])
+    lo, pr, la = e.forward_pcm(x.cuda(), 0.5)
+    lo = lo.cpu()
+    d = (lo - want).abs()
+    lab_want, probs_want = R.interpret(want, 0.5)
+    agree = la.cpu().numpy() == lab_want
+    margin = want.abs().min(dim=1).values.numpy()
+    print(f"corpus: max |logit diff| {d.max():.4f} mean {d.mean():.4f}; agreement {agree.mean():.4f} "
+          f"(cal {agree[:FX.N_CAL].mean():.4f}, held-out {agree[FX.N_CAL:].mean():.4f}); "
+          f"min margin {margin.min():.4f}; disagreements' margins {margin[~agree]}")
+    assert d.max() <= LOGIT_TOL
+    assert np.all(margin[~agree] <= LOGIT_TOL), "a decision flipped outside the logit tolerance band"
+    assert agree.mean() >= 0.999 or np.all(margin[~agree] <= LOGIT_TOL)
+    # device vs the CPU emulation of the device data path (localises kernel bugs, not a parity claim)
+    emu = E.ensemble_bf16(img3[:8, :1], sd)
+    print("device vs bf16 emulation: max |diff|", (lo[:8] - emu).abs().max().item())
+
+
+def test_host_entry_and_clip_reduce():
+    e = G.engine(2)
+    x = FX.synth_segments(12, first=500)
+    lo_d, pr_d, la_d = e.forward_pcm(x.cuda(), 0.5)
+    lo_h, pr_h, la_h = e.forward_host(x.pin_memory(), 0.5)
+    lo_p, _, _ = e.forward_host(x, 0.5)                      # pageable source goes through the staging buffers
+    assert torch.equal(lo_d.cpu(), lo_h) and torch.equal(la_d.cpu(), la_h) and torch.equal(lo_h, lo_p)
+    clip_id = torch.tensor([0, 0, 0, 1, 1, 3, 3, 3, 3, 3, 4, 4], dtype=torch.int32)
+    cp, cl = e.clip_reduce(pr_d, clip_id.cuda(), 5, 0.5)
+    want_p, want_l = R.clip_aggregate(pr_d.cpu().numpy(), clip_id.numpy(), 5, 0.5)
+    np.testing.assert_allclose(cp.cpu().numpy(), want_p, rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(cl.cpu().numpy(), want_l)
+    assert int(cl[2]) == -1                                   # clip without segments
