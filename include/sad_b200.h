@@ -103,7 +103,7 @@ int sad_forward_host(sad_ctx* ctx, const float* pcm_host, int B, float threshold
                      float* probs_host, int32_t* labels_host);
 
 /* ---- clip aggregation: replaces inference_runner.py:328-334 ------------------------------------ */
-/* clip_id [B] int32 (any order, values in [0,n_clips)); clip_probs [n_clips,N+1] = mean over the clip's
+/* clip_id [B] int32 SORTED ascending (segments of a clip are contiguous), values in [0,n_clips); clip_probs [n_clips,N+1] = mean over the clip's
  * segments of probs; clip_label = rule :207-213 applied to the clip mean (-1 for a clip with no segment). */
 int sad_clip_reduce(sad_ctx* ctx, const float* probs_dev, const int32_t* clip_id_dev, int B, int n_clips,
                     float threshold, float* clip_probs_dev, int32_t* clip_label_dev, void* stream);
@@ -113,6 +113,17 @@ int sad_n_heads(const sad_ctx* ctx);
 int sad_max_batch(const sad_ctx* ctx);
 /* Number of kernels this library has launched on the context since creation. */
 long long sad_launch_count(const sad_ctx* ctx);
+/* Live profiling (bench.py): when enabled, every kernel class launched by sad_forward* is bracketed by CUDA events
+ * on the launching stream.  Kinds 0..19 = the 20 convolutions in state_dict order (0 = stem), then the classes
+ * below.  sad_profile_read synchronises on the recorded events and returns accumulated milliseconds and the number
+ * of bracketed launch groups per kind (arrays of SAD_PROF_KINDS).  Enabling resets the counters.              */
+#define SAD_PROF_FRONTEND 20 /* fill + stft_mel + db_clamp_stats                  */
+#define SAD_PROF_IMAGE 21    /* standardise/resize image + stem im2col            */
+#define SAD_PROF_POOL 22     /* 3x3/2 max pool                                    */
+#define SAD_PROF_HEAD 23     /* avg-pool + MLP + merge + decision                 */
+#define SAD_PROF_KINDS 24
+int sad_profile_enable(sad_ctx* ctx, int on);
+int sad_profile_read(sad_ctx* ctx, double* ms_by_kind, long long* launches_by_kind);
 /* Run ONE convolution layer of one head on caller buffers (NHWC bf16): layer = index into the 20 convs in
  * state_dict order (0 = stem conv1 is not available here; 1..19).  `in` [B,Hi,Wi,Cin], `residual`
  * [B,Ho,Wo,Cout] or NULL, `out` [B,Ho,Wo,Cout].  Used by the per-layer parity tests.                */

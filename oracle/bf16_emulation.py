@@ -33,10 +33,10 @@ def _q(x: torch.Tensor) -> torch.Tensor:
 
 
 def backbone_bf16(img1: torch.Tensor, sd: Dict[str, torch.Tensor], p: str, taps: List = None):
-    """img1: [B,1,512,512] fp32 single-channel image (the three reference channels are identical,
+    """img1: [B,1,512,512] (or a general [B,3,512,512]) fp32; single-channel image (the three reference channels are identical,
     IR:173, so conv1's weights are summed over Cin).  Returns [B,512,16,16] fp32-valued bf16."""
     w, b = fold_bn(sd[p + "conv1.weight"], sd, p + "bn1")
-    w1 = _q(w.sum(dim=1, keepdim=True))
+    w1 = _q(w.sum(dim=1, keepdim=True)) if img1.shape[1] == 1 else _q(w)   # 3-channel input: general stem
     x = F.conv2d(_q(img1), w1, b, stride=2, padding=3)
     x = _q(F.relu(x))
     x = F.max_pool2d(x, 3, 2, 1)

@@ -171,6 +171,14 @@ struct sad_ctx {
     float* d_res_probs = nullptr;
     int32_t* d_res_labels = nullptr;
     long long res_capacity = 0;
+
+    // optional live profiling: CUDA-event pairs around each kernel class (bench.py's roofline numbers)
+    bool prof_on = false;
+    struct ProfRec { int kind; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[SAD_PROF_KINDS] = {0};
+    long long prof_n[SAD_PROF_KINDS] = {0};
 };
 
 namespace {
@@ -196,6 +204,45 @@ int fail(sad_ctx* c, int code, const char* fmt, ...) {
 template <typename T>
 cudaError_t dalloc(T** p, size_t n) {
     return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+}
+
+// ---- live profiling -------------------------------------------------------------------------------
+struct ProfScope {
+    sad_ctx* c;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int kind;
+    ProfScope(sad_ctx* c_, int kind_, cudaStream_t st_) : c(c_), st(st_), kind(kind_) {
+        if (!c->prof_on) return;
+        auto get = [&]() {
+            cudaEvent_t e = nullptr;
+            if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        a = get();
+        b = get();
+        cudaEventRecord(a, st);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        c->prof_recs.push_back({kind, a, b});
+    }
+};
+
+void prof_collect(sad_ctx* c) {
+    for (auto& r : c->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            c->prof_ms[r.kind] += ms;
+            c->prof_n[r.kind] += 1;
+        }
+        c->prof_pool.push_back(r.a);
+        c->prof_pool.push_back(r.b);
+    }
+    c->prof_recs.clear();
+    cudaGetLastError();
 }
 
 // ---- tensor maps -----------------------------------------------------------------------------------
@@ -562,6 +609,8 @@ int sad_destroy(sad_ctx* c) {
         if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
         if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
     }
+    prof_collect(c);
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     cudaGetLastError();
@@ -840,6 +889,31 @@ int sad_debug_conv(sad_ctx* c, int head, int layer, const void* in, const void* 
     return SAD_OK;
 }
 
+int sad_profile_enable(sad_ctx* c, int on) {
+    if (!c) return SAD_EINVAL;
+    cudaSetDevice(c->device);
+    prof_collect(c);
+    c->prof_on = on != 0;
+    if (on) {
+        for (int i = 0; i < SAD_PROF_KINDS; ++i) {
+            c->prof_ms[i] = 0;
+            c->prof_n[i] = 0;
+        }
+    }
+    return SAD_OK;
+}
+
+int sad_profile_read(sad_ctx* c, double* ms_by_kind, long long* launches_by_kind) {
+    if (!c) return SAD_EINVAL;
+    cudaSetDevice(c->device);
+    prof_collect(c);   // synchronises on the recorded events
+    for (int i = 0; i < SAD_PROF_KINDS; ++i) {
+        if (ms_by_kind) ms_by_kind[i] = c->prof_ms[i];
+        if (launches_by_kind) launches_by_kind[i] = c->prof_n[i];
+    }
+    return SAD_OK;
+}
+
 long long sad_debug_read(sad_ctx* c, int which, void* dst, long long capacity, void* stream) {
     if (!c || !dst) return SAD_EINVAL;
     const long long B = c->last_B, H = c->H;
@@ -874,26 +948,39 @@ int run_chunk(sad_ctx* c, const float* pcm, const float* x_nchw, int B, float th
     c->last_B = B;
     sad::ConvLaunch stem;
     if (pcm) {
-        CU_OK(c, sad::frontend_logmel_launch(pcm, B, c->d_window, c->d_mel, c->d_db, c->d_segmax, nullptr, c->d_musig, st,
-                                             &c->launches));
+        {
+            ProfScope ps(c, SAD_PROF_FRONTEND, st);
+            CU_OK(c, sad::frontend_logmel_launch(pcm, B, c->d_window, c->d_mel, c->d_db, c->d_segmax, nullptr, c->d_musig, st,
+                                                 &c->launches));
+        }
+        ProfScope ps(c, SAD_PROF_IMAGE, st);
         CU_OK(c, sad::image_launch_bf16(c->d_db, c->d_musig, c->d_resize, c->d_img, B, st, &c->launches));
         CU_OK(c, sad::im2col_stem1_launch(c->d_img, c->d_A1, B, st, &c->launches));
         stem = c->stem1;
     } else {
+        ProfScope ps(c, SAD_PROF_IMAGE, st);
         CU_OK(c, sad::im2col_stem3_launch(x_nchw, c->d_A3, B, st, &c->launches));
         stem = c->stem3;
     }
     set_batch(&stem, B, H);
-    CU_OK(c, sad::conv_umma_launch(stem, c->num_sms, st));
-    c->launches += 1;
-    CU_OK(c, sad::maxpool_launch(c->d_stem, c->d_buf[BX], 1LL * H * B, st, &c->launches));
+    {
+        ProfScope ps(c, 0, st);
+        CU_OK(c, sad::conv_umma_launch(stem, c->num_sms, st));
+        c->launches += 1;
+    }
+    {
+        ProfScope ps(c, SAD_PROF_POOL, st);
+        CU_OK(c, sad::maxpool_launch(c->d_stem, c->d_buf[BX], 1LL * H * B, st, &c->launches));
+    }
     for (size_t i = 0; i < c->plan.size(); ++i) {
         sad::ConvLaunch L = c->plan_launch[i];
         set_batch(&L, B, H);
+        ProfScope ps(c, c->plan[i].conv, st);
         CU_OK(c, sad::conv_umma_launch(L, c->num_sms, st));
         c->launches += 1;
     }
     sad::HeadWeights hw{c->d_w1t, c->d_b1, c->d_w2t, c->d_b2, c->d_w3, c->d_b3};
+    ProfScope ps(c, SAD_PROF_HEAD, st);
     CU_OK(c, sad::head_mlp_launch(c->d_buf[BX], hw, B, H, c->d_head_logits, st, &c->launches));
     CU_OK(c, sad::merge_decide_launch(c->d_head_logits, B, H, thr, logits, probs, labels, st, &c->launches));
     return SAD_OK;

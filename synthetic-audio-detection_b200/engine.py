@@ -209,6 +209,19 @@ class Engine:
         _lib.check(self.ctx, int(n), "sad_debug_read")
         return out
 
+    PROF_KINDS = 24
+
+    def profile_enable(self, on: bool = True):
+        _lib.check(self.ctx, self.lib.sad_profile_enable(self.ctx, int(on)), "sad_profile_enable")
+
+    def profile_read(self):
+        """(ms_by_kind[24], launches_by_kind[24]); kinds 0..19 = convolutions (0 = stem), 20 front end,
+        21 image+im2col, 22 max pool, 23 head/merge."""
+        ms = (C.c_double * self.PROF_KINDS)()
+        n = (C.c_longlong * self.PROF_KINDS)()
+        _lib.check(self.ctx, self.lib.sad_profile_read(self.ctx, ms, n), "sad_profile_read")
+        return list(ms), list(n)
+
     @property
     def launches(self) -> int:
         return int(self.lib.sad_launch_count(self.ctx))

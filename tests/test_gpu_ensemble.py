@@ -48,14 +48,20 @@ def test_images_entry_matches_fused_entry():
     d = np.abs(lo.cpu().numpy() - want)
     print("forward_images: max |logit diff|", d.max())
     assert d.max() <= LOGIT_TOL
-    # a genuinely 3-channel image (channels differ) exercises the K=147 packing
+    # a genuinely 3-channel image (channels differ) exercises the K=147 packing.  White noise is far outside the
+    # distribution the BN statistics were calibrated on, so the logits are large; the bar is relative to their
+    # scale, plus a tight check against the CPU emulation of the device data path.
     g = torch.Generator().manual_seed(5)
     rgb = torch.randn(2, 3, 512, 512, generator=g)
     want = R.ensemble_forward(rgb, sd).numpy()
+    emu = E.ensemble_bf16(rgb, sd).numpy()
     lo, _, _ = e.forward_images(rgb.cuda(), 0.5)
     d = np.abs(lo.cpu().numpy() - want)
-    print("forward_images rgb: max |logit diff|", d.max())
-    assert d.max() <= 2 * LOGIT_TOL        # out-of-distribution input: BN statistics were calibrated on log-mels
+    scale = max(1.0, np.abs(want).max() / FX.TARGET)
+    print("forward_images rgb: max |logit diff|", d.max(), "logit scale", np.abs(want).max(),
+          "vs emulation", np.abs(lo.cpu().numpy() - emu).max())
+    assert d.max() <= LOGIT_TOL * scale
+    assert np.abs(lo.cpu().numpy() - emu).max() <= 0.25 * LOGIT_TOL * scale
 
 
 def test_decisions_and_logits_on_corpus():
