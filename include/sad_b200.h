@@ -129,6 +129,10 @@ int sad_profile_read(sad_ctx* ctx, double* ms_by_kind, long long* launches_by_ki
  * [B,Ho,Wo,Cout] or NULL, `out` [B,Ho,Wo,Cout].  Used by the per-layer parity tests.                */
 int sad_debug_conv(sad_ctx* ctx, int head, int layer, const void* in_dev, const void* residual_dev, void* out_dev,
                    int B, int relu, void* stream);
+/* Run front end + fused stem/max-pool on pcm [B,128000] (B <= max_batch) and copy the pooled stem output, NHWC bf16
+ * [H*B,128,128,64] (head-major), to out_dev.  Used by the stem parity test; sad_debug_read(which=0) then returns the
+ * bf16 image the stem consumed.                                                                                  */
+int sad_debug_stem(sad_ctx* ctx, const float* pcm_dev, int B, void* out_dev, void* stream);
 /* Copy an internal activation of the last sad_forward* chunk to the caller (tests only).
  * which: 0 = image bf16 [B,512,512]; 1 = pooled stem out bf16 [H*B,128,128,64]; 2 = layer4 out bf16
  * [H*B,16,16,512]; 3 = per-head logits fp32 [H*B,2].  Returns the number of bytes written.         */

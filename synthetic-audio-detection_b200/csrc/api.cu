@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -19,6 +20,7 @@
 #include "conv_umma.h"
 #include "frontend.h"
 #include "head.h"
+#include "stem_fused.h"
 
 namespace {
 
@@ -135,7 +137,7 @@ struct sad_ctx {
     // weights
     bf16* d_w[20] = {nullptr};          // [H][Cout][taps*Cin]; index 0 unused (stem has its own two packings)
     float* d_bias[20] = {nullptr};      // [H][Cout]
-    bf16* d_w_stem1 = nullptr;          // [H][64][64]   1-channel (summed) stem, K = 49 -> 64
+    bf16* d_w_stem1 = nullptr;          // [H][64][64]   1-channel (summed) stem: k = ky*8+kx, k=56..58 bias hi/mid/lo
     bf16* d_w_stem3 = nullptr;          // [H][64][192]  3-channel stem, K = 147 -> 192
     float *d_w1t = nullptr, *d_b1 = nullptr, *d_w2t = nullptr, *d_b2 = nullptr, *d_w3 = nullptr, *d_b3 = nullptr;
 
@@ -149,7 +151,6 @@ struct sad_ctx {
     unsigned* d_segmax = nullptr;       // [Bc]
     float* d_musig = nullptr;           // [Bc][2]
     bf16* d_img = nullptr;              // [Bc][512][512]
-    bf16* d_A1 = nullptr;               // [Bc][65536][64]
     bf16* d_A3 = nullptr;               // [Bc][65536][192] (allocated on first sad_forward_images)
     bf16* d_stem = nullptr;             // [H*Bc][256][256][64]
     bf16* d_buf[4] = {nullptr};         // X, Y, T, D
@@ -157,10 +158,12 @@ struct sad_ctx {
     int last_B = 0;
 
     // launch descriptors with tensor maps bound to the workspace
-    sad::ConvLaunch stem1, stem3;
+    sad::StemLaunch stem1;              // fused stem + maxpool for the single-channel image (PCM path)
+    sad::ConvLaunch stem3;              // 3-channel stem as a GEMM over an im2col matrix (sad_forward_images)
     std::vector<sad::ConvLaunch> plan_launch;
     std::vector<Step> plan;
     bool stem3_ready = false;
+    int rows_mode = 2;                  // layer1 row-stationary kernel: 0 off, 2 on (1 = probe: descriptor base-offset field set, WRONG on sm_100a)
 
     // end-to-end path
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
@@ -289,6 +292,10 @@ bool encode_act_map(CUtensorMap* m, const void* base, int C, int W, int H, long 
     return true;
 }
 
+bool encode_pix_map(CUtensorMap* m, const void* base, int C, long long pixels, int box_px, char* err, int errlen) {
+    return encode_weight_map(m, base, C, pixels, box_px, err, errlen);   // same 2-D {inner, rows} geometry
+}
+
 bool encode_weight_map(CUtensorMap* m, const void* base, long long K, long long rows, int box_rows, char* err,
                        int errlen) {
     EncodeTiledFn fn = encode_fn(err, errlen);
@@ -310,16 +317,33 @@ bool encode_weight_map(CUtensorMap* m, const void* base, long long K, long long 
 
 }  // namespace sad
 
+namespace sad {
+cudaError_t conv_rows_launch(const ConvLaunch& p, int heads, int base_offset_mode, int num_sms, cudaStream_t stream);
+}
+
 namespace {
 
+cudaError_t launch_conv(sad_ctx* c, int ci, const sad::ConvLaunch& L, int heads, cudaStream_t st);
+
 // Fill one ConvLaunch for conv `ci` reading `in` (NHWC [n_imgs][hin][hin][cin]) and writing `out`.
+bool is_rows_layer(int ci) {
+    const ConvSpec& s = convs()[ci];
+    return s.cin == 64 && s.cout == 64 && s.k == 3 && s.stride == 1 && s.hin == 128;
+}
+
 bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const bf16* res, bf16* out, long long n_imgs,
                  int relu) {
     const ConvSpec& s = convs()[ci];
     memset(L, 0, sizeof(*L));
     const int Wo = s.hout, Hi = s.hin, C = s.cin;
     const int rows = 128 / Wo;
-    if (s.stride == 1) {
+    if (c->rows_mode && is_rows_layer(ci)) {
+        // row-stationary kernel (conv_rows.cu): one box = a whole halo'd input row {64 ch, 130 px, 1 row}
+        if (!sad::encode_act_map(&L->a_map[0], in, C, Hi, Hi, n_imgs, C, 1LL * Hi * C, 1LL * Hi * Hi * C, Wo + 2, 1, c->err,
+                                 sizeof(c->err)))
+            return false;
+        for (int i = 1; i < 4; ++i) L->a_map[i] = L->a_map[0];
+    } else if (s.stride == 1) {
         if (!sad::encode_act_map(&L->a_map[0], in, C, Hi, Hi, n_imgs, C, 1LL * Hi * C, 1LL * Hi * Hi * C, Wo, rows, c->err,
                                  sizeof(c->err)))
             return false;
@@ -335,6 +359,9 @@ bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const b
     const long long K = 1LL * s.k * s.k * s.cin;
     if (!sad::encode_weight_map(&L->b_map, c->d_w[ci], K, 1LL * c->H * s.cout, n_tile, c->err, sizeof(c->err)))
         return false;
+    const long long pixels = n_imgs * s.hout * s.hout;
+    if (!sad::encode_pix_map(&L->out_map, out, s.cout, pixels, 32, c->err, sizeof(c->err))) return false;
+    if (!sad::encode_pix_map(&L->res_map, res ? res : out, s.cout, pixels, 128, c->err, sizeof(c->err))) return false;
     L->bias = c->d_bias[ci];
     L->residual = res;
     L->out = out;
@@ -360,6 +387,8 @@ bool make_stem_launch(sad_ctx* c, sad::ConvLaunch* L, const bf16* A, const bf16*
         return false;
     for (int i = 1; i < 4; ++i) L->a_map[i] = L->a_map[0];
     if (!sad::encode_weight_map(&L->b_map, w, Kpad, 1LL * c->H * 64, 64, c->err, sizeof(c->err))) return false;
+    if (!sad::encode_pix_map(&L->out_map, c->d_stem, 64, 1LL * c->H * c->Bc * 65536, 32, c->err, sizeof(c->err))) return false;
+    L->res_map = L->out_map;
     L->bias = c->d_bias[0];
     L->residual = nullptr;
     L->out = c->d_stem;
@@ -380,6 +409,13 @@ bool make_stem_launch(sad_ctx* c, sad::ConvLaunch* L, const bf16* A, const bf16*
 void set_batch(sad::ConvLaunch* L, int B, int H) {
     L->imgs_per_head = B;
     L->total_tiles = H * B * L->m_tiles_per_img * L->n_tiles;
+}
+
+bool is_rows_layer(int ci);
+cudaError_t launch_conv(sad_ctx* c, int ci, const sad::ConvLaunch& L, int heads, cudaStream_t st) {
+    if (ci > 0 && c->rows_mode && is_rows_layer(ci))
+        return sad::conv_rows_launch(L, heads, c->rows_mode == 1 ? 1 : 0, c->num_sms, st);
+    return sad::conv_umma_launch(L, c->num_sms, st);
 }
 
 // ---- default front-end constants (overridable through sad_set_frontend_constants) -------------------
@@ -526,6 +562,7 @@ int sad_create(sad_ctx** out, int device, int n_heads, int max_batch) {
     c->Bc = max_batch;
     c->num_sms = prop.multiProcessorCount;
     c->loaded.assign(n_heads, 0);
+    if (const char* e = getenv("SAD_CONV_ROWS")) c->rows_mode = atoi(e);
     *out = c;   // returned even on failure so the caller can read sad_last_error, then sad_destroy
     CU_OK(c, cudaSetDevice(device));
 
@@ -565,14 +602,16 @@ int sad_create(sad_ctx** out, int device, int n_heads, int max_batch) {
     CU_OK(c, dalloc(&c->d_segmax, Bc));
     CU_OK(c, dalloc(&c->d_musig, Bc * 2));
     CU_OK(c, dalloc(&c->d_img, Bc * 512 * 512));
-    CU_OK(c, dalloc(&c->d_A1, Bc * 65536 * 64));
-    CU_OK(c, dalloc(&c->d_stem, HB * 65536 * 64));
     for (int i = 0; i < 3; ++i) CU_OK(c, dalloc(&c->d_buf[i], HB * 128 * 128 * 64));
     CU_OK(c, dalloc(&c->d_buf[BD], HB * 64 * 64 * 128));
     CU_OK(c, dalloc(&c->d_head_logits, HB * 2));
 
     // launch plan bound to the workspace
-    if (!make_stem_launch(c, &c->stem1, c->d_A1, c->d_w_stem1, 64)) return SAD_ECUDA;
+    memset(&c->stem1, 0, sizeof(c->stem1));
+    if (!sad::encode_weight_map(&c->stem1.w_map, c->d_w_stem1, 64, H * 64, 128, c->err, sizeof(c->err))) return SAD_ECUDA;
+    if (!sad::encode_pix_map(&c->stem1.out_map, c->d_buf[BX], 64, HB * 128 * 128, 32, c->err, sizeof(c->err))) return SAD_ECUDA;
+    c->stem1.img = c->d_img;
+    c->stem1.H = n_heads;
     c->plan = build_plan();
     c->plan_launch.resize(c->plan.size());
     for (size_t i = 0; i < c->plan.size(); ++i) {
@@ -600,7 +639,7 @@ int sad_destroy(sad_ctx* c) {
         cudaFree(c->d_bias[i]);
     }
     void* ptrs[] = {c->d_w_stem1, c->d_w_stem3, c->d_w1t, c->d_b1, c->d_w2t, c->d_b2, c->d_w3, c->d_b3, c->d_window,
-                    c->d_mel, c->d_resize, c->d_db, c->d_segmax, c->d_musig, c->d_img, c->d_A1, c->d_A3, c->d_stem,
+                    c->d_mel, c->d_resize, c->d_db, c->d_segmax, c->d_musig, c->d_img, c->d_A3, c->d_stem,
                     c->d_buf[0], c->d_buf[1], c->d_buf[2], c->d_buf[3], c->d_head_logits, c->d_pcm[0], c->d_pcm[1],
                     c->d_res_logits, c->d_res_probs, c->d_res_labels};
     for (void* p : ptrs) cudaFree(p);
@@ -650,7 +689,7 @@ int sad_load_weights(sad_ctx* c, int head, const float* const* T, int n_tensors)
             // stem, two packings: channel-summed K=49 (the reference's three input channels are identical,
             // inference_runner.py:173) and the general 3-channel K=147.
             std::vector<bf16> p1(64 * 64, to_bf16(0.0)), p3(64 * 192, to_bf16(0.0));
-            for (int o = 0; o < 64; ++o)
+            for (int o = 0; o < 64; ++o) {
                 for (int tap = 0; tap < 49; ++tap) {
                     double sum = 0.0;
                     for (int ch = 0; ch < 3; ++ch) {
@@ -658,8 +697,18 @@ int sad_load_weights(sad_ctx* c, int head, const float* const* T, int n_tensors)
                         sum += v;
                         p3[o * 192 + tap * 3 + ch] = to_bf16(v);
                     }
-                    p1[o * 64 + tap] = to_bf16(sum);
+                    p1[o * 64 + (tap / 7) * 8 + tap % 7] = to_bf16(sum);      // fused stem: k = ky*8 + kx
                 }
+                // folded BN shift as three bf16 terms against the constant {1,1,1} slots of the A tile (k = 56..58)
+                const float b = static_cast<float>(t[o]);
+                const bf16 hi = __float2bfloat16_rn(b);
+                const float r1 = b - __bfloat162float(hi);
+                const bf16 mid = __float2bfloat16_rn(r1);
+                const bf16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+                p1[o * 64 + 56] = hi;
+                p1[o * 64 + 57] = mid;
+                p1[o * 64 + 58] = lo;
+            }
             CU_OK(c, cudaMemcpy(c->d_w_stem1 + static_cast<size_t>(head) * 64 * 64, p1.data(), p1.size() * sizeof(bf16),
                                 cudaMemcpyHostToDevice));
             CU_OK(c, cudaMemcpy(c->d_w_stem3 + static_cast<size_t>(head) * 64 * 192, p3.data(),
@@ -779,6 +828,7 @@ int sad_forward_images(sad_ctx* c, const float* x, int B, float thr, float* logi
     CU_OK(c, cudaSetDevice(c->device));
     if (!c->stem3_ready) {
         CU_OK(c, dalloc(&c->d_A3, static_cast<size_t>(c->Bc) * 65536 * 192));
+        CU_OK(c, dalloc(&c->d_stem, static_cast<size_t>(c->H) * c->Bc * 65536 * 64));
         if (!make_stem_launch(c, &c->stem3, c->d_A3, c->d_w_stem3, 192)) return SAD_ECUDA;
         c->stem3_ready = true;
     }
@@ -884,7 +934,7 @@ int sad_debug_conv(sad_ctx* c, int head, int layer, const void* in, const void* 
         return SAD_ECUDA;
     L.bias = c->d_bias[layer] + static_cast<size_t>(head) * s.cout;
     set_batch(&L, B, 1);
-    CU_OK(c, sad::conv_umma_launch(L, c->num_sms, static_cast<cudaStream_t>(stream)));
+    CU_OK(c, launch_conv(c, layer, L, 1, static_cast<cudaStream_t>(stream)));
     c->launches += 1;
     return SAD_OK;
 }
@@ -911,6 +961,24 @@ int sad_profile_read(sad_ctx* c, double* ms_by_kind, long long* launches_by_kind
         if (ms_by_kind) ms_by_kind[i] = c->prof_ms[i];
         if (launches_by_kind) launches_by_kind[i] = c->prof_n[i];
     }
+    return SAD_OK;
+}
+
+int sad_debug_stem(sad_ctx* c, const float* pcm, int B, void* out, void* stream) {
+    if (!c || !pcm || !out || B < 1 || B > c->Bc) return SAD_EINVAL;
+    for (int h = 0; h < c->H; ++h)
+        if (!c->loaded[h]) return fail(c, SAD_ESTATE, "weights of head %d not loaded", h);
+    CU_OK(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU_OK(c, sad::frontend_logmel_launch(pcm, B, c->d_window, c->d_mel, c->d_db, c->d_segmax, nullptr, c->d_musig, st,
+                                         &c->launches));
+    CU_OK(c, sad::image_launch_bf16(c->d_db, c->d_musig, c->d_resize, c->d_img, B, st, &c->launches));
+    sad::StemLaunch sl = c->stem1;
+    sl.B = B;
+    CU_OK(c, sad::stem_fused_launch(sl, c->num_sms, st));
+    c->launches += 1;
+    c->last_B = B;
+    CU_OK(c, cudaMemcpyAsync(out, c->d_buf[BX], static_cast<size_t>(c->H) * B * 128 * 128 * 64 * 2, cudaMemcpyDeviceToDevice, st));
     return SAD_OK;
 }
 
@@ -946,29 +1014,33 @@ int run_chunk(sad_ctx* c, const float* pcm, const float* x_nchw, int B, float th
     if (B == 0) return SAD_OK;
     const int H = c->H;
     c->last_B = B;
-    sad::ConvLaunch stem;
     if (pcm) {
         {
             ProfScope ps(c, SAD_PROF_FRONTEND, st);
             CU_OK(c, sad::frontend_logmel_launch(pcm, B, c->d_window, c->d_mel, c->d_db, c->d_segmax, nullptr, c->d_musig, st,
                                                  &c->launches));
         }
-        ProfScope ps(c, SAD_PROF_IMAGE, st);
-        CU_OK(c, sad::image_launch_bf16(c->d_db, c->d_musig, c->d_resize, c->d_img, B, st, &c->launches));
-        CU_OK(c, sad::im2col_stem1_launch(c->d_img, c->d_A1, B, st, &c->launches));
-        stem = c->stem1;
-    } else {
-        ProfScope ps(c, SAD_PROF_IMAGE, st);
-        CU_OK(c, sad::im2col_stem3_launch(x_nchw, c->d_A3, B, st, &c->launches));
-        stem = c->stem3;
-    }
-    set_batch(&stem, B, H);
-    {
+        {
+            ProfScope ps(c, SAD_PROF_IMAGE, st);
+            CU_OK(c, sad::image_launch_bf16(c->d_db, c->d_musig, c->d_resize, c->d_img, B, st, &c->launches));
+        }
         ProfScope ps(c, 0, st);
-        CU_OK(c, sad::conv_umma_launch(stem, c->num_sms, st));
+        sad::StemLaunch sl = c->stem1;
+        sl.B = B;
+        CU_OK(c, sad::stem_fused_launch(sl, c->num_sms, st));
         c->launches += 1;
-    }
-    {
+    } else {
+        {
+            ProfScope ps(c, SAD_PROF_IMAGE, st);
+            CU_OK(c, sad::im2col_stem3_launch(x_nchw, c->d_A3, B, st, &c->launches));
+        }
+        sad::ConvLaunch stem = c->stem3;
+        set_batch(&stem, B, H);
+        {
+            ProfScope ps(c, 0, st);
+            CU_OK(c, sad::conv_umma_launch(stem, c->num_sms, st));
+            c->launches += 1;
+        }
         ProfScope ps(c, SAD_PROF_POOL, st);
         CU_OK(c, sad::maxpool_launch(c->d_stem, c->d_buf[BX], 1LL * H * B, st, &c->launches));
     }
@@ -976,7 +1048,7 @@ int run_chunk(sad_ctx* c, const float* pcm, const float* x_nchw, int B, float th
         sad::ConvLaunch L = c->plan_launch[i];
         set_batch(&L, B, H);
         ProfScope ps(c, c->plan[i].conv, st);
-        CU_OK(c, sad::conv_umma_launch(L, c->num_sms, st));
+        CU_OK(c, launch_conv(c, c->plan[i].conv, L, H, st));
         c->launches += 1;
     }
     sad::HeadWeights hw{c->d_w1t, c->d_b1, c->d_w2t, c->d_b2, c->d_w3, c->d_b3};

@@ -1,0 +1,295 @@
+// K3b: row-stationary 3x3 / stride-1 convolution for the 64-channel, 128x128 layer1 maps (tcgen05 + TMEM).
+//
+// Why a second kernel: with Cout = 64 the generic kernel (conv_umma.cu) needs a fresh 16 KB A tile from L2 every
+// 128 tensor cycles -- 9 TMA fetches of (almost) the same input rows per output tile -- and measures 27% of the
+// tensor peak, exactly the unique-data L2->SM bandwidth (~35 B/clk/SM).  Here every input row is fetched ONCE:
+//
+//   smem:  weights of the current head, 9 taps x [64 co][64 ci] bf16 (72 KB, SWIZZLE_128B, resident)
+//          ring of kRing halo'd input rows: one TMA box {64 ch, 130 px (x = -1..128), 1 row} = 130 x 128 B each;
+//          the zero padding (x = -1, 128 and rows -1, 128) is TMA out-of-bounds fill.
+//   MMA :  output row y = sum over taps (ky,kx) of  A = 128 consecutive smem rows of input row y+ky-1 starting at
+//          pixel kx (a descriptor whose start address is shifted by kx*128 B, "matrix base offset" = kx), times
+//          B = tap weights.  36 UMMAs (128x64x16) per output row into a double-buffered TMEM accumulator.
+//   work:  unit = (head, image, strip of 32 output rows); persistent CTAs walk units round-robin; weights are
+//          re-fetched only when the head changes.
+//
+// Replaces, for layer1.{0,1}.conv{1,2}, the conv2d+batch_norm(+add)+relu of timm's BasicBlock inside
+// BinaryClassifier.forward (reference modular/source/inference_runner.py:49-51).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "conv_umma.h"
+#include "ptx.cuh"
+
+namespace sad {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kW = 128;                       // output / input width and height of layer1
+constexpr int kStripRows = 32;
+constexpr int kStripsPerImg = kW / kStripRows;
+constexpr int kRowBox = kW + 2;               // 130 pixels incl. the halo
+constexpr int kRowBytes = kRowBox * 128;      // 16640 B written by one TMA box
+constexpr int kSlotBytes = 17 * 1024;         // slot pitch (1024-aligned so the swizzle phase of pixel p is p mod 8)
+constexpr int kRing = 5;
+constexpr int kTapBytes = 64 * 128;           // one tap's [64 co][64 ci] bf16
+constexpr int kWBytes = 9 * kTapBytes;        // 72 KB
+constexpr int kTileBytes = 128 * 128;         // one output / residual tile: 128 px x 64 ch bf16
+constexpr int kResRing = 2;
+constexpr int kOutBytes = 4 * 2 * 4096;       // per epilogue warp: 2 staging buffers of 32 px x 128 B
+constexpr int kSmemBytes = kWBytes + kRing * kSlotBytes + kResRing * kTileBytes + kOutBytes + 1024 + 256;
+constexpr int kTmemCols = 128;                // 2 accumulators x 64 columns
+
+// Descriptor for 128 rows starting at a 128-byte-aligned (not 1024-aligned) address inside a SWIZZLE_128B region.
+// MEASURED on B200: the tensor core applies the 128B swizzle to the ABSOLUTE shared-memory address bits (like TMA
+// does when it writes), so a shifted start needs NO "matrix base offset" (bits 49-51 stay 0); setting it to
+// (addr >> 7) & 7 gives wrong results (tests/test_gpu_conv.py with SAD_CONV_ROWS=1 vs 2).
+__device__ __forceinline__ uint64_t desc_shifted(uint32_t addr, int base_offset_mode) {
+    uint64_t d = umma_desc_sw128(addr);
+    if (base_offset_mode) d |= static_cast<uint64_t>((addr >> 7) & 7u) << 49;
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_rows_kernel(const __grid_constant__ ConvLaunch p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* wsm = smem;
+    uint8_t* ring = smem + kWBytes;
+    uint8_t* res_sm = ring + kRing * kSlotBytes;            // [kResRing][128 px][128 B] swizzled (TMA load)
+    uint8_t* out_sm = res_sm + kResRing * kTileBytes;       // [4 warps][2][32 px][128 B] swizzled (TMA store)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_sm + kOutBytes);
+    uint64_t* in_full = bars;                   // [kRing]
+    uint64_t* in_empty = bars + kRing;          // [kRing]
+    uint64_t* w_full = bars + 2 * kRing;        // [1]
+    uint64_t* w_empty = w_full + 1;             // [1]
+    uint64_t* tmem_full = w_empty + 1;          // [2]
+    uint64_t* tmem_empty = tmem_full + 2;       // [2]
+    uint64_t* res_full = tmem_empty + 2;        // [kResRing]
+    uint64_t* res_empty = res_full + kResRing;  // [kResRing]
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_empty + kResRing);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.a_map[0]);
+        tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.out_map);
+        tma_prefetch_desc(&p.res_map);
+        for (int s = 0; s < kResRing; ++s) {
+            mbar_init(&res_full[s], 1);
+            mbar_init(&res_empty[s], 4);
+        }
+        for (int s = 0; s < kRing; ++s) {
+            mbar_init(&in_full[s], 1);
+            mbar_init(&in_empty[s], 1);
+        }
+        mbar_init(w_full, 1);
+        mbar_init(w_empty, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_base_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    const int units_per_head = p.imgs_per_head * kStripsPerImg;
+    const int total_units = p.total_tiles;      // heads * imgs * strips
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int cur_head = -1;
+            uint32_t w_loads = 0;
+            uint32_t seq = 0;                   // input rows loaded so far (ring position)
+            uint32_t rseq = 0;                  // residual tiles loaded so far
+            const bool has_res = p.residual != nullptr;
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                const int head = u / units_per_head;
+                const int r = u - head * units_per_head;
+                const int img = head * p.imgs_per_head + r / kStripsPerImg;
+                const int y0 = (r % kStripsPerImg) * kStripRows;
+                if (head != cur_head) {
+                    mbar_wait(w_empty, (w_loads & 1) ^ 1);      // previous head's MMAs have drained
+                    mbar_expect_tx(w_full, kWBytes);
+                    for (int tap = 0; tap < 9; ++tap)
+                        tma_load_2d(wsm + tap * kTapBytes, &p.b_map, w_full, tap * 64, head * 64);
+                    ++w_loads;
+                    cur_head = head;
+                }
+                for (int iy = y0 - 1; iy <= y0 + kStripRows; ++iy, ++seq) {
+                    const int slot = seq % kRing;
+                    mbar_wait(&in_empty[slot], ((seq / kRing) & 1) ^ 1);
+                    mbar_expect_tx(&in_full[slot], kRowBytes);
+                    tma_load_4d(ring + slot * kSlotBytes, &p.a_map[0], &in_full[slot], 0, -1, iy, img);
+                    if (has_res && iy >= y0 + 1) {          // residual tile of output row iy-1 (needed last)
+                        const int rs = rseq % kResRing;
+                        mbar_wait(&res_empty[rs], ((rseq / kResRing) & 1) ^ 1);
+                        mbar_expect_tx(&res_full[rs], kTileBytes);
+                        tma_load_2d(res_sm + rs * kTileBytes, &p.res_map, &res_full[rs], 0, (img * kW + (iy - 1)) * kW);
+                        ++rseq;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ UMMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+            const uint32_t w_addr = smem_u32(wsm);
+            const uint32_t ring_addr = smem_u32(ring);
+            int cur_head = -1;
+            uint32_t w_loads = 0;
+            uint32_t seq0 = 0;                  // ring position of the unit's first input row (y0-1)
+            uint32_t waited = 0;                // rows [0, waited) of the global sequence are known to have landed
+            uint32_t tile = 0;
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                const int head = u / units_per_head;
+                if (head != cur_head) {
+                    if (cur_head >= 0) umma_commit(w_empty);   // all MMAs that read the old weights are done
+                    mbar_wait(w_full, w_loads & 1);
+                    ++w_loads;
+                    cur_head = head;
+                }
+                for (int j = 0; j < kStripRows; ++j, ++tile) {
+                    // rows seq0+j, +1, +2 must be resident
+                    while (waited < seq0 + j + 3) {
+                        mbar_wait(&in_full[waited % kRing], (waited / kRing) & 1);
+                        ++waited;
+                    }
+                    const int acc = tile & 1;
+                    mbar_wait(&tmem_empty[acc], ((tile >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * 64;
+                    uint32_t first = 1;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const uint32_t row_addr = ring_addr + ((seq0 + j + ky) % kRing) * kSlotBytes;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const uint64_t adesc = desc_shifted(row_addr + kx * 128, p.shared_input /*mode flag*/);
+                            const uint64_t bdesc = umma_desc_sw128(w_addr + (ky * 3 + kx) * kTapBytes);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
+                                first = 0;
+                            }
+                        }
+                    }
+                    umma_commit(&in_empty[(seq0 + j) % kRing]);          // input row y-1 is no longer needed
+                    if (j == kStripRows - 1) {
+                        umma_commit(&in_empty[(seq0 + j + 1) % kRing]);
+                        umma_commit(&in_empty[(seq0 + j + 2) % kRing]);
+                    }
+                    umma_commit(&tmem_full[acc]);
+                }
+                seq0 += kStripRows + 2;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // TMEM -> registers -> (+bias, +residual from smem, ReLU, bf16) -> swizzled smem -> TMA store.  Each warp owns
+        // the 32 pixels of its TMEM lane quarter and two private 4 KB staging buffers, so no cross-warp barrier.
+        const int quarter = warp & 3;
+        uint8_t* my_out = out_sm + quarter * 2 * 4096;
+        const bool has_res = p.residual != nullptr;
+        uint32_t tile = 0;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            const int head = u / units_per_head;
+            const int r = u - head * units_per_head;
+            const int img = head * p.imgs_per_head + r / kStripsPerImg;
+            const int y0 = (r % kStripsPerImg) * kStripRows;
+            const float4* bias4 = reinterpret_cast<const float4*>(p.bias + head * 64);
+            for (int j = 0; j < kStripRows; ++j, ++tile) {
+                const int acc = tile & 1;
+                mbar_wait(&tmem_full[acc], (tile >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 64;
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr, v0);
+                tmem_ld32(taddr + 32, v1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);             // accumulator is in registers: release it
+                const int rs = tile % kResRing;
+                if (has_res) mbar_wait(&res_full[rs], (tile / kResRing) & 1);
+                if (lane == 0) tma_store_wait_read<1>();                  // staging buffer (tile & 1) is free again
+                __syncwarp();
+                uint8_t* stage = my_out + (tile & 1) * 4096;
+                const uint8_t* res_row = res_sm + rs * kTileBytes;
+                const int prow = quarter * 32 + lane;                     // pixel row inside the 128-px tile
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {                          // 8 channels = one 16-byte chunk
+                    const uint32_t* v = ch < 4 ? v0 : v1;
+                    const int o = (ch & 3) * 8;
+                    const float4 b0 = __ldg(bias4 + ch * 2), b1 = __ldg(bias4 + ch * 2 + 1);
+                    float f[8] = {__uint_as_float(v[o + 0]) + b0.x, __uint_as_float(v[o + 1]) + b0.y,
+                                  __uint_as_float(v[o + 2]) + b0.z, __uint_as_float(v[o + 3]) + b0.w,
+                                  __uint_as_float(v[o + 4]) + b1.x, __uint_as_float(v[o + 5]) + b1.y,
+                                  __uint_as_float(v[o + 6]) + b1.z, __uint_as_float(v[o + 7]) + b1.w};
+                    if (has_res) {
+                        const uint4 rr = *reinterpret_cast<const uint4*>(res_row + sw128_offset(prow, ch));
+                        const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            f[2 * q] += __uint_as_float(rw[q] << 16);
+                            f[2 * q + 1] += __uint_as_float(rw[q] & 0xFFFF0000u);
+                        }
+                    }
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float a0 = f[2 * q], a1 = f[2 * q + 1];
+                        if (p.relu) {
+                            a0 = fmaxf(a0, 0.f);
+                            a1 = fmaxf(a1, 0.f);
+                        }
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(a0, a1);
+                        pk[q] = *reinterpret_cast<uint32_t*>(&b2);
+                    }
+                    *reinterpret_cast<uint4*>(stage + sw128_offset(lane, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (has_res) mbar_arrive(&res_empty[rs]);
+                    tma_store_2d(&p.out_map, stage, 0, (img * kW + (y0 + j)) * kW + quarter * 32);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+}  // namespace
+
+// `p` as built for the generic kernel, except: a_map[0] must have box {64, 130, 1, 1}; total_tiles is recomputed
+// here as the number of (head, image, strip) units; p.shared_input is reused as the base-offset mode flag.
+cudaError_t conv_rows_launch(const ConvLaunch& p_in, int heads, int base_offset_mode, int num_sms, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    ConvLaunch p = p_in;
+    p.total_tiles = heads * p.imgs_per_head * kStripsPerImg;
+    p.shared_input = base_offset_mode;
+    const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+    conv_rows_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace sad

@@ -40,9 +40,12 @@ template <int N_TILE>
 struct Cfg {
     static constexpr int kBBytes = N_TILE * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+    // epilogue staging: per epilogue warp kOutBufs buffers of [32 px][64 ch] bf16 (4 KB, SWIZZLE_128B) for TMA stores
+    static constexpr int kOutBufs = N_TILE == 256 ? 1 : 2;
+    static constexpr int kOutBytes = 4 * kOutBufs * 4096;
+    static constexpr int kStages = ((208 * 1024 - kOutBytes) / kStageBytes) > 8 ? 8 : ((208 * 1024 - kOutBytes) / kStageBytes);
     static constexpr int kTmemCols = 2 * N_TILE < 32 ? 32 : 2 * N_TILE;   // 128 / 256 / 512: powers of two
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int N_TILE>
@@ -51,7 +54,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* tiles = smem;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint8_t* out_sm = smem + C::kStages * C::kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_sm + C::kOutBytes);
     uint64_t* full_bar = bars;                      // [kStages]
     uint64_t* empty_bar = bars + C::kStages;        // [kStages]
     uint64_t* tmem_full = bars + 2 * C::kStages;    // [2]
@@ -64,6 +68,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
         tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.out_map);
         for (int s = 0; s < C::kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -152,9 +157,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // Per 64-channel block: TMEM -> registers -> +bias (+residual) -> ReLU -> bf16 -> swizzled smem staging ->
+        // one TMA store of [32 px][64 ch] per warp (fully coalesced; a lane writing its own 128-byte pixel row
+        // straight to global touches 32 lines per store instruction and made the epilogue the bottleneck).
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;          // pixel inside the 128-pixel tile
+        uint8_t* my_out = out_sm + quarter * C::kOutBufs * 4096;
         int it = 0;
+        uint32_t nstore = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const int head = tile / tiles_per_head;
             int r = tile - head * tiles_per_head;
@@ -163,57 +173,73 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             const int m_t = r % p.m_tiles_per_img;
             const int img = r / p.m_tiles_per_img;
             const int acc = it & 1;
-            const long long pix =
-                (static_cast<long long>(head) * p.imgs_per_head + img) * (p.m_tiles_per_img * kBlockM) +
-                m_t * kBlockM + row;
+            const long long pix0 =
+                (static_cast<long long>(head) * p.imgs_per_head + img) * (p.m_tiles_per_img * kBlockM) + m_t * kBlockM;
             const int co0 = n_t * N_TILE;
-            const float* bias = p.bias + head * p.Cout + co0;
-            __nv_bfloat16* out = p.out + pix * p.Cout + co0;
-            const __nv_bfloat16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+            const float4* bias4 = reinterpret_cast<const float4*>(p.bias + head * p.Cout + co0);
+            const __nv_bfloat16* res = p.residual ? p.residual + (pix0 + row) * p.Cout + co0 : nullptr;
 
             mbar_wait(&tmem_full[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * N_TILE;
 #pragma unroll 1
-            for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                tmem_ld_wait();
-                uint4 rv[4];
+            for (int c0 = 0; c0 < N_TILE; c0 += 64, ++nstore) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr + c0, v0);
+                tmem_ld32(taddr + c0 + 32, v1);
+                uint4 rv[8];
                 if (res) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(res + c0) + q);
+                    for (int q = 0; q < 8; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(res + c0) + q);
                 }
-                uint4 ov[4];
+                tmem_ld_wait();
+                if (c0 + 64 >= N_TILE) {              // whole accumulator is in registers: hand TMEM back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                }
+                if (lane == 0) tma_store_wait_read<C::kOutBufs - 1>();
+                __syncwarp();
+                uint8_t* stage = my_out + (nstore % C::kOutBufs) * 4096;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t packed[4];
+                for (int ch = 0; ch < 8; ++ch) {      // 8 channels = one 16-byte chunk
+                    const uint32_t* v = ch < 4 ? v0 : v1;
+                    const int o = (ch & 3) * 8;
+                    const float4 b0 = __ldg(bias4 + (c0 >> 2) + ch * 2), b1 = __ldg(bias4 + (c0 >> 2) + ch * 2 + 1);
+                    float f[8] = {__uint_as_float(v[o + 0]) + b0.x, __uint_as_float(v[o + 1]) + b0.y,
+                                  __uint_as_float(v[o + 2]) + b0.z, __uint_as_float(v[o + 3]) + b0.w,
+                                  __uint_as_float(v[o + 4]) + b1.x, __uint_as_float(v[o + 5]) + b1.y,
+                                  __uint_as_float(v[o + 6]) + b1.z, __uint_as_float(v[o + 7]) + b1.w};
+                    if (res) {
+                        const uint32_t rw[4] = {rv[ch].x, rv[ch].y, rv[ch].z, rv[ch].w};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int c = q * 8 + j * 2;
-                        float x0 = __uint_as_float(v[c]) + __ldg(bias + c0 + c);
-                        float x1 = __uint_as_float(v[c + 1]) + __ldg(bias + c0 + c + 1);
-                        if (res) {
-                            const uint32_t rr = reinterpret_cast<const uint32_t*>(&rv[q])[j];
-                            x0 += __uint_as_float(rr << 16);
-                            x1 += __uint_as_float(rr & 0xFFFF0000u);
+                        for (int q = 0; q < 4; ++q) {
+                            f[2 * q] += __uint_as_float(rw[q] << 16);
+                            f[2 * q + 1] += __uint_as_float(rw[q] & 0xFFFF0000u);
                         }
-                        if (p.relu) {
-                            x0 = fmaxf(x0, 0.f);
-                            x1 = fmaxf(x1, 0.f);
-                        }
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(x0, x1);
-                        packed[j] = *reinterpret_cast<uint32_t*>(&b2);
                     }
-                    ov[q] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                }
+                    uint32_t pk[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(out + c0)[q] = ov[q];
+                    for (int q = 0; q < 4; ++q) {
+                        float a0 = f[2 * q], a1 = f[2 * q + 1];
+                        if (p.relu) {
+                            a0 = fmaxf(a0, 0.f);
+                            a1 = fmaxf(a1, 0.f);
+                        }
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(a0, a1);
+                        pk[q] = *reinterpret_cast<uint32_t*>(&b2);
+                    }
+                    *reinterpret_cast<uint4*>(stage + sw128_offset(lane, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&p.out_map, stage, co0 + c0, static_cast<int>(pix0) + quarter * 32);
+                    tma_store_commit();
+                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (lane == 0) tma_store_wait<0>();
     }
 
     tc_fence_before();

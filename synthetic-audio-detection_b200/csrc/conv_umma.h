@@ -9,6 +9,8 @@ namespace sad {
 struct alignas(64) ConvLaunch {
     CUtensorMap a_map[4];   // input views; stride 1 uses [0] (all four equal), stride 2 uses parity (py*2+px)
     CUtensorMap b_map;      // packed weights [heads*Cout][taps*Cin] bf16, K-major
+    CUtensorMap out_map;    // output viewed as {Cout, pixels}: box {64 ch, 32 px}, SWIZZLE_128B (TMA store)
+    CUtensorMap res_map;    // residual viewed as {Cout, pixels}: box {64 ch, 128 px} (TMA load); valid iff residual
     const float* bias;      // [heads*Cout] fp32 (folded BN shift)
     const __nv_bfloat16* residual;   // NHWC [heads*imgs][Ho*Wo][Cout] or nullptr
     __nv_bfloat16* out;     // NHWC [heads*imgs][Ho*Wo][Cout]
@@ -32,6 +34,8 @@ cudaError_t conv_umma_launch(const ConvLaunch& p, int num_sms, cudaStream_t stre
 // 4-D NHWC bf16 activation view: dims {C, W, H, N}; element (c,x,y,n) at base + c + x*sx + y*sy + n*sn (elements).
 bool encode_act_map(CUtensorMap* m, const void* base, int C, int W, int H, long long N, long long sx, long long sy,
                     long long sn, int box_w, int box_h, char* err, int errlen);
+// 2-D pixel-major view of an NHWC tensor: dims {C, pixels}; box {64 ch, box_px}.
+bool encode_pix_map(CUtensorMap* m, const void* base, int C, long long pixels, int box_px, char* err, int errlen);
 // 2-D weight view: dims {K, rows}; box {64, box_rows}.
 bool encode_weight_map(CUtensorMap* m, const void* base, long long K, long long rows, int box_rows, char* err,
                        int errlen);

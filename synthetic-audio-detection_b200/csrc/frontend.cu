@@ -231,37 +231,6 @@ __global__ void __launch_bounds__(256) image_kernel(const float* __restrict__ db
     }
 }
 
-// Stem im2col for the single-channel image: A[img][oy*256+ox][k], k = ky*7+kx (49 real taps, zero to 64),
-// value = image[2*oy+ky-3][2*ox+kx-3] (zero outside).  One thread per 16-byte chunk (8 taps).
-__global__ void __launch_bounds__(256) im2col_stem1_kernel(const __nv_bfloat16* __restrict__ img,
-                                                           __nv_bfloat16* __restrict__ A, long long n_chunks) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n_chunks) return;
-    const int chunk = static_cast<int>(i & 7);
-    const long long pix = i >> 3;
-    const int ox = static_cast<int>(pix & 255);
-    const int oy = static_cast<int>((pix >> 8) & 255);
-    const long long b = pix >> 16;
-    const unsigned short* src = reinterpret_cast<const unsigned short*>(img) + b * 512 * 512;
-    unsigned short v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int k = chunk * 8 + j;
-        unsigned short val = 0;
-        if (k < 49) {
-            const int iy = 2 * oy + k / 7 - 3, ix = 2 * ox + k % 7 - 3;
-            if (iy >= 0 && iy < 512 && ix >= 0 && ix < 512) val = src[iy * 512 + ix];
-        }
-        v[j] = val;
-    }
-    uint4 o;
-    o.x = v[0] | (static_cast<unsigned>(v[1]) << 16);
-    o.y = v[2] | (static_cast<unsigned>(v[3]) << 16);
-    o.z = v[4] | (static_cast<unsigned>(v[5]) << 16);
-    o.w = v[6] | (static_cast<unsigned>(v[7]) << 16);
-    reinterpret_cast<uint4*>(A)[i] = o;
-}
-
 // Stem im2col for a generic 3-channel NCHW fp32 image: k = (ky*7+kx)*3 + c (147 real taps, zero to 192).
 __global__ void __launch_bounds__(256) im2col_stem3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ A,
                                                            long long n_chunks) {
@@ -392,12 +361,6 @@ cudaError_t image_launch_f32(const float* db, const float* mu_sigma, const Resiz
 cudaError_t image_launch_bf16(const float* db, const float* mu_sigma, const ResizeTable* rt, __nv_bfloat16* img, int B,
                               cudaStream_t stream, long long* launches) {
     image_kernel<__nv_bfloat16><<<dim3(512, B), 256, 0, stream>>>(db, mu_sigma, rt, img);
-    if (launches) *launches += 1;
-    return cudaGetLastError();
-}
-cudaError_t im2col_stem1_launch(const __nv_bfloat16* img, __nv_bfloat16* A, int B, cudaStream_t stream, long long* launches) {
-    const long long n = static_cast<long long>(B) * 65536 * 8;
-    im2col_stem1_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(img, A, n);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

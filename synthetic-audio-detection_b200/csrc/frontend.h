@@ -34,8 +34,6 @@ cudaError_t image_launch_f32(const float* db, const float* mu_sigma, const Resiz
                              cudaStream_t stream, long long* launches);
 cudaError_t image_launch_bf16(const float* db, const float* mu_sigma, const ResizeTable* rt, __nv_bfloat16* img, int B,
                               cudaStream_t stream, long long* launches);
-cudaError_t im2col_stem1_launch(const __nv_bfloat16* img, __nv_bfloat16* A, int B, cudaStream_t stream,
-                                long long* launches);
 cudaError_t im2col_stem3_launch(const float* x, __nv_bfloat16* A, int B, cudaStream_t stream, long long* launches);
 cudaError_t maxpool_launch(const __nv_bfloat16* in, __nv_bfloat16* out, long long n_img, cudaStream_t stream,
                            long long* launches);

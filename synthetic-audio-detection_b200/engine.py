@@ -203,6 +203,15 @@ class Engine:
                                                      int(relu), _stream(self.device)), "sad_debug_conv")
         return out
 
+    def debug_stem(self, pcm: torch.Tensor) -> torch.Tensor:
+        """Pooled stem output [H*B,128,128,64] bf16 for pcm [B,128000] (B <= max_batch)."""
+        self._check(pcm, (SEGMENT,))
+        B = pcm.shape[0]
+        out = torch.empty(self.n_heads * B, 128, 128, 64, device=self.device, dtype=torch.bfloat16)
+        _lib.check(self.ctx, self.lib.sad_debug_stem(self.ctx, _ptr(pcm), B, _ptr(out), _stream(self.device)),
+                   "sad_debug_stem")
+        return out
+
     def debug_read(self, which: int, shape, dtype) -> torch.Tensor:
         out = torch.empty(shape, device=self.device, dtype=dtype)
         n = self.lib.sad_debug_read(self.ctx, which, _ptr(out), out.numel() * out.element_size(), _stream(self.device))

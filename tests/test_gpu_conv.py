@@ -57,3 +57,31 @@ def test_conv_layer(idx, head):
     bad = (err > tol).float().mean().item()
     print(f"{name}: max abs err {err.max():.4f} (|want| max {want.abs().max():.2f}), frac out of tol {bad:.2e}")
     assert bad == 0.0
+
+
+def test_fused_stem_and_pool():
+    """K2 (conv 7x7/2 + BN + ReLU + maxpool 3x3/2 fused, 1-channel folded stem) vs torch fp32 conv/pool fed with the
+    SAME bf16 image and bf16 folded weights the device uses."""
+    from oracle import restatement as R
+    n_heads = 2
+    sd = G.merged_sd(n_heads)
+    e = G.engine(n_heads)
+    x = FX.synth_segments(3, first=700)
+    got = e.debug_stem(x.cuda())
+    img = e.debug_read(0, (3, 512, 512), torch.bfloat16)
+    torch.cuda.synchronize()
+    img = img.float().cpu()
+    want_img = R.waveform_to_image(x)
+    assert (img - want_img).abs().max() <= 2.0 ** -8 * want_img.abs().max() + 1e-3      # bf16 rounding of the image
+    got = got.float().cpu().view(n_heads, 3, 128, 128, 64)
+    for h in range(n_heads):
+        p = f"sub_models.{h}.base."
+        w, b = E.fold_bn(sd[p + "conv1.weight"], sd, p + "bn1")
+        w1 = w.sum(dim=1, keepdim=True).to(torch.bfloat16).float()
+        y = F.max_pool2d(F.relu(F.conv2d(img.unsqueeze(1), w1, b, stride=2, padding=3)), 3, 2, 1)
+        want = y.permute(0, 2, 3, 1)
+        err = (got[h] - want).abs()
+        tol = 2.0 ** -7 * want.abs() + 2e-2
+        print(f"stem head {h}: max abs err {err.max():.4f} (|want| max {want.abs().max():.2f}), "
+              f"frac out of tol {(err > tol).float().mean():.2e}")
+        assert (err > tol).float().mean() == 0.0
