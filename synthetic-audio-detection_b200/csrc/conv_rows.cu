@@ -1,15 +1,22 @@
 // K3b: row-stationary 3x3 / stride-1 convolution for the 64-channel, 128x128 layer1 maps (tcgen05 + TMEM).
 //
 // Why a second kernel: with Cout = 64 the generic kernel (conv_umma.cu) needs a fresh 16 KB A tile from L2 every
-// 128 tensor cycles -- 9 TMA fetches of (almost) the same input rows per output tile -- and measures 27% of the
-// tensor peak, exactly the unique-data L2->SM bandwidth (~35 B/clk/SM).  Here every input row is fetched ONCE:
+// 128 tensor cycles -- 9 TMA fetches of (almost) the same input rows per output tile -- and measured 27% of the
+// tensor peak, exactly the unique-data L2->SM bandwidth (~35 B/clk/SM).  A first row-stationary version (one
+// 128x64x16 UMMA per tap and k-step, 36 per output row) reached 47%: with N = 64 the tensor core is fed 6 KB of
+// shared-memory operands per 32-cycle instruction and the operand fetch (~70 B/clk measured) becomes the limit.
+// This version folds the three VERTICAL taps into N:
 //
-//   smem:  weights of the current head, 9 taps x [64 co][64 ci] bf16 (72 KB, SWIZZLE_128B, resident)
-//          ring of kRing halo'd input rows: one TMA box {64 ch, 130 px (x = -1..128), 1 row} = 130 x 128 B each;
-//          the zero padding (x = -1, 128 and rows -1, 128) is TMA out-of-bounds fill.
-//   MMA :  output row y = sum over taps (ky,kx) of  A = 128 consecutive smem rows of input row y+ky-1 starting at
-//          pixel kx (a descriptor whose start address is shifted by kx*128 B, "matrix base offset" = kx), times
-//          B = tap weights.  36 UMMAs (128x64x16) per output row into a double-buffered TMEM accumulator.
+//   smem:  weights of the current head as 3 (kx) x [192 = 3 ky x 64 co][64 ci] bf16 (72 KB, SWIZZLE_128B, resident)
+//          ring of halo'd input rows: one TMA box {64 ch, 130 px (x = -1..128), 1 row} = 130 x 128 B each; the
+//          zero padding (x = -1, 128 and rows -1, 128) is TMA out-of-bounds fill.  Each row is fetched ONCE.
+//   MMA :  input row i, horizontal tap kx:  A = 128 consecutive smem rows starting at pixel kx (descriptor start
+//          shifted by kx*128 B), B = [ky*64+co][ci]  ->  D[x][ky*64+co] = contribution of input row i to output row
+//          i-ky.  TMEM is a ring of 8 accumulators of 64 columns, output row T at slot (-T mod 8), so the three
+//          destinations (T, T-1, T-2) are CONSECUTIVE columns and one UMMA 128x192x16 serves all three
+//          (12 UMMAs per input row instead of 36; 120 KB instead of 216 KB of operand reads per output row).
+//          All UMMAs accumulate; the epilogue hands a block back zeroed (tcgen05.st).
+//   epilogue: TMEM -> +bias (+residual, TMA-loaded to smem) -> ReLU -> bf16 -> swizzled smem -> TMA store.
 //   work:  unit = (head, image, strip of 32 output rows); persistent CTAs walk units round-robin; weights are
 //          re-fetched only when the head changes.
 //
@@ -29,43 +36,49 @@ constexpr int kThreads = 192;
 constexpr int kW = 128;                       // output / input width and height of layer1
 constexpr int kStripRows = 32;
 constexpr int kStripsPerImg = kW / kStripRows;
+constexpr int kInRows = kStripRows + 2;       // input rows per unit
 constexpr int kRowBox = kW + 2;               // 130 pixels incl. the halo
 constexpr int kRowBytes = kRowBox * 128;      // 16640 B written by one TMA box
 constexpr int kSlotBytes = 17 * 1024;         // slot pitch (1024-aligned so the swizzle phase of pixel p is p mod 8)
-constexpr int kRing = 5;
-constexpr int kTapBytes = 64 * 128;           // one tap's [64 co][64 ci] bf16
+constexpr int kRing = 4;
+constexpr int kTapBytes = 64 * 128;           // one (kx,ky) block: [64 co][64 ci] bf16
 constexpr int kWBytes = 9 * kTapBytes;        // 72 KB
 constexpr int kTileBytes = 128 * 128;         // one output / residual tile: 128 px x 64 ch bf16
-constexpr int kResRing = 2;
+constexpr int kResRing = 3;
 constexpr int kOutBytes = 4 * 2 * 4096;       // per epilogue warp: 2 staging buffers of 32 px x 128 B
-constexpr int kSmemBytes = kWBytes + kRing * kSlotBytes + kResRing * kTileBytes + kOutBytes + 1024 + 256;
-constexpr int kTmemCols = 128;                // 2 accumulators x 64 columns
+constexpr int kSmemBytes = kWBytes + kRing * kSlotBytes + kResRing * kTileBytes + kOutBytes + 1024 + 512;
+constexpr int kAccSlots = 8;
+constexpr int kTmemCols = 512;                // 8 accumulators x 64 columns
 
-// Descriptor for 128 rows starting at a 128-byte-aligned (not 1024-aligned) address inside a SWIZZLE_128B region.
 // MEASURED on B200: the tensor core applies the 128B swizzle to the ABSOLUTE shared-memory address bits (like TMA
-// does when it writes), so a shifted start needs NO "matrix base offset" (bits 49-51 stay 0); setting it to
-// (addr >> 7) & 7 gives wrong results (tests/test_gpu_conv.py with SAD_CONV_ROWS=1 vs 2).
-__device__ __forceinline__ uint64_t desc_shifted(uint32_t addr, int base_offset_mode) {
-    uint64_t d = umma_desc_sw128(addr);
-    if (base_offset_mode) d |= static_cast<uint64_t>((addr >> 7) & 7u) << 49;
-    return d;
+// does when it writes), so a descriptor whose start is shifted by whole 128-byte rows needs NO "matrix base offset"
+// (bits 49-51 stay 0); setting it to (addr >> 7) & 7 gives wrong results.
+
+__device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+        "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(taddr),
+        "r"(0u)
+        : "memory");
 }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 __global__ void __launch_bounds__(kThreads, 1) conv_rows_kernel(const __grid_constant__ ConvLaunch p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* wsm = smem;
+    uint8_t* wsm = smem;                                    // [kx][ky][64 co][128 B]
     uint8_t* ring = smem + kWBytes;
     uint8_t* res_sm = ring + kRing * kSlotBytes;            // [kResRing][128 px][128 B] swizzled (TMA load)
     uint8_t* out_sm = res_sm + kResRing * kTileBytes;       // [4 warps][2][32 px][128 B] swizzled (TMA store)
     uint64_t* bars = reinterpret_cast<uint64_t*>(out_sm + kOutBytes);
     uint64_t* in_full = bars;                   // [kRing]
-    uint64_t* in_empty = bars + kRing;          // [kRing]
-    uint64_t* w_full = bars + 2 * kRing;        // [1]
+    uint64_t* in_empty = in_full + kRing;       // [kRing]
+    uint64_t* w_full = in_empty + kRing;        // [1]
     uint64_t* w_empty = w_full + 1;             // [1]
-    uint64_t* tmem_full = w_empty + 1;          // [2]
-    uint64_t* tmem_empty = tmem_full + 2;       // [2]
-    uint64_t* res_full = tmem_empty + 2;        // [kResRing]
+    uint64_t* acc_full = w_empty + 1;           // [kAccSlots]  output row complete (tcgen05.commit)
+    uint64_t* acc_empty = acc_full + kAccSlots; // [kAccSlots]  block read out and zeroed (4 epilogue warps)
+    uint64_t* res_full = acc_empty + kAccSlots; // [kResRing]
     uint64_t* res_empty = res_full + kResRing;  // [kResRing]
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_empty + kResRing);
 
@@ -87,9 +100,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_rows_kernel(const __grid_con
         }
         mbar_init(w_full, 1);
         mbar_init(w_empty, 1);
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);
+        for (int a = 0; a < kAccSlots; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 4);
         }
         fence_barrier_init();
     }
@@ -118,21 +131,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_rows_kernel(const __grid_con
                 if (head != cur_head) {
                     mbar_wait(w_empty, (w_loads & 1) ^ 1);      // previous head's MMAs have drained
                     mbar_expect_tx(w_full, kWBytes);
-                    for (int tap = 0; tap < 9; ++tap)
-                        tma_load_2d(wsm + tap * kTapBytes, &p.b_map, w_full, tap * 64, head * 64);
+                    for (int kx = 0; kx < 3; ++kx)
+                        for (int ky = 0; ky < 3; ++ky)
+                            tma_load_2d(wsm + (kx * 3 + ky) * kTapBytes, &p.b_map, w_full, (ky * 3 + kx) * 64, head * 64);
                     ++w_loads;
                     cur_head = head;
                 }
-                for (int iy = y0 - 1; iy <= y0 + kStripRows; ++iy, ++seq) {
+                for (int i = 0; i < kInRows; ++i, ++seq) {
                     const int slot = seq % kRing;
                     mbar_wait(&in_empty[slot], ((seq / kRing) & 1) ^ 1);
                     mbar_expect_tx(&in_full[slot], kRowBytes);
-                    tma_load_4d(ring + slot * kSlotBytes, &p.a_map[0], &in_full[slot], 0, -1, iy, img);
-                    if (has_res && iy >= y0 + 1) {          // residual tile of output row iy-1 (needed last)
+                    tma_load_4d(ring + slot * kSlotBytes, &p.a_map[0], &in_full[slot], 0, -1, y0 - 1 + i, img);
+                    if (has_res && i >= 2) {                // residual tile of output row i-2 (complete after row i)
                         const int rs = rseq % kResRing;
                         mbar_wait(&res_empty[rs], ((rseq / kResRing) & 1) ^ 1);
                         mbar_expect_tx(&res_full[rs], kTileBytes);
-                        tma_load_2d(res_sm + rs * kTileBytes, &p.res_map, &res_full[rs], 0, (img * kW + (iy - 1)) * kW);
+                        tma_load_2d(res_sm + rs * kTileBytes, &p.res_map, &res_full[rs], 0, (img * kW + (y0 + i - 2)) * kW);
                         ++rseq;
                     }
                 }
@@ -141,14 +155,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_rows_kernel(const __grid_con
     } else if (warp == 1) {
         // ------------------------------------------------------------------ UMMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
             const uint32_t w_addr = smem_u32(wsm);
             const uint32_t ring_addr = smem_u32(ring);
             int cur_head = -1;
             uint32_t w_loads = 0;
-            uint32_t seq0 = 0;                  // ring position of the unit's first input row (y0-1)
-            uint32_t waited = 0;                // rows [0, waited) of the global sequence are known to have landed
-            uint32_t tile = 0;
+            uint32_t seq = 0;                   // input rows consumed so far
+            uint32_t tbase = 0;                 // global index of this unit's output row 0
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 const int head = u / units_per_head;
                 if (head != cur_head) {
@@ -157,39 +169,41 @@ __global__ void __launch_bounds__(kThreads, 1) conv_rows_kernel(const __grid_con
                     ++w_loads;
                     cur_head = head;
                 }
-                for (int j = 0; j < kStripRows; ++j, ++tile) {
-                    // rows seq0+j, +1, +2 must be resident
-                    while (waited < seq0 + j + 3) {
-                        mbar_wait(&in_full[waited % kRing], (waited / kRing) & 1);
-                        ++waited;
+                for (int i = 0; i < kInRows; ++i, ++seq) {
+                    // input row i feeds output rows j = i - ky, ky in [ky_lo, ky_hi]
+                    const int ky_lo = i >= kStripRows ? i - (kStripRows - 1) : 0;
+                    const int ky_hi = i < 2 ? i : 2;
+                    if (i < kStripRows) {       // output row j = i starts accumulating: its block must be free (zeroed)
+                        const uint32_t T = tbase + i;
+                        mbar_wait(&acc_empty[(0u - T) & 7u], (T >> 3) & 1);   // use n of a slot waits for empty-event n (0 = initial zeroing)
                     }
-                    const int acc = tile & 1;
-                    mbar_wait(&tmem_empty[acc], ((tile >> 1) & 1) ^ 1);
+                    const int slot = seq % kRing;
+                    mbar_wait(&in_full[slot], (seq / kRing) & 1);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * 64;
-                    uint32_t first = 1;
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const uint32_t row_addr = ring_addr + ((seq0 + j + ky) % kRing) * kSlotBytes;
+                    const uint32_t row_addr = ring_addr + slot * kSlotBytes;
+                    // destination blocks: ky = ky_lo .. ky_hi  <->  output rows T_i - ky  <->  slots s0, s0+1, ... (mod 8)
+                    const uint32_t s0 = (0u - (tbase + i - ky_lo)) & 7u;
+                    const int nky = ky_hi - ky_lo + 1;
+                    const int n_first = (s0 + nky <= 8u) ? nky : static_cast<int>(8u - s0);   // blocks before the ring wraps
+#pragma unroll 1
+                    for (int seg = 0; seg < 2; ++seg) {
+                        const int nb = seg == 0 ? n_first : nky - n_first;
+                        if (nb == 0) break;
+                        const int kyb = seg == 0 ? ky_lo : ky_lo + n_first;
+                        const uint32_t d_tmem = tmem_base + (seg == 0 ? s0 : 0u) * 64;
+                        const uint32_t idesc = umma_idesc_bf16(128, 64 * nb);
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
-                            const uint64_t adesc = desc_shifted(row_addr + kx * 128, p.shared_input /*mode flag*/);
-                            const uint64_t bdesc = umma_desc_sw128(w_addr + (ky * 3 + kx) * kTapBytes);
+                            const uint64_t adesc = umma_desc_sw128(row_addr + kx * 128);
+                            const uint64_t bdesc = umma_desc_sw128(w_addr + (kx * 3 + kyb) * kTapBytes);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
-                                first = 0;
-                            }
+                            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
                         }
                     }
-                    umma_commit(&in_empty[(seq0 + j) % kRing]);          // input row y-1 is no longer needed
-                    if (j == kStripRows - 1) {
-                        umma_commit(&in_empty[(seq0 + j + 1) % kRing]);
-                        umma_commit(&in_empty[(seq0 + j + 2) % kRing]);
-                    }
-                    umma_commit(&tmem_full[acc]);
+                    umma_commit(&in_empty[slot]);
+                    if (i >= 2) umma_commit(&acc_full[(0u - (tbase + i - 2)) & 7u]);   // output row i-2 is complete
                 }
-                seq0 += kStripRows + 2;
+                tbase += kStripRows;
             }
         }
     } else {
@@ -197,32 +211,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_rows_kernel(const __grid_con
         // TMEM -> registers -> (+bias, +residual from smem, ReLU, bf16) -> swizzled smem -> TMA store.  Each warp owns
         // the 32 pixels of its TMEM lane quarter and two private 4 KB staging buffers, so no cross-warp barrier.
         const int quarter = warp & 3;
+        const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+        // all accumulators start at zero (every UMMA accumulates)
+        for (int cidx = 0; cidx < kTmemCols; cidx += 32) tmem_st32_zero(tmem_base + lane_base + cidx);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0)
+            for (int a = 0; a < kAccSlots; ++a) mbar_arrive(&acc_empty[a]);
+
         uint8_t* my_out = out_sm + quarter * 2 * 4096;
         const bool has_res = p.residual != nullptr;
-        uint32_t tile = 0;
+        uint32_t T = 0;                          // global output-row counter
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             const int head = u / units_per_head;
             const int r = u - head * units_per_head;
             const int img = head * p.imgs_per_head + r / kStripsPerImg;
             const int y0 = (r % kStripsPerImg) * kStripRows;
             const float4* bias4 = reinterpret_cast<const float4*>(p.bias + head * 64);
-            for (int j = 0; j < kStripRows; ++j, ++tile) {
-                const int acc = tile & 1;
-                mbar_wait(&tmem_full[acc], (tile >> 1) & 1);
+            for (int j = 0; j < kStripRows; ++j, ++T) {
+                const uint32_t slot = (0u - T) & 7u;
+                mbar_wait(&acc_full[slot], (T >> 3) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 64;
+                const uint32_t taddr = tmem_base + lane_base + slot * 64;
                 uint32_t v0[32], v1[32];
                 tmem_ld32(taddr, v0);
                 tmem_ld32(taddr + 32, v1);
                 tmem_ld_wait();
+                tmem_st32_zero(taddr);
+                tmem_st32_zero(taddr + 32);
+                tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);             // accumulator is in registers: release it
-                const int rs = tile % kResRing;
-                if (has_res) mbar_wait(&res_full[rs], (tile / kResRing) & 1);
-                if (lane == 0) tma_store_wait_read<1>();                  // staging buffer (tile & 1) is free again
+                if (lane == 0) mbar_arrive(&acc_empty[slot]);             // block is zero again: next user may start
+                const int rs = T % kResRing;
+                if (has_res) mbar_wait(&res_full[rs], (T / kResRing) & 1);
+                if (lane == 0) tma_store_wait_read<1>();                  // staging buffer (T & 1) is free again
                 __syncwarp();
-                uint8_t* stage = my_out + (tile & 1) * 4096;
+                uint8_t* stage = my_out + (T & 1) * 4096;
                 const uint8_t* res_row = res_sm + rs * kTileBytes;
                 const int prow = quarter * 32 + lane;                     // pixel row inside the 128-px tile
 #pragma unroll
@@ -276,8 +302,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_rows_kernel(const __grid_con
 }  // namespace
 
 // `p` as built for the generic kernel, except: a_map[0] must have box {64, 130, 1, 1}; total_tiles is recomputed
-// here as the number of (head, image, strip) units; p.shared_input is reused as the base-offset mode flag.
-cudaError_t conv_rows_launch(const ConvLaunch& p_in, int heads, int base_offset_mode, int num_sms, cudaStream_t stream) {
+// here as the number of (head, image, strip) units.
+cudaError_t conv_rows_launch(const ConvLaunch& p_in, int heads, int /*unused*/, int num_sms, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -286,7 +312,6 @@ cudaError_t conv_rows_launch(const ConvLaunch& p_in, int heads, int base_offset_
     }
     ConvLaunch p = p_in;
     p.total_tiles = heads * p.imgs_per_head * kStripsPerImg;
-    p.shared_input = base_offset_mode;
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     conv_rows_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
     return cudaGetLastError();
