@@ -609,7 +609,7 @@ int sad_create(sad_ctx** out, int device, int n_heads, int max_batch) {
     // launch plan bound to the workspace
     memset(&c->stem1, 0, sizeof(c->stem1));
     if (!sad::encode_weight_map(&c->stem1.w_map, c->d_w_stem1, 64, H * 64, 128, c->err, sizeof(c->err))) return SAD_ECUDA;
-    if (!sad::encode_pix_map(&c->stem1.out_map, c->d_buf[BX], 64, HB * 128 * 128, 32, c->err, sizeof(c->err))) return SAD_ECUDA;
+    if (!sad::encode_pix_map(&c->stem1.out_map, c->d_buf[BX], 64, HB * 128 * 128, 128, c->err, sizeof(c->err))) return SAD_ECUDA;
     c->stem1.img = c->d_img;
     c->stem1.H = n_heads;
     c->plan = build_plan();

@@ -1,21 +1,26 @@
 // K2: fused stem for the single-channel log-mel image:
 //     conv 7x7 / stride 2 / pad 3 (1 -> 64 channels per head, BN folded) + ReLU + maxpool 3x3 / stride 2 / pad 1
-// for TWO heads at a time (N = 128), never materialising the 64 x 256 x 256 conv output (8 MB per head and segment).
+// for TWO heads at a time, never materialising the 64 x 256 x 256 conv output (8 MB per head and segment).
 // Replaces conv1 / bn1 / act1 / maxpool of timm's ResNet inside BinaryClassifier.forward (reference
 // modular/source/inference_runner.py:49-51); the three identical input channels (:173) are folded into one by
 // summing conv1's weights over Cin (api.cu).
 //
-// GEMM view per conv-output row r (256 pixels): two M=128 tiles, "even" (row i <-> conv pixel x = 2i) and "odd"
-// (row i <-> x = 2i+1), so that TMEM lane i holds exactly the conv pixels pooled output px = i needs (2i, 2i+1 in its
-// own lane, 2i-1 in lane i-1).  K = 64: chunk ky (16 B) of a row = the 8 image pixels [2x-3, 2x+4] of image row
-// 2r+ky-3 (7 taps + one zero-weight slot); chunk 7 = {1,1,1,0,...} against {bias_hi, bias_mid, bias_lo} so the folded
-// BN shift is added by the tensor core in fp32 (bias split into three bf16 terms, exact to 24 bits).
-//   builders (4 warps): read the bf16 image (L2 resident) with 8-byte loads, funnel-shift, write both tiles into
-//                       SWIZZLE_128B shared memory; double buffered.
-//   MMA (1 thread)    : 8 x tcgen05.mma 128x128x16 per conv row into TMEM (even: cols 0-127, odd: 128-255; x2 buffers).
-//   epilogue (4 warps): h = max(even, odd, odd of lane-1) per conv row (cross-warp lane via a tiny smem exchange),
-//                       3-row vertical max carried in registers as packed bf16, ReLU, bf16, TMA store of the
-//                       pooled row [32 px][64 ch] per warp and head.
+// GEMM view per conv-output row r:   D[co][x] = sum_k W[co][k] * P[x][k]
+//   M = 128 output channels (2 heads x 64)  -> TMEM LANES are channels
+//   N = 256 conv pixels of the row          -> TMEM COLUMNS are pixels
+//   K = 64: chunk ky (16 B) of pixel x = the 8 image pixels [2x-3, 2x+4] of image row 2r+ky-3 (7 taps + one
+//       zero-weight slot); chunk 7 = {1,1,1,0,...} against {bias_hi, bias_mid, bias_lo} so the folded BN shift is
+//       added by the tensor core in fp32 (bias split into three bf16 terms, exact to 24 bits).
+// With channels on lanes, both pooling directions are per-thread register work: horizontal max over columns
+// 2p-1, 2p, 2p+1, vertical max carried across conv rows as packed bf16 -- no shuffles, no cross-warp exchange.
+// (A first version had pixels on lanes and was epilogue-bound: 12 TMEM round trips, 128 shuffles and a block
+// barrier per conv row; ncu showed the builders and the MMA warp spinning on the epilogue's barriers.)
+//   builders (4 warps): read the bf16 image (L2 resident) with 8-byte loads, funnel-shift, write the [256 px][128 B]
+//                       pixel tile into SWIZZLE_128B shared memory; double buffered.
+//   MMA (1 thread)    : 4 x tcgen05.mma 128x256x16 per conv row into TMEM (2 buffers x 256 columns).
+//   epilogue (4 warps): per thread = one channel: 8 x tcgen05.ld of 32 columns, pooling, ReLU, bf16; every second
+//                       conv row the pooled row is transposed through swizzled smem and written with TMA stores
+//                       ([128 px][64 ch] per head).
 // Work unit = (image, head pair, strip of 32 pooled rows); persistent CTAs, round-robin.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -31,18 +36,18 @@ constexpr int kThreads = 288;                  // warp 0: MMA + TMA; warps 1-4: 
 constexpr int kStripRows = 32;                 // pooled rows per unit
 constexpr int kStrips = 128 / kStripRows;
 constexpr int kConvRowsPerUnit = 2 * kStripRows + 1;
-constexpr int kTile = 128 * 128;               // one A tile (128 rows x 128 B) = one weight block (128 co x 64 k)
-constexpr int kABytes = 2 /*bufs*/ * 2 /*even,odd*/ * kTile;     // 64 KB
-constexpr int kWBytes = 2 * kTile;                                // 32 KB (double buffered)
-constexpr int kOutBytes = 4 /*warps*/ * 2 /*bufs*/ * 2 /*heads*/ * 4096;   // 64 KB
-constexpr int kXchgBytes = 2 /*bufs*/ * 4 /*warps*/ * 128 * 4;    // 4 KB
-constexpr int kSmemBytes = kABytes + kWBytes + kOutBytes + kXchgBytes + 1024 + 256;
-constexpr int kTmemCols = 512;                 // 2 buffers x (even 128 + odd 128)
+constexpr int kPixTile = 256 * 128;            // pixel tile: 256 rows x 128 B
+constexpr int kWTile = 128 * 128;              // weight tile: 128 co x 64 k
+constexpr int kPBytes = 2 * kPixTile;          // 64 KB (double buffered)
+constexpr int kWBytes = 2 * kWTile;            // 32 KB (double buffered)
+constexpr int kHeadTile = 128 * 128;           // staging: [128 px][64 ch] bf16 per head
+constexpr int kOutBytes = 2 /*bufs*/ * 2 /*heads*/ * kHeadTile;   // 64 KB
+constexpr int kSmemBytes = kPBytes + kWBytes + kOutBytes + 1024 + 256;
+constexpr int kTmemCols = 512;                 // 2 buffers x 256 pixel columns
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(n) : "memory");
 }
-
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -55,13 +60,12 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_constant__ StemLaunch p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* a_sm = smem;                               // [buf][even|odd][128][128 B]
-    uint8_t* w_sm = a_sm + kABytes;                     // [buf][128 co][128 B]
-    uint8_t* out_sm = w_sm + kWBytes;                   // [warp][buf][head][32 px][128 B]
-    float* xchg = reinterpret_cast<float*>(out_sm + kOutBytes);   // [buf][warp][128 ch]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + kXchgBytes);
-    uint64_t* a_full = bars;            // [2] count 128 (builder threads)
-    uint64_t* a_empty = bars + 2;       // [2] tcgen05.commit
+    uint8_t* p_sm = smem;                               // [buf][256 px][128 B]
+    uint8_t* w_sm = p_sm + kPBytes;                     // [buf][128 co][128 B]
+    uint8_t* out_sm = w_sm + kWBytes;                   // [buf][head][128 px][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_sm + kOutBytes);
+    uint64_t* p_full = bars;            // [2] count 128 (builder threads)
+    uint64_t* p_empty = bars + 2;       // [2] tcgen05.commit
     uint64_t* w_full = bars + 4;        // [2] TMA
     uint64_t* w_empty = bars + 6;       // [2] tcgen05.commit
     uint64_t* tmem_full = bars + 8;     // [2]
@@ -75,8 +79,8 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
         tma_prefetch_desc(&p.w_map);
         tma_prefetch_desc(&p.out_map);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], 128);
-            mbar_init(&a_empty[i], 1);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&p_empty[i], 1);
             mbar_init(&w_full[i], 1);
             mbar_init(&w_empty[i], 1);
             mbar_init(&tmem_full[i], 1);
@@ -86,10 +90,13 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
     }
     if (warp == 0) tmem_alloc<kTmemCols>(tmem_base_slot);
     if (warp >= 1 && warp <= 4) {
-        // chunk 7 of every A row is constant: {1, 1, 1, 0, 0, 0, 0, 0} (bias terms), written once
+        // chunk 7 of every pixel row is constant: {1, 1, 1, 0, 0, 0, 0, 0} (bias terms), written once
         const int i = (warp - 1) * 32 + lane;
         const uint4 ones = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);
-        for (int t = 0; t < 4; ++t) *reinterpret_cast<uint4*>(a_sm + t * kTile + sw128_offset(i, 7)) = ones;
+        for (int b = 0; b < 2; ++b) {
+            *reinterpret_cast<uint4*>(p_sm + b * kPixTile + sw128_offset(2 * i, 7)) = ones;
+            *reinterpret_cast<uint4*>(p_sm + b * kPixTile + sw128_offset(2 * i + 1, 7)) = ones;
+        }
         fence_proxy_async();
     }
     tc_fence_before();
@@ -102,11 +109,11 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
     if (warp == 0) {
         // ------------------------------------------------------------------ weights TMA + UMMA issue
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
             uint32_t ui = 0, arow = 0;
             const int first = blockIdx.x;
             if (first < p.total_units) {
-                mbar_expect_tx(&w_full[0], kTile);
+                mbar_expect_tx(&w_full[0], kWTile);
                 tma_load_2d(w_sm, &p.w_map, &w_full[0], 0, (first / units_per_group) * 128);
             }
             for (int u = first; u < p.total_units; u += gridDim.x, ++ui) {
@@ -115,35 +122,30 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                 if (un < p.total_units) {                 // prefetch the next unit's weights into the other buffer
                     const int nb = wb ^ 1;
                     mbar_wait(&w_empty[nb], (((ui + 1) >> 1) & 1) ^ 1);
-                    mbar_expect_tx(&w_full[nb], kTile);
-                    tma_load_2d(w_sm + nb * kTile, &p.w_map, &w_full[nb], 0, (un / units_per_group) * 128);
+                    mbar_expect_tx(&w_full[nb], kWTile);
+                    tma_load_2d(w_sm + nb * kWTile, &p.w_map, &w_full[nb], 0, (un / units_per_group) * 128);
                 }
                 mbar_wait(&w_full[wb], (ui >> 1) & 1);
-                const uint32_t w_addr = smem_u32(w_sm + wb * kTile);
+                const uint64_t adesc = umma_desc_sw128(smem_u32(w_sm + wb * kWTile));
                 for (int t = 0; t < kConvRowsPerUnit; ++t, ++arow) {
                     const int b = arow & 1;
                     const uint32_t ph = (arow >> 1) & 1;
-                    mbar_wait(&a_full[b], ph);
+                    mbar_wait(&p_full[b], ph);
                     mbar_wait(&tmem_empty[b], ph ^ 1);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(a_sm + b * 2 * kTile);
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(p_sm + b * kPixTile));
+                    const uint32_t d = tmem_base + b * 256;
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const uint64_t adesc = umma_desc_sw128(a_addr + half * kTile);
-                        const uint64_t bdesc = umma_desc_sw128(w_addr);
-                        const uint32_t d = tmem_base + b * 256 + half * 128;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
-                    }
-                    umma_commit(&a_empty[b]);
+                    for (int k = 0; k < 4; ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
+                    umma_commit(&p_empty[b]);
                     umma_commit(&tmem_full[b]);
                 }
                 umma_commit(&w_empty[wb]);
             }
         }
     } else if (warp <= 4) {
-        // ------------------------------------------------------------------ builders: image -> A tiles
-        const int i = (warp - 1) * 32 + lane;          // A row: even tile <-> conv x = 2i, odd tile <-> x = 2i+1
+        // ------------------------------------------------------------------ builders: image -> pixel tile
+        const int i = (warp - 1) * 32 + lane;          // builds conv pixels x = 2i and 2i+1
         uint32_t arow = 0;
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
             const int r0 = u % units_per_group;
@@ -168,9 +170,8 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                     }
                     w[ky][0] = q0.x; w[ky][1] = q0.y; w[ky][2] = q1.x; w[ky][3] = q1.y; w[ky][4] = q2.x; w[ky][5] = q2.y;
                 }
-                mbar_wait(&a_empty[b], ((arow >> 1) & 1) ^ 1);
-                uint8_t* ae = a_sm + (b * 2 + 0) * kTile;
-                uint8_t* ao = a_sm + (b * 2 + 1) * kTile;
+                mbar_wait(&p_empty[b], ((arow >> 1) & 1) ^ 1);
+                uint8_t* tile = p_sm + b * kPixTile;
 #pragma unroll
                 for (int ky = 0; ky < 7; ++ky) {
                     // even pixel x = 2i: image pixels [4i-3, 4i+4] = halves starting at the high half of word 0
@@ -179,19 +180,22 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                     // odd pixel x = 2i+1: image pixels [4i-1, 4i+6]
                     const uint4 co = make_uint4(__funnelshift_r(w[ky][1], w[ky][2], 16), __funnelshift_r(w[ky][2], w[ky][3], 16),
                                                 __funnelshift_r(w[ky][3], w[ky][4], 16), __funnelshift_r(w[ky][4], w[ky][5], 16));
-                    *reinterpret_cast<uint4*>(ae + sw128_offset(i, ky)) = ce;
-                    *reinterpret_cast<uint4*>(ao + sw128_offset(i, ky)) = co;
+                    *reinterpret_cast<uint4*>(tile + sw128_offset(2 * i, ky)) = ce;
+                    *reinterpret_cast<uint4*>(tile + sw128_offset(2 * i + 1, ky)) = co;
                 }
                 fence_proxy_async();
-                mbar_arrive(&a_full[b]);
+                mbar_arrive(&p_full[b]);
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: pool + store
-        const int q = warp & 3;                        // TMEM lane quarter; pooled px = q*32 + lane
-        uint8_t* my_out = out_sm + q * (2 * 2 * 4096);
+        // ------------------------------------------------------------------ epilogue: pool + transpose + store
+        const int q = warp & 3;                        // TMEM lane quarter
+        const int c = q * 32 + lane;                   // channel within the head pair (lane of the accumulator)
+        const int hh = c >> 6;                         // head within the pair
+        const int cc = c & 63;                         // channel within the head
+        const int et = threadIdx.x - 5 * 32;           // 0..127 within the epilogue group
         uint32_t arow = 0, nemit = 0;
-        uint32_t carry[64];                            // running vertical max, 128 channels as packed bf16
+        uint32_t carry[64];                            // running vertical max: 128 pooled px as packed bf16 pairs
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
             const int g = u / units_per_group;
             const int r0 = u % units_per_group;
@@ -200,88 +204,67 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
             for (int t = 0; t < kConvRowsPerUnit; ++t, ++arow) {
                 const int b = arow & 1;
                 const int r = 2 * py0 - 1 + t;
-                mbar_wait(&tmem_full[b], (arow >> 1) & 1);
-                tc_fence_after();
-                const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * 256;
-                float* xw = xchg + (b * 4 + q) * 128;
-                // pre-pass: lane 31's odd-pixel values are the "x-1" neighbour of the next warp's lane 0
-#pragma unroll 1
-                for (int cb = 0; cb < 4; ++cb) {
-                    uint32_t o[32];
-                    tmem_ld32(tbase + 128 + cb * 32, o);
-                    tmem_ld_wait();
-                    if (lane == 31) {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) xw[cb * 32 + c] = __uint_as_float(o[c]);
-                    }
-                }
-                named_bar_sync(1, 128);
-                const float* xr = xchg + (b * 4 + (q > 0 ? q - 1 : 0)) * 128;
                 const bool emit = (t >= 2) && ((t & 1) == 0);
                 const int eb = nemit & 1;
                 if (emit) {
-                    if (lane == 0) tma_store_wait_read<1>();       // staging buffer `eb` has been read out
-                    __syncwarp();
+                    if (et == 0) tma_store_wait_read<1>();         // staging buffer `eb` has been read out
+                    named_bar_sync(1, 128);
                 }
+                mbar_wait(&tmem_full[b], (arow >> 1) & 1);
+                tc_fence_after();
+                const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * 256;
+                uint8_t* stage = out_sm + (eb * 2 + hh) * kHeadTile + (cc & 7) * 2;   // + swizzled (px, chunk cc/8)
+                float prev = -INFINITY;                            // conv pixel 2p-1 of the chunk's first pooled px
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb) {
-                    uint32_t e[32], o[32];
-                    tmem_ld32(tbase + cb * 32, e);
-                    tmem_ld32(tbase + 128 + cb * 32, o);
+                for (int cb = 0; cb < 8; ++cb) {                   // 32 conv pixels -> 16 pooled pixels
+                    uint32_t v[32];
+                    tmem_ld32(tbase + cb * 32, v);
                     tmem_ld_wait();
-                    if (cb == 3) {                                  // accumulators fully read: release the TMEM buffer
+                    if (cb == 7) {                                  // accumulator fully read: release the TMEM buffer
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty[b]);
                     }
-                    uint32_t hb[16];
+                    uint32_t hb[8];
 #pragma unroll
-                    for (int c = 0; c < 32; c += 2) {
-                        float h2[2];
-#pragma unroll
-                        for (int s = 0; s < 2; ++s) {
-                            const float ov = __uint_as_float(o[c + s]);
-                            float op = __shfl_up_sync(0xffffffffu, ov, 1);
-                            if (lane == 0) op = q > 0 ? xr[cb * 32 + c + s] : -INFINITY;
-                            h2[s] = fmaxf(fmaxf(__uint_as_float(e[c + s]), ov), op);
-                        }
-                        hb[c >> 1] = pack_bf16(h2[0], h2[1]);
+                    for (int j = 0; j < 8; ++j) {
+                        const float a0 = __uint_as_float(v[4 * j]), a1 = __uint_as_float(v[4 * j + 1]);
+                        const float a2 = __uint_as_float(v[4 * j + 2]), a3 = __uint_as_float(v[4 * j + 3]);
+                        const float h0 = fmaxf(fmaxf(prev, a0), a1);      // pooled px 16cb+2j   : conv 2p-1, 2p, 2p+1
+                        const float h1 = fmaxf(fmaxf(a1, a2), a3);        // pooled px 16cb+2j+1
+                        prev = a3;
+                        hb[j] = pack_bf16(h0, h1);
                     }
                     if (t == 0) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) carry[cb * 16 + j] = r < 0 ? 0xFF80FF80u /* -inf, -inf */ : hb[j];
+                        for (int j = 0; j < 8; ++j) carry[cb * 8 + j] = r < 0 ? 0xFF80FF80u /* -inf, -inf */ : hb[j];
                     } else if (!emit) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) carry[cb * 16 + j] = bf16x2_max(carry[cb * 16 + j], hb[j]);
+                        for (int j = 0; j < 8; ++j) carry[cb * 8 + j] = bf16x2_max(carry[cb * 8 + j], hb[j]);
                     } else {
-                        // pooled row done: relu(max(carry, h)); this conv row also starts the next pooled row
-                        uint8_t* stage = my_out + (eb * 2 + (cb >> 1)) * 4096;     // head = cb / 2
-                        const uint32_t zero = 0u;
+                        // pooled row done: relu(max(carry, h)); this conv row also starts the next pooled row.
+                        // Transpose through smem: this thread owns channel cc, pixels 16cb .. 16cb+15.
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            uint32_t v[4];
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                const int j = j4 * 4 + jj;
-                                v[jj] = bf16x2_max(bf16x2_max(carry[cb * 16 + j], hb[j]), zero);
-                                carry[cb * 16 + j] = hb[j];
-                            }
-                            *reinterpret_cast<uint4*>(stage + sw128_offset(lane, (cb & 1) * 4 + j4)) =
-                                make_uint4(v[0], v[1], v[2], v[3]);
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t o = bf16x2_max(bf16x2_max(carry[cb * 8 + j], hb[j]), 0u);
+                            carry[cb * 8 + j] = hb[j];
+                            const int px = cb * 16 + 2 * j;
+                            *reinterpret_cast<uint16_t*>(stage + sw128_offset(px, cc >> 3)) = static_cast<uint16_t>(o & 0xFFFFu);
+                            *reinterpret_cast<uint16_t*>(stage + sw128_offset(px + 1, cc >> 3)) = static_cast<uint16_t>(o >> 16);
                         }
                     }
                 }
                 if (emit) {
                     fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
+                    named_bar_sync(1, 128);
+                    if (et == 0) {
                         const int py = py0 + (t >> 1) - 1;
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const int head = g * 2 + hh;
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const int head = g * 2 + h2;
                             if (head < p.H) {
-                                const int pix = ((head * p.B + img) * 128 + py) * 128 + q * 32;
-                                tma_store_2d(&p.out_map, my_out + (eb * 2 + hh) * 4096, 0, pix);
+                                const int pix = ((head * p.B + img) * 128 + py) * 128;
+                                tma_store_2d(&p.out_map, out_sm + (eb * 2 + h2) * kHeadTile, 0, pix);
                             }
                         }
                         tma_store_commit();
@@ -290,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                 }
             }
         }
-        if (lane == 0) tma_store_wait<0>();
+        if (et == 0) tma_store_wait<0>();
     }
 
     tc_fence_before();
