@@ -1,0 +1,58 @@
+"""Parameter container with timm's ResNet key layout (conv1, bn1, layer{1..4}.{0,1}.{conv1,bn1,conv2,bn2,
+downsample.{0,1}}), so state_dicts written by the reference (model_merger.py:154-159) load unchanged.
+
+The reference builds this trunk with ``timm.create_model(name, pretrained=True, num_classes=0)``
+(inference_runner.py:35), which needs the network; here the modules are only parameter holders -- the arithmetic
+runs in the sm_100a kernels -- so construction is offline and cheap.  Only resnet18 is wired to kernels (SURVEY 8f4
+lists the deeper variants as "next").
+"""
+import torch
+import torch.nn as nn
+
+SUPPORTED = ("resnet18",)
+
+
+class _BasicBlock(nn.Module):
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.act1 = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.act2 = nn.ReLU(inplace=True)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+
+
+class ResNetTrunk(nn.Module):
+    """resnet18 feature trunk; ``forward_features`` is served by the CUDA engine of the owning classifier."""
+
+    def __init__(self, model_name: str = "resnet18"):
+        super().__init__()
+        if model_name not in SUPPORTED:
+            raise NotImplementedError(
+                f"backbone {model_name!r}: only {SUPPORTED} has sm_100a kernels in this build (SURVEY.md 8f4)")
+        self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.act1 = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        cin = 64
+        for li, cout in enumerate((64, 128, 256, 512), start=1):
+            stride = 1 if li == 1 else 2
+            setattr(self, f"layer{li}", nn.Sequential(_BasicBlock(cin, cout, stride), _BasicBlock(cout, cout, 1)))
+            cin = cout
+        self.num_features = 512
+        for m in self.modules():                      # timm's init: kaiming-normal convs, unit BN
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        self._features_fn = None                      # installed by BinaryClassifier
+
+    def forward_features(self, x: torch.Tensor) -> torch.Tensor:
+        if self._features_fn is None:
+            raise RuntimeError("ResNetTrunk has no engine attached; use it through BinaryClassifier")
+        return self._features_fn(x)
+
+    def forward(self, x):
+        return self.forward_features(x).mean((2, 3))

@@ -1,0 +1,146 @@
+"""Host logic of the drop-in API (no GPU): checkpoint layout, loader errors, merger CSV rules, WAV ingest, configs.
+Reference behaviour cited as IR:/MM: lines of /root/reference/modular/source/{inference_runner,model_merger}.py."""
+import os
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures as FX
+from oracle import reference_api
+import sad_b200.inference_runner as IR
+import sad_b200.model_merger as MM
+
+
+def test_dataclass_defaults_match_reference():
+    a, s = IR.AudioConfig(), IR.SpectrogramConfig()
+    assert (a.sample_rate, a.window_size, a.overlap, a.silence_threshold) == (32000, 4.0, 0.85, 1e-4)     # IR:127-132
+    assert (s.n_fft, s.hop_length, s.n_mels, s.f_min, s.f_max, s.top_db, s.norm) == (2048, 512, 128, 20, 12000, 80, "slaney")
+    assert IR.window_and_hop(32000, a) == (128000, 19200)              # IR:181 float quirk
+    assert IR.window_and_hop(32000, IR.AudioConfig(32000, 4.0, 0.0, 1e-3)) == (128000, 128000)
+
+
+def test_state_dict_keys_match_reference_layout():
+    m = IR.ModularMultiHeadClassifier([IR.BinaryClassifier(), IR.BinaryClassifier()])
+    want = FX.merged_state_dict(2, calibrate=False)
+    got = m.state_dict()
+    assert list(got.keys()) == list(want.keys())
+    assert all(got[k].shape == want[k].shape and got[k].dtype == want[k].dtype for k in want)
+
+
+@pytest.mark.skipif(not reference_api.available(), reason="reference sources not on this machine")
+def test_state_dict_keys_match_live_reference():
+    RIR, _ = reference_api.load()
+    ref = RIR.ModularMultiHeadClassifier([RIR.BinaryClassifier(), RIR.BinaryClassifier()]).state_dict()
+    mine = IR.ModularMultiHeadClassifier([IR.BinaryClassifier(), IR.BinaryClassifier()]).state_dict()
+    assert list(ref.keys()) == list(mine.keys())
+    assert all(ref[k].shape == mine[k].shape for k in ref)
+
+
+def test_load_merged_model_errors_and_sparse_indices(tmp_path, capsys):
+    sd = FX.merged_state_dict(2, calibrate=False)
+    p = tmp_path / "m.pth"
+    torch.save({"state_dict": sd}, p)
+    with pytest.raises(ValueError, match="does not contain metadata for class names"):     # IR:85-86
+        IR.load_merged_model(str(p), torch.device("cpu"))
+    torch.save({"state_dict": sd, "metadata": {"foo": 1}}, p)
+    with pytest.raises(ValueError):
+        IR.load_merged_model(str(p), torch.device("cpu"))
+    torch.save({"metadata": {"class_names": ["a", "Real"]}}, p)
+    with pytest.raises(KeyError):                                                           # IR:83
+        IR.load_merged_model(str(p), torch.device("cpu"))
+    # non-contiguous indices are sorted and packed densely (IR:89-98); missing keys keep fresh values (IR:105-110)
+    sparse = {k.replace("sub_models.1.", "sub_models.7."): v for k, v in sd.items()}
+    del sparse["sub_models.7.head.10.bias"]
+    torch.save({"state_dict": sparse, "metadata": {"class_names": ["A", "B", "Real"]}}, p)
+    model, meta = IR.load_merged_model(str(p), torch.device("cpu"))
+    assert "Found 2 sub-model(s): [0, 7]" in capsys.readouterr().out
+    assert len(model.sub_models) == 2 and meta["class_names"] == ["A", "B", "Real"]
+    assert torch.equal(model.sub_models[1].base.conv1.weight, sd["sub_models.1.base.conv1.weight"])
+    assert not model.training
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    m = IR.ModularMultiHeadClassifier([IR.BinaryClassifier()]).eval()
+    with pytest.raises(Exception, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 512, 512))
+    with pytest.raises(Exception, match="no CPU fallback|CUDA"):
+        IR.waveform_to_spectrogram(torch.zeros(128000), 32000, IR.SpectrogramConfig())
+    with pytest.raises(NotImplementedError):
+        IR.waveform_to_spectrogram(torch.zeros(128000), 16000, IR.SpectrogramConfig())
+    with pytest.raises(NotImplementedError):
+        IR.BinaryClassifier("resnet50")
+
+
+def test_interpret_rule():
+    names = ["A", "B"]
+    cases = [([-1.0, -2.0, 3.0], "Real"), ([-1.0, -2.0, -3.0], "A"), ([2.0, 3.0, 5.0], "B"), ([0.0, -1.0, 0.0], "A")]
+    for z, want in cases:
+        lab, s = IR.interpret_multihead_logits(torch.tensor(z), 0.5, names, "Real")
+        assert lab == want and s.dtype == np.float32 and s.shape == (3,)
+    assert IR.interpret_multihead_logits(torch.tensor([0.0, 9.0, -9.0]), 0.5, ["A"], "Real")[0] == "Synthetic_2"
+
+
+def test_merger_cli_roundtrip(tmp_path, capsys):
+    """MM:93-160: CSV -> merged checkpoint with class_names = synthetic... + [most common real]."""
+    for i in range(3):
+        g = torch.Generator().manual_seed(50 + i)
+        sub = {k: v for k, v in FX.random_head_state(g).items()}
+        torch.save({"state_dict": sub, "epoch": 3}, tmp_path / f"m{i}.pth")
+    csv = tmp_path / "merge.csv"
+    csv.write_text("model_filename,synthetic_class,real_class\nm0.pth,SynA,Real\nm1.pth,SynB,Human\nm2.pth,SynC,Real\n")
+    out = tmp_path / "merged.pth"
+    MM.main(["--submodels-folder", str(tmp_path), "--csv-file", str(csv), "--output-path", str(out)])
+    txt = capsys.readouterr().out
+    assert "Warning: Not all real_class values match" in txt and "Saved merged model" in txt
+    ck = torch.load(out)
+    assert ck["metadata"]["class_names"] == ["SynA", "SynB", "SynC", "Real"]
+    assert len(ck["state_dict"]) == 3 * 136
+    g = torch.Generator().manual_seed(51)
+    assert torch.equal(ck["state_dict"]["sub_models.1.base.layer3.0.conv2.weight"],
+                       FX.random_head_state(g)["base.layer3.0.conv2.weight"])
+    model, meta = IR.load_merged_model(str(out), torch.device("cpu"))
+    assert len(model.sub_models) == 3
+    # trainer-style checkpoints without the "base." prefix only match head.* (MM:55 strict=False quirk)
+    bare = {k.replace("base.", ""): v for k, v in FX.random_head_state(torch.Generator().manual_seed(1)).items()}
+    torch.save({"state_dict": bare}, tmp_path / "bare.pth")
+    sm = MM.load_sub_model(str(tmp_path / "bare.pth"), torch.device("cpu"))
+    assert torch.equal(sm.head[2].weight, bare["head.2.weight"])
+    assert not torch.equal(sm.base.conv1.weight, bare["conv1.weight"])
+
+
+def _write_wav(path, x, sr, bits=16, channels=1):
+    x = np.asarray(x, np.float32)
+    if channels > 1:
+        x = np.stack([x] * channels, axis=1).reshape(-1)
+    if bits == 16:
+        raw = (np.clip(x, -1, 1) * 32767).astype("<i2").tobytes(); tag = 1
+    else:
+        raw = x.astype("<f4").tobytes(); tag = 3
+    hdr = b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVE" + b"fmt " + struct.pack(
+        "<IHHIIHH", 16, tag, channels, sr, sr * channels * bits // 8, channels * bits // 8, bits) + b"data" + struct.pack("<I", len(raw))
+    open(path, "wb").write(hdr + raw)
+
+
+def test_preprocess_waveform(tmp_path):
+    """IR:144-155: mono mix, zero-pad short clips to one window, resample when the rate differs."""
+    rng = np.random.default_rng(0)
+    x = np.clip(0.2 * rng.standard_normal(50000), -0.99, 0.99).astype(np.float32)
+    _write_wav(tmp_path / "short.wav", x, 32000, bits=32)
+    wf, sr = IR.preprocess_waveform(str(tmp_path / "short.wav"), IR.AudioConfig())
+    assert sr == 32000 and wf.shape[0] == 128000 and torch.equal(wf[:50000], torch.from_numpy(x)) and float(wf[50000:].abs().max()) == 0
+    _write_wav(tmp_path / "stereo16.wav", x, 32000, bits=16, channels=2)
+    wf2, _ = IR.preprocess_waveform(str(tmp_path / "stereo16.wav"), IR.AudioConfig())
+    assert float((wf2[:50000] - torch.from_numpy(x)).abs().max()) < 1e-4      # 16-bit quantisation
+    _write_wav(tmp_path / "r16k.wav", x[:40000], 16000, bits=32)
+    wf3, sr3 = IR.preprocess_waveform(str(tmp_path / "r16k.wav"), IR.AudioConfig())
+    assert sr3 == 32000 and wf3.shape[0] == 128000
+    import torchaudio
+    want = torchaudio.transforms.Resample(16000, 32000)(torch.from_numpy(x[:40000]))
+    assert torch.equal(wf3[:want.shape[0]], want)
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.wav").write_bytes(b"not a wav file at all")
+        IR.preprocess_waveform(str(tmp_path / "bad.wav"), IR.AudioConfig())
