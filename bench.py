@@ -250,7 +250,7 @@ def run_native(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * K / (float(t.item()) / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": B * SEGMENT_BYTES, "d2h_bytes_per_step": B * ((H + 1) * 8 + 4)}
+               "h2d_bytes_per_step": world * B * SEGMENT_BYTES, "d2h_bytes_per_step": world * B * ((H + 1) * 8 + 4)}
         del xh
 
     if rank != 0:
