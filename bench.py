@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=2048, help="segments per GPU per step")
     ap.add_argument("--heads", type=int, default=6)
-    ap.add_argument("--max-batch", type=int, default=64, help="segments per internal pass (workspace size)")
+    ap.add_argument("--max-batch", type=int, default=128, help="segments per internal pass (workspace size)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="segments in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

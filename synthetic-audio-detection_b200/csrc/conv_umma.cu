@@ -36,21 +36,25 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
 
-template <int N_TILE>
+// MT = M tiles (of 128 pixels) that share one B (weight) stage.  With MT = 2 the same bytes in flight feed twice the
+// tensor cycles; used for N_TILE = 128 (layer2), which was limited by stage bytes in flight over TMA latency.
+template <int N_TILE, int MT>
 struct Cfg {
     static constexpr int kBBytes = N_TILE * kBlockK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStageBytes = MT * kABytes + kBBytes;
     // epilogue staging: per epilogue warp kOutBufs buffers of [32 px][64 ch] bf16 (4 KB, SWIZZLE_128B) for TMA stores
     static constexpr int kOutBufs = N_TILE == 256 ? 1 : 2;
     static constexpr int kOutBytes = 4 * kOutBufs * 4096;
     static constexpr int kStages = ((208 * 1024 - kOutBytes) / kStageBytes) > 8 ? 8 : ((208 * 1024 - kOutBytes) / kStageBytes);
-    static constexpr int kTmemCols = 2 * N_TILE < 32 ? 32 : 2 * N_TILE;   // 128 / 256 / 512: powers of two
+    static constexpr int kAccCols = MT * N_TILE;                          // one accumulator set (MT tiles)
+    static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // double buffered: 128 / 256 / 512
+    static_assert(kTmemCols <= 512, "accumulators do not fit TMEM");
     static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int N_TILE>
+template <int N_TILE, int MT>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvLaunch p) {
-    using C = Cfg<N_TILE>;
+    using C = Cfg<N_TILE, MT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* tiles = smem;
@@ -88,20 +92,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     const int taps = p.ksize * p.ksize;
     const int cblocks = p.Cin / kBlockK;
     const int ksteps = taps * cblocks;
-    const int tiles_per_head = p.imgs_per_head * p.m_tiles_per_img * p.n_tiles;
+    const int m_groups = p.m_tiles_per_img / MT;              // groups of MT consecutive M tiles of one image
+    const int tiles_per_head = p.imgs_per_head * m_groups * p.n_tiles;
+    const int total_groups = p.total_tiles / MT;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < total_groups; tile += gridDim.x) {
                 const int head = tile / tiles_per_head;
                 int r = tile - head * tiles_per_head;
                 const int n_t = r % p.n_tiles;
                 r /= p.n_tiles;
-                const int m_t = r % p.m_tiles_per_img;
-                const int img = r / p.m_tiles_per_img;
+                const int m_t = (r % m_groups) * MT;
+                const int img = r / m_groups;
                 const int img_in = p.shared_input ? img : head * p.imgs_per_head + img;
                 const int oy0 = m_t * p.rows_per_tile;
                 const int wrow = head * p.Cout + n_t * N_TILE;
@@ -117,9 +123,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     for (int cb = 0; cb < cblocks; ++cb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* a_dst = tiles + stage * C::kStageBytes;
-                        uint8_t* b_dst = a_dst + kABytes;
+                        uint8_t* b_dst = a_dst + MT * kABytes;
                         mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-                        tma_load_4d(a_dst, &p.a_map[map], &full_bar[stage], cb * kBlockK, x0, y0, img_in);
+#pragma unroll
+                        for (int m = 0; m < MT; ++m)
+                            tma_load_4d(a_dst + m * kABytes, &p.a_map[map], &full_bar[stage], cb * kBlockK, x0,
+                                        y0 + m * p.rows_per_tile, img_in);
                         tma_load_2d(b_dst, &p.b_map, &full_bar[stage], tap * p.Cin + cb * kBlockK, wrow);
                         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                     }
@@ -133,21 +142,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < total_groups; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
                 mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * N_TILE;
+                const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(tiles + stage * C::kStageBytes);
-                    const uint64_t adesc = umma_desc_sw128(a_addr);
-                    const uint64_t bdesc = umma_desc_sw128(a_addr + kABytes);
+                    const uint64_t bdesc = umma_desc_sw128(a_addr + MT * kABytes);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in >>4 units
-                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+                    for (int m = 0; m < MT; ++m) {
+                        const uint64_t adesc = umma_desc_sw128(a_addr + m * kABytes);
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in >>4 units
+                            umma_bf16(d_tmem + m * N_TILE, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);   // frees this smem stage once the MMAs have read it
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -165,23 +177,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         uint8_t* my_out = out_sm + quarter * C::kOutBufs * 4096;
         int it = 0;
         uint32_t nstore = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; tile < total_groups; tile += gridDim.x, ++it) {
             const int head = tile / tiles_per_head;
             int r = tile - head * tiles_per_head;
             const int n_t = r % p.n_tiles;
             r /= p.n_tiles;
-            const int m_t = r % p.m_tiles_per_img;
-            const int img = r / p.m_tiles_per_img;
+            const int m_t = (r % m_groups) * MT;
+            const int img = r / m_groups;
             const int acc = it & 1;
-            const long long pix0 =
-                (static_cast<long long>(head) * p.imgs_per_head + img) * (p.m_tiles_per_img * kBlockM) + m_t * kBlockM;
             const int co0 = n_t * N_TILE;
             const float4* bias4 = reinterpret_cast<const float4*>(p.bias + head * p.Cout + co0);
-            const __nv_bfloat16* res = p.residual ? p.residual + (pix0 + row) * p.Cout + co0 : nullptr;
 
             mbar_wait(&tmem_full[acc], (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * N_TILE;
+#pragma unroll 1
+            for (int m = 0; m < MT; ++m) {
+            const long long pix0 = (static_cast<long long>(head) * p.imgs_per_head + img) * (p.m_tiles_per_img * kBlockM) +
+                                   (m_t + m) * kBlockM;
+            const __nv_bfloat16* res = p.residual ? p.residual + (pix0 + row) * p.Cout + co0 : nullptr;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::kAccCols + m * N_TILE;
 #pragma unroll 1
             for (int c0 = 0; c0 < N_TILE; c0 += 64, ++nstore) {
                 uint32_t v0[32], v1[32];
@@ -193,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     for (int q = 0; q < 8; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(res + c0) + q);
                 }
                 tmem_ld_wait();
-                if (c0 + 64 >= N_TILE) {              // whole accumulator is in registers: hand TMEM back to the MMA warp
+                if (c0 + 64 >= N_TILE && m == MT - 1) {   // whole accumulator set is in registers: hand TMEM back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -238,6 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     tma_store_commit();
                 }
             }
+            }
         }
         if (lane == 0) tma_store_wait<0>();
     }
@@ -247,18 +262,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
-template <int N_TILE>
+template <int N_TILE, int MT>
 cudaError_t launch_t(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
-    using C = Cfg<N_TILE>;
+    using C = Cfg<N_TILE, MT>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<N_TILE, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C::kSmemBytes);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-    conv_umma_kernel<N_TILE><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+    const int groups = p.total_tiles / MT;
+    int grid = groups < num_sms ? groups : num_sms;
+    conv_umma_kernel<N_TILE, MT><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -268,9 +284,9 @@ int conv_n_tile(int Cout) { return Cout >= 256 ? 256 : Cout; }
 
 cudaError_t conv_umma_launch(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
     switch (p.n_tile) {
-        case 64: return launch_t<64>(p, num_sms, stream);
-        case 128: return launch_t<128>(p, num_sms, stream);
-        case 256: return launch_t<256>(p, num_sms, stream);
+        case 64: return launch_t<64, 1>(p, num_sms, stream);
+        case 128: return (p.m_tiles_per_img % 2 == 0) ? launch_t<128, 2>(p, num_sms, stream) : launch_t<128, 1>(p, num_sms, stream);
+        case 256: return launch_t<256, 1>(p, num_sms, stream);
         default: return cudaErrorInvalidValue;
     }
 }
