@@ -260,6 +260,10 @@ def run_native(args):
 
     pk = peaks()
     flops = dict(S.conv_flops_per_head_segment(folded_stem=True))
+    for c2 in (6, 11, 16):                      # downsample branch (index c2+1) runs inside conv2 when fused
+        if prof_ms[c2 + 1] == 0:
+            flops[c2] += flops[c2 + 1]
+            flops[c2 + 1] = 0.0
     conv_ms = sum(prof_ms[i] for i in range(20))
     conv_launches = sum(prof_n[i] for i in range(20))
     conv_tflop = sum(flops[i] for i in range(20)) * 1e9 * H * B * K / 1e12

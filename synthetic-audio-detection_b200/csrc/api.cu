@@ -99,26 +99,31 @@ struct Step {
     int conv;
     int in, res, out;
     int relu;
+    int fused_ds;   // conv index of a downsample branch accumulated into this conv (reads buffer X), or -1
 };
-std::vector<Step> build_plan() {
+std::vector<Step> build_plan(bool fuse_ds) {
     std::vector<Step> p;
     int ci = 1;
     for (int li = 0; li < 4; ++li) {
         if (li == 0) {
-            p.push_back({ci + 0, BX, BNONE, BT, 1});
-            p.push_back({ci + 1, BT, BX, BY, 1});
+            p.push_back({ci + 0, BX, BNONE, BT, 1, -1});
+            p.push_back({ci + 1, BT, BX, BY, 1, -1});
             ci += 2;
+        } else if (fuse_ds) {
+            p.push_back({ci + 0, BX, BNONE, BT, 1, -1});
+            p.push_back({ci + 1, BT, BNONE, BY, 1, ci + 2});   // conv2 + downsample(X) accumulated in one tile
+            ci += 3;
         } else {
-            p.push_back({ci + 0, BX, BNONE, BT, 1});
-            p.push_back({ci + 2, BX, BNONE, BD, 0});
-            p.push_back({ci + 1, BT, BD, BY, 1});
+            p.push_back({ci + 0, BX, BNONE, BT, 1, -1});
+            p.push_back({ci + 2, BX, BNONE, BD, 0, -1});
+            p.push_back({ci + 1, BT, BD, BY, 1, -1});
             ci += 3;
         }
-        p.push_back({ci + 0, BY, BNONE, BT, 1});
-        p.push_back({ci + 1, BT, BY, BX, 1});
+        p.push_back({ci + 0, BY, BNONE, BT, 1, -1});
+        p.push_back({ci + 1, BT, BY, BX, 1, -1});
         ci += 2;
     }
-    return p;   // 19 steps; the trunk output ends in X
+    return p;   // 19 (16 with fused downsamples) steps; the trunk output ends in X
 }
 
 constexpr double kBnEps = 1e-5;
@@ -163,6 +168,8 @@ struct sad_ctx {
     std::vector<sad::ConvLaunch> plan_launch;
     std::vector<Step> plan;
     bool stem3_ready = false;
+    int fuse_ds = 1;                    // fold each block's 1x1/s2 downsample conv into conv2 as extra K blocks
+    float* d_bias_fused[20] = {nullptr}; // [H][Cout] = bias(conv2) + bias(downsample) for conv indices 6, 11, 16
     int rows_mode = 2;                  // layer1 row-stationary kernel: 0 off, 2 on (1 = probe: descriptor base-offset field set, WRONG on sm_100a)
 
     // end-to-end path
@@ -332,7 +339,7 @@ bool is_rows_layer(int ci) {
 }
 
 bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const bf16* res, bf16* out, long long n_imgs,
-                 int relu) {
+                 int relu, int fused_ds = -1, const bf16* ds_in = nullptr) {
     const ConvSpec& s = convs()[ci];
     memset(L, 0, sizeof(*L));
     const int Wo = s.hout, Hi = s.hin, C = s.cin;
@@ -376,6 +383,23 @@ bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const b
     L->n_tiles = s.cout / n_tile;
     L->relu = relu;
     L->shared_input = 0;
+    L->k2_blocks = 0;
+    L->a2_map = L->a_map[0];
+    L->b2_map = L->b_map;
+    if (fused_ds >= 0) {
+        const ConvSpec& d = convs()[fused_ds];         // 1x1, stride 2, pad 0, same Cout and output size as `s`
+        if (d.cout != s.cout || d.hout != s.hout || d.k != 1 || d.stride != 2) {
+            snprintf(c->err, sizeof(c->err), "conv %d cannot absorb downsample %d", ci, fused_ds);
+            return false;
+        }
+        if (!sad::encode_act_map(&L->a2_map, ds_in, d.cin, d.hin / 2, d.hin / 2, n_imgs, 2LL * d.cin, 2LL * d.hin * d.cin,
+                                 1LL * d.hin * d.hin * d.cin, Wo, rows, c->err, sizeof(c->err)))
+            return false;
+        if (!sad::encode_weight_map(&L->b2_map, c->d_w[fused_ds], d.cin, 1LL * c->H * d.cout, n_tile, c->err, sizeof(c->err)))
+            return false;
+        L->k2_blocks = d.cin / 64;
+        L->bias = c->d_bias_fused[ci];
+    }
     return true;
 }
 
@@ -563,6 +587,7 @@ int sad_create(sad_ctx** out, int device, int n_heads, int max_batch) {
     c->num_sms = prop.multiProcessorCount;
     c->loaded.assign(n_heads, 0);
     if (const char* e = getenv("SAD_CONV_ROWS")) c->rows_mode = atoi(e);
+    if (const char* e = getenv("SAD_FUSE_DS")) c->fuse_ds = atoi(e);
     *out = c;   // returned even on failure so the caller can read sad_last_error, then sad_destroy
     CU_OK(c, cudaSetDevice(device));
 
@@ -573,6 +598,7 @@ int sad_create(sad_ctx** out, int device, int n_heads, int max_batch) {
         CU_OK(c, dalloc(&c->d_bias[i], H * s.cout));
     }
     CU_OK(c, dalloc(&c->d_bias[0], H * 64));
+    for (int ci : {6, 11, 16}) CU_OK(c, dalloc(&c->d_bias_fused[ci], H * convs()[ci].cout));
     CU_OK(c, dalloc(&c->d_w_stem1, H * 64 * 64));
     CU_OK(c, dalloc(&c->d_w_stem3, H * 64 * 192));
     CU_OK(c, dalloc(&c->d_w1t, H * 512 * 512));
@@ -612,12 +638,12 @@ int sad_create(sad_ctx** out, int device, int n_heads, int max_batch) {
     if (!sad::encode_pix_map(&c->stem1.out_map, c->d_buf[BX], 64, HB * 128 * 128, 128, c->err, sizeof(c->err))) return SAD_ECUDA;
     c->stem1.img = c->d_img;
     c->stem1.H = n_heads;
-    c->plan = build_plan();
+    c->plan = build_plan(c->fuse_ds != 0);
     c->plan_launch.resize(c->plan.size());
     for (size_t i = 0; i < c->plan.size(); ++i) {
         const Step& s = c->plan[i];
         if (!make_launch(c, &c->plan_launch[i], s.conv, c->d_buf[s.in], s.res == BNONE ? nullptr : c->d_buf[s.res],
-                         c->d_buf[s.out], HB, s.relu))
+                         c->d_buf[s.out], HB, s.relu, s.fused_ds, c->d_buf[BX]))
             return SAD_ECUDA;
     }
 
@@ -638,6 +664,7 @@ int sad_destroy(sad_ctx* c) {
         cudaFree(c->d_w[i]);
         cudaFree(c->d_bias[i]);
     }
+    for (int i = 0; i < 20; ++i) cudaFree(c->d_bias_fused[i]);
     void* ptrs[] = {c->d_w_stem1, c->d_w_stem3, c->d_w1t, c->d_b1, c->d_w2t, c->d_b2, c->d_w3, c->d_b3, c->d_window,
                     c->d_mel, c->d_resize, c->d_db, c->d_segmax, c->d_musig, c->d_img, c->d_A3, c->d_stem,
                     c->d_buf[0], c->d_buf[1], c->d_buf[2], c->d_buf[3], c->d_head_logits, c->d_pcm[0], c->d_pcm[1],
@@ -674,6 +701,7 @@ int sad_load_weights(sad_ctx* c, int head, const float* const* T, int n_tensors)
         if (!T[i]) return fail(c, SAD_EINVAL, "tensor %d (%s) is null", i, sad_weight_name(i));
     CU_OK(c, cudaSetDevice(c->device));
     std::vector<double> s, t;
+    std::vector<std::vector<float>> host_bias(20);
     int ti = 0;
     for (int ci = 0; ci < 20; ++ci) {
         const ConvSpec& cs = convs()[ci];
@@ -682,6 +710,7 @@ int sad_load_weights(sad_ctx* c, int head, const float* const* T, int n_tensors)
         ti += 5;
         std::vector<float> bias(cs.cout);
         for (int o = 0; o < cs.cout; ++o) bias[o] = static_cast<float>(t[o]);
+        host_bias[ci] = bias;
         CU_OK(c, cudaMemcpy(c->d_bias[ci] + static_cast<size_t>(head) * cs.cout, bias.data(), cs.cout * sizeof(float),
                             cudaMemcpyHostToDevice));
         const int kk = cs.k * cs.k;
@@ -724,6 +753,12 @@ int sad_load_weights(sad_ctx* c, int head, const float* const* T, int n_tensors)
             CU_OK(c, cudaMemcpy(c->d_w[ci] + static_cast<size_t>(head) * cs.cout * K, p.data(), p.size() * sizeof(bf16),
                                 cudaMemcpyHostToDevice));
         }
+    }
+    for (int ci : {6, 11, 16}) {   // conv2 of the first block of layers 2-4 absorbs the downsample branch (index ci+1)
+        std::vector<float> fb(host_bias[ci].size());
+        for (size_t o = 0; o < fb.size(); ++o) fb[o] = host_bias[ci][o] + host_bias[ci + 1][o];
+        CU_OK(c, cudaMemcpy(c->d_bias_fused[ci] + static_cast<size_t>(head) * fb.size(), fb.data(), fb.size() * sizeof(float),
+                            cudaMemcpyHostToDevice));
     }
     // head: Linear(512,512)+BN1d, Linear(512,256)+BN1d, Linear(256,2)
     {

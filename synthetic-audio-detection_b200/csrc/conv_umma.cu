@@ -73,6 +73,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
         tma_prefetch_desc(&p.b_map);
         tma_prefetch_desc(&p.out_map);
+        if (p.k2_blocks) {
+            tma_prefetch_desc(&p.a2_map);
+            tma_prefetch_desc(&p.b2_map);
+        }
         for (int s = 0; s < C::kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 
     const int taps = p.ksize * p.ksize;
     const int cblocks = p.Cin / kBlockK;
-    const int ksteps = taps * cblocks;
+    const int ksteps = taps * cblocks + p.k2_blocks;    // + fused downsample branch (1x1, stride 2) K blocks
     const int m_groups = p.m_tiles_per_img / MT;              // groups of MT consecutive M tiles of one image
     const int tiles_per_head = p.imgs_per_head * m_groups * p.n_tiles;
     const int total_groups = p.total_tiles / MT;
@@ -132,6 +136,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                         tma_load_2d(b_dst, &p.b_map, &full_bar[stage], tap * p.Cin + cb * kBlockK, wrow);
                         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                     }
+                }
+                // fused downsample branch: out += x[2*oy, 2*ox, :] * w_ds  (parity-(0,0) view, no tap offset)
+                for (int cb = 0; cb < p.k2_blocks; ++cb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* a_dst = tiles + stage * C::kStageBytes;
+                    uint8_t* b_dst = a_dst + MT * kABytes;
+                    mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+                        tma_load_4d(a_dst + m * kABytes, &p.a2_map, &full_bar[stage], cb * kBlockK, 0,
+                                    oy0 + m * p.rows_per_tile, img_in);
+                    tma_load_2d(b_dst, &p.b2_map, &full_bar[stage], cb * kBlockK, wrow);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }

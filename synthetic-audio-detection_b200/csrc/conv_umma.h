@@ -11,6 +11,8 @@ struct alignas(64) ConvLaunch {
     CUtensorMap b_map;      // packed weights [heads*Cout][taps*Cin] bf16, K-major
     CUtensorMap out_map;    // output viewed as {Cout, pixels}: box {64 ch, 32 px}, SWIZZLE_128B (TMA store)
     CUtensorMap res_map;    // residual viewed as {Cout, pixels}: box {64 ch, 128 px} (TMA load); valid iff residual
+    CUtensorMap a2_map;     // optional second input (fused 1x1/stride-2 downsample branch): parity-(0,0) view of the block input
+    CUtensorMap b2_map;     // its weights [heads*Cout][Cin2] bf16; the extra k2_blocks K-steps accumulate into the same tile
     const float* bias;      // [heads*Cout] fp32 (folded BN shift)
     const __nv_bfloat16* residual;   // NHWC [heads*imgs][Ho*Wo][Cout] or nullptr
     __nv_bfloat16* out;     // NHWC [heads*imgs][Ho*Wo][Cout]
@@ -24,6 +26,7 @@ struct alignas(64) ConvLaunch {
     int total_tiles;        // heads * imgs * m_tiles_per_img * n_tiles
     int relu;
     int shared_input;       // 1: every head reads image `img` (stem); 0: head h reads image h*B+img
+    int k2_blocks;          // Cin2 / 64 extra K blocks read through a2_map / b2_map (0 = none)
 };
 
 int conv_n_tile(int Cout);
