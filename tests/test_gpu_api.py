@@ -110,3 +110,22 @@ def test_cli_all_silent_writes_empty_result(merged_ckpt, tmp_path):
     out = tmp_path / "res.json"
     IR.main(["--merged-model", merged_ckpt, "--audio", str(wav), "--output-json", str(out)])
     assert json.loads(out.read_text()) == {"filename": str(wav), "segments": [], "percentages": {}}   # IR:264-273
+
+
+def test_batch_folder_driver(merged_ckpt, tmp_path):
+    """a folder of WAVs -> one JSON per clip + summary.json, same numbers as the single-file CLI."""
+    import sad_b200.batch_runner as BR
+    folder, out = tmp_path / "wavs", tmp_path / "out"
+    folder.mkdir()
+    for i, n in enumerate((3 * 128000 + 5, 128000, 60000)):
+        _write_wav(str(folder / f"c{i}.wav"), FX.synth_clip(n, seed=30 + i).numpy(), 32000, bits=32)
+    _write_wav(str(folder / "zsilent.wav"), np.zeros(2 * 128000, np.float32), 32000, bits=16)
+    (folder / "notes.txt").write_text("ignored")
+    BR.main(["--merged-model", merged_ckpt, "--folder", str(folder), "--out-dir", str(out)])
+    summary = json.loads((out / "summary.json").read_text())
+    assert [os.path.basename(r["filename"]) for r in summary] == ["c0.wav", "c1.wav", "c2.wav", "zsilent.wav"]
+    assert [r["n_segments"] for r in summary] == [3, 1, 1, 0] and summary[3]["label"] == ""
+    single = tmp_path / "single.json"
+    IR.main(["--merged-model", merged_ckpt, "--audio", str(folder / "c0.wav"), "--output-json", str(single)])
+    assert json.loads(single.read_text()) == json.loads((out / "c0.json").read_text())
+    assert summary[0]["label"] in FX.class_names(2)
