@@ -10,8 +10,10 @@
 //       v[q]  = in[j + q*N/R] * exp(-2*pi*i * k*q / (Ns*R)),  q = 0..R-1
 //       V     = DFT_R(v)
 //       out[(j/Ns)*Ns*R + k + q*Ns] = V[q]
-// Twiddles come from one table W[n] = exp(-2*pi*i*n/2048), n < 2048 (k*q < Ns*R always), so no twiddle is
-// ever produced by repeated multiplication.
+// Twiddles are table look-ups of exp(-2*pi*i*n/2048) (k*q < Ns*R always), never produced by repeated
+// multiplication.  The table is stored PER PASS as tw[q-1][k] so that the lanes of a warp (consecutive k) read
+// consecutive entries: indexing one W[2048] table by (k*q)*stride put every lane on the same bank (ncu: 54% of the
+// kernel's shared-memory wavefronts were bank conflicts).
 //
 // Shared-memory layout: separate re/im float arrays, logical index a stored at pad(a):
 //   after pass 1: pad1(a) = a + a/32        (stride-8 writes -> conflict free)
@@ -35,6 +37,15 @@ constexpr int kFftBuf = 2304;   // floats per component: max padded index is pad
 struct cpx {
     float x, y;
 };
+
+// Per-pass twiddle tables (entry n of the flattened struct has angle fft_twiddle_angle(n)): W_L^{k*q} with L = Ns*R of the pass.
+struct FftTwiddles {
+    cpx p2[7][8];      // pass 2: L = 64,   k = t & 7,  q = 1..7
+    cpx p3[7][64];     // pass 3: L = 512,  k = t & 63, q = 1..7
+    cpx p4[3][512];    // pass 4: L = 2048, k = j,      q = 1..3
+};
+constexpr int kFftTwiddleCount = 7 * 8 + 7 * 64 + 3 * 512;   // 2040 complex values
+
 
 SAD_HD cpx cadd(cpx a, cpx b) { return {a.x + b.x, a.y + b.y}; }
 SAD_HD cpx csub(cpx a, cpx b) { return {a.x - b.x, a.y - b.y}; }
@@ -91,7 +102,16 @@ SAD_HD void fft_pass1(int t, const cpx* in8, float* re, float* im) {
 }
 // Passes 2 and 3 are split into a load phase and a store phase because the transform is done in place:
 // every thread must have read its inputs before any thread overwrites them (one barrier in between).
-SAD_HD void fft_pass2_load(int t, const float* re, const float* im, const cpx* tw, cpx* v) {
+// n-th entry of the flattened FftTwiddles -> (pass table, q, k) -> angle index m of exp(-2*pi*i*m/2048)
+SAD_HD int fft_twiddle_angle(int n) {
+    if (n < 56) return ((n & 7) * (n / 8 + 1)) << 5;
+    n -= 56;
+    if (n < 448) return ((n & 63) * (n / 64 + 1)) << 2;
+    n -= 448;
+    return (n & 511) * (n / 512 + 1);
+}
+
+SAD_HD void fft_pass2_load(int t, const float* re, const float* im, const FftTwiddles& tw, cpx* v) {
     const int k = t & 7;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -99,7 +119,7 @@ SAD_HD void fft_pass2_load(int t, const float* re, const float* im, const cpx* t
     for (int q = 0; q < 8; ++q) {
         const int a = pad1(t + 256 * q);
         cpx x = {re[a], im[a]};
-        v[q] = q == 0 ? x : cmul(x, tw[(k * q) << 5]);   // exp(-2 pi i k q / 64)
+        v[q] = q == 0 ? x : cmul(x, tw.p2[q ? q - 1 : 0][k]);   // exp(-2 pi i k q / 64)
     }
     dft8(v);
 }
@@ -114,7 +134,7 @@ SAD_HD void fft_pass2_store(int t, const cpx* v, float* re, float* im) {
         im[a] = v[q].y;
     }
 }
-SAD_HD void fft_pass3_load(int t, const float* re, const float* im, const cpx* tw, cpx* v) {
+SAD_HD void fft_pass3_load(int t, const float* re, const float* im, const FftTwiddles& tw, cpx* v) {
     const int k = t & 63;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -122,7 +142,7 @@ SAD_HD void fft_pass3_load(int t, const float* re, const float* im, const cpx* t
     for (int q = 0; q < 8; ++q) {
         const int a = pad2(t + 256 * q);
         cpx x = {re[a], im[a]};
-        v[q] = q == 0 ? x : cmul(x, tw[(k * q) << 2]);   // exp(-2 pi i k q / 512)
+        v[q] = q == 0 ? x : cmul(x, tw.p3[q ? q - 1 : 0][k]);   // exp(-2 pi i k q / 512)
     }
     dft8(v);
 }
@@ -137,7 +157,7 @@ SAD_HD void fft_pass3_store(int t, const cpx* v, float* re, float* im) {
     }
 }
 // Pass 4: radix 4, Ns = 512; thread t handles j = t and j = t + 256.  Output is the natural-order spectrum.
-SAD_HD void fft_pass4_load(int t, const float* re, const float* im, const cpx* tw, cpx* v /*[8]*/) {
+SAD_HD void fft_pass4_load(int t, const float* re, const float* im, const FftTwiddles& tw, cpx* v /*[8]*/) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -148,7 +168,7 @@ SAD_HD void fft_pass4_load(int t, const float* re, const float* im, const cpx* t
 #endif
         for (int q = 0; q < 4; ++q) {
             cpx x = {re[j + 512 * q], im[j + 512 * q]};
-            v[4 * h + q] = q == 0 ? x : cmul(x, tw[j * q]);   // exp(-2 pi i j q / 2048)
+            v[4 * h + q] = q == 0 ? x : cmul(x, tw.p4[q ? q - 1 : 0][j]);   // exp(-2 pi i j q / 2048)
         }
         dft4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
     }

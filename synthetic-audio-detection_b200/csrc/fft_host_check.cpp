@@ -19,10 +19,13 @@ static int max_conflict(const std::vector<int>& addrs) {   // addrs: 32 word add
 }
 
 int main() {
-    std::vector<cpx> tw(kFftN);
-    for (int n = 0; n < kFftN; ++n) {
-        double ang = -2.0 * M_PI * n / kFftN;
-        tw[n] = {(float)std::cos(ang), (float)std::sin(ang)};
+    static FftTwiddles twt;
+    {
+        cpx* flat = reinterpret_cast<cpx*>(&twt);
+        for (int n = 0; n < kFftTwiddleCount; ++n) {
+            double ang = -2.0 * M_PI * fft_twiddle_angle(n) / kFftN;
+            flat[n] = {(float)std::cos(ang), (float)std::sin(ang)};
+        }
     }
     std::vector<float> a(kFftN), b(kFftN);
     srand(7);
@@ -37,11 +40,11 @@ int main() {
         for (int q = 0; q < 8; ++q) in8[q] = {a[t + 256 * q], b[t + 256 * q]};
         fft_pass1(t, in8, re.data(), im.data());
     }
-    for (int t = 0; t < kFftThreads; ++t) fft_pass2_load(t, re.data(), im.data(), tw.data(), &regs[t * 8]);
+    for (int t = 0; t < kFftThreads; ++t) fft_pass2_load(t, re.data(), im.data(), twt, &regs[t * 8]);
     for (int t = 0; t < kFftThreads; ++t) fft_pass2_store(t, &regs[t * 8], re.data(), im.data());
-    for (int t = 0; t < kFftThreads; ++t) fft_pass3_load(t, re.data(), im.data(), tw.data(), &regs[t * 8]);
+    for (int t = 0; t < kFftThreads; ++t) fft_pass3_load(t, re.data(), im.data(), twt, &regs[t * 8]);
     for (int t = 0; t < kFftThreads; ++t) fft_pass3_store(t, &regs[t * 8], re.data(), im.data());
-    for (int t = 0; t < kFftThreads; ++t) fft_pass4_load(t, re.data(), im.data(), tw.data(), &regs[t * 8]);
+    for (int t = 0; t < kFftThreads; ++t) fft_pass4_load(t, re.data(), im.data(), twt, &regs[t * 8]);
     for (int t = 0; t < kFftThreads; ++t) fft_pass4_store(t, &regs[t * 8], re.data(), im.data());
 
     // float64 reference
@@ -84,6 +87,42 @@ int main() {
             worst = std::max(worst, std::max(max_conflict(s1), std::max(max_conflict(l2), std::max(max_conflict(s2),
                              std::max(max_conflict(l3), max_conflict(s3))))));
         }
+    // twiddle reads are 8-byte: hardware serves a warp in two half-warp passes; within each, distinct 8-byte
+    // addresses must fall on distinct bank PAIRS (identical addresses broadcast)
+    auto conflict64 = [](const std::vector<long>& byte_addr) {
+        int w = 1;
+        for (int half = 0; half < 2; ++half) {
+            int cnt[16] = {0};
+            std::vector<long> seen;
+            for (int l = 16 * half; l < 16 * half + 16; ++l) {
+                bool dup = false;
+                for (long a : seen) dup |= (a == byte_addr[l]);
+                if (dup) continue;
+                seen.push_back(byte_addr[l]);
+                w = std::max(w, ++cnt[(byte_addr[l] / 8) & 15]);
+            }
+        }
+        return w;
+    };
+    int worst_tw = 1;
+    const char* base = reinterpret_cast<const char*>(&twt);
+    for (int w = 0; w < 8; ++w)
+        for (int q = 1; q < 8; ++q) {
+            std::vector<long> a2, a3, a4a, a4b;
+            for (int l = 0; l < 32; ++l) {
+                int t = w * 32 + l;
+                a2.push_back(reinterpret_cast<const char*>(&twt.p2[q - 1][t & 7]) - base);
+                a3.push_back(reinterpret_cast<const char*>(&twt.p3[q - 1][t & 63]) - base);
+                if (q < 4) {
+                    a4a.push_back(reinterpret_cast<const char*>(&twt.p4[q - 1][t]) - base);
+                    a4b.push_back(reinterpret_cast<const char*>(&twt.p4[q - 1][t + 256]) - base);
+                }
+            }
+            worst_tw = std::max(worst_tw, std::max(conflict64(a2), conflict64(a3)));
+            if (q < 4) worst_tw = std::max(worst_tw, std::max(conflict64(a4a), conflict64(a4b)));
+        }
+    printf("max_twiddle_conflict %d\n", worst_tw);
+    worst = std::max(worst, worst_tw);
     printf("max_bank_conflict %d\n", worst);
     int max_index = 0;
     for (int a2 = 0; a2 < kFftN; ++a2) max_index = std::max(max_index, std::max(pad1(a2), pad2(a2)));

@@ -39,7 +39,7 @@ __device__ __forceinline__ float ord2f(unsigned u) {
 }
 
 struct __align__(16) StftSmem {
-    cpx tw[kFftN];                  // 16 KB   exp(-2 pi i n / 2048)
+    FftTwiddles tw;                 // 16 KB   per-pass twiddle tables, conflict-free [q][k] layout
     float re[kFftBuf];              // 9 KB
     float im[kFftBuf];              // 9 KB
     float pw[2][772];               // power spectra of the two frames, bins 0..768 (mel support is 2..768)
@@ -64,10 +64,13 @@ __global__ void __launch_bounds__(kFftThreads) stft_mel_kernel(const float* __re
     const int nf = min(kFramesPerCta, kFrames - f0);
     const float* x = pcm + static_cast<size_t>(b) * kSeg;
 
-    for (int n = t; n < kFftN; n += kFftThreads) {
-        float sn, cs;
-        sincospif(static_cast<float>(n) * (1.0f / 1024.0f), &sn, &cs);
-        s.tw[n] = {cs, -sn};
+    {
+        cpx* flat = reinterpret_cast<cpx*>(&s.tw);
+        for (int n = t; n < kFftTwiddleCount; n += kFftThreads) {
+            float sn, cs;
+            sincospif(static_cast<float>(fft_twiddle_angle(n)) * (1.0f / 1024.0f), &sn, &cs);
+            flat[n] = {cs, -sn};
+        }
     }
     for (int i = t; i < 1536; i += kFftThreads) s.mel_w[i] = i < mel->n_weights ? mel->w[i] : 0.f;
     if (t < kMels) {
