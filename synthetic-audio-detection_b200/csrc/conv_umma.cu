@@ -24,6 +24,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "conv_umma.h"
 #include "ptx.cuh"
 
@@ -31,7 +33,6 @@ namespace sad {
 
 namespace {
 
-constexpr int kThreads = 192;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
@@ -43,17 +44,24 @@ struct Cfg {
     static constexpr int kBBytes = N_TILE * kBlockK * 2;
     static constexpr int kStageBytes = MT * kABytes + kBBytes;
     // epilogue staging: per epilogue warp kOutBufs buffers of [32 px][64 ch] bf16 (4 KB, SWIZZLE_128B) for TMA stores
-    static constexpr int kOutBufs = N_TILE == 256 ? 1 : 2;
-    static constexpr int kOutBytes = 4 * kOutBufs * 4096;
-    static constexpr int kStages = ((208 * 1024 - kOutBytes) / kStageBytes) > 8 ? 8 : ((208 * 1024 - kOutBytes) / kStageBytes);
     static constexpr int kAccCols = MT * N_TILE;                          // one accumulator set (MT tiles)
-    static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // double buffered: 128 / 256 / 512
+    static constexpr int kAccBufs = 2 * kAccCols <= 512 ? 2 : 1;          // double buffered when it fits TMEM
+    static constexpr int kTmemCols = kAccBufs * kAccCols < 32 ? 32 : kAccBufs * kAccCols;   // 128 / 256 / 512
     static_assert(kTmemCols <= 512, "accumulators do not fit TMEM");
+    // With a single accumulator set the MMA warp idles while it is drained, so the two M tiles are drained in parallel
+    // by two epilogue warp groups (8 warps).
+    static constexpr int kEpiGroups = (kAccBufs == 1 && MT == 2) ? 2 : 1;
+    static constexpr int kThreadsCfg = 64 + 128 * kEpiGroups;
+    static constexpr int kOutBufs = N_TILE == 256 ? 1 : 2;
+    static constexpr int kOutBytes = 4 * kEpiGroups * kOutBufs * 4096;
+    static constexpr int kBudget = 224 * 1024;
+    static constexpr int kStages = ((kBudget - kOutBytes) / kStageBytes) > 8 ? 8 : ((kBudget - kOutBytes) / kStageBytes);
     static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 template <int N_TILE, int MT>
-__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvLaunch p) {
+__global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_kernel(const __grid_constant__ ConvLaunch p) {
     using C = Cfg<N_TILE, MT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -83,7 +91,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);
+            mbar_init(&tmem_empty[a], 4 * C::kEpiGroups);
         }
         fence_barrier_init();
     }
@@ -160,8 +168,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < total_groups; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                const int acc = it % C::kAccBufs;
+                mbar_wait(&tmem_empty[acc], ((it / C::kAccBufs) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
                 for (int ks = 0; ks < ksteps; ++ks) {
@@ -191,7 +199,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         // straight to global touches 32 lines per store instruction and made the epilogue the bottleneck).
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;          // pixel inside the 128-pixel tile
-        uint8_t* my_out = out_sm + quarter * C::kOutBufs * 4096;
+        const int egroup = (warp - 2) >> 2;           // which epilogue warp group (0 unless kEpiGroups == 2)
+        uint8_t* my_out = out_sm + (egroup * 4 + quarter) * C::kOutBufs * 4096;
         int it = 0;
         uint32_t nstore = 0;
         for (int tile = blockIdx.x; tile < total_groups; tile += gridDim.x, ++it) {
@@ -201,14 +210,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             r /= p.n_tiles;
             const int m_t = (r % m_groups) * MT;
             const int img = r / m_groups;
-            const int acc = it & 1;
+            const int acc = it % C::kAccBufs;
             const int co0 = n_t * N_TILE;
             const float4* bias4 = reinterpret_cast<const float4*>(p.bias + head * p.Cout + co0);
 
-            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            mbar_wait(&tmem_full[acc], (it / C::kAccBufs) & 1);
             tc_fence_after();
+            const int m_lo = C::kEpiGroups == 2 ? egroup : 0;
+            const int m_hi = C::kEpiGroups == 2 ? egroup + 1 : MT;
 #pragma unroll 1
-            for (int m = 0; m < MT; ++m) {
+            for (int m = m_lo; m < m_hi; ++m) {
             const long long pix0 = (static_cast<long long>(head) * p.imgs_per_head + img) * (p.m_tiles_per_img * kBlockM) +
                                    (m_t + m) * kBlockM;
             const __nv_bfloat16* res = p.residual ? p.residual + (pix0 + row) * p.Cout + co0 : nullptr;
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     for (int q = 0; q < 8; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(res + c0) + q);
                 }
                 tmem_ld_wait();
-                if (c0 + 64 >= N_TILE && m == MT - 1) {   // whole accumulator set is in registers: hand TMEM back to the MMA warp
+                if (c0 + 64 >= N_TILE && m == m_hi - 1) {   // this group's accumulators are in registers: hand TMEM back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -291,7 +302,7 @@ cudaError_t launch_t(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
     }
     const int groups = p.total_tiles / MT;
     int grid = groups < num_sms ? groups : num_sms;
-    conv_umma_kernel<N_TILE, MT><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+    conv_umma_kernel<N_TILE, MT><<<grid, C::kThreadsCfg, C::kSmemBytes, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -303,7 +314,8 @@ cudaError_t conv_umma_launch(const ConvLaunch& p, int num_sms, cudaStream_t stre
     switch (p.n_tile) {
         case 64: return launch_t<64, 1>(p, num_sms, stream);
         case 128: return (p.m_tiles_per_img % 2 == 0) ? launch_t<128, 2>(p, num_sms, stream) : launch_t<128, 1>(p, num_sms, stream);
-        case 256: return launch_t<256, 1>(p, num_sms, stream);
+        case 256: return (p.m_tiles_per_img % 2 == 0 && getenv("SAD_MT256") && atoi(getenv("SAD_MT256")) == 2)
+                             ? launch_t<256, 2>(p, num_sms, stream) : launch_t<256, 1>(p, num_sms, stream);
         default: return cudaErrorInvalidValue;
     }
 }
