@@ -269,6 +269,13 @@ def run_native(args):
     conv_tflop = sum(flops[i] for i in range(20)) * 1e9 * H * B * K / 1e12
     achieved = conv_tflop / (conv_ms / 1e3) if conv_ms > 0 else 0.0
     peak = pk["bf16_tflops_sustained"]
+    traffic = None                              # DRAM bytes per conv launch from the committed ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+        if tj.get("chunk") == args.max_batch and tj.get("heads") == H:
+            traffic = tj["dram_bytes_per_launch_mean"]
     per_layer = {str(i): round(flops[i] * 1e9 * H * B * K / 1e12 / (prof_ms[i] / 1e3), 1) if prof_ms[i] > 0 else None
                  for i in range(20)}
     fe_ms = prof_ms[20]
@@ -285,8 +292,9 @@ def run_native(args):
                    "weights": "random-init resnet18 x heads (seed 0)", "parallelism": f"segment-sharded x{world}"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak if peak else None, "traffic": None,
-                     "kernel": "conv_umma_kernel<64|128|256> (20 launches per chunk)",
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "kernel": "conv_umma_kernel<128,2|256,1> + conv_rows_kernel + stem_fused_kernel (17 launches per chunk)",
+                     "algorithmic_bytes_per_launch": (H * args.max_batch * 40.0e6) / 17.0,
                      "flops_model": "18.1278 GFLOP/head/segment (channel-folded stem, K=49)",
                      "peak_source": pk["source"] + " bf16_tflops_sustained",
                      "kernel_ms_per_step": conv_ms / K, "kernel_launches": int(conv_launches),
