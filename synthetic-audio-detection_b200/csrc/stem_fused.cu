@@ -18,7 +18,7 @@
 //   builders (4 warps): read the bf16 image (L2 resident) with 8-byte loads, funnel-shift, write the [256 px][128 B]
 //                       pixel tile into SWIZZLE_128B shared memory; double buffered.
 //   MMA (1 thread)    : 4 x tcgen05.mma 128x256x16 per conv row into TMEM (2 buffers x 256 columns).
-//   epilogue (8 warps): per thread = one channel x one half of the row (128 conv px): 4 x tcgen05.ld of 32 columns
+//   epilogue (8 warps): per thread = one channel x one half of the row (128 conv px): 4 x tcgen05.ld of 32 columns (16 warps measured slower)
 //                       (software-pipelined against the pooling math), pooling, ReLU, bf16; every second conv row the
 //                       pooled row is transposed through swizzled smem and written with TMA stores
 //                       ([128 px][64 ch] per head).
@@ -33,7 +33,11 @@ namespace sad {
 
 namespace {
 
-constexpr int kThreads = 416;                  // warp 0: MMA + TMA; warps 1-4: builders; warps 5-12: epilogue (2 groups)
+constexpr int kEpiGroups = 2;                  // epilogue warp groups; each owns 256/kEpiGroups conv pixels of a row
+constexpr int kEpiThreads = 128 * kEpiGroups;
+constexpr int kGroupCols = 256 / kEpiGroups;   // conv pixels (TMEM columns) per group
+constexpr int kChunks = kGroupCols / 32;       // tcgen05.ld chunks of 32 columns per group and row
+constexpr int kThreads = 32 + 128 + kEpiThreads;   // warp 0: MMA + TMA; warps 1-4: builders; then the epilogue warps
 constexpr int kStripRows = 32;                 // pooled rows per unit
 constexpr int kStrips = 128 / kStripRows;
 constexpr int kConvRowsPerUnit = 2 * kStripRows + 1;
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
     uint64_t* w_full = bars + 4;        // [2] TMA
     uint64_t* w_empty = bars + 6;       // [2] tcgen05.commit
     uint64_t* tmem_full = bars + 8;     // [2]
-    uint64_t* tmem_empty = bars + 10;   // [2] count 8 (epilogue warps)
+    uint64_t* tmem_empty = bars + 10;   // [2] count 4 * kEpiGroups (epilogue warps)
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5;
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
             mbar_init(&w_full[i], 1);
             mbar_init(&w_empty[i], 1);
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 8);
+            mbar_init(&tmem_empty[i], 4 * kEpiGroups);
         }
         fence_barrier_init();
     }
@@ -191,13 +195,13 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
     } else {
         // ------------------------------------------------------------------ epilogue: pool + transpose + store
         const int q = warp & 3;                        // TMEM lane quarter
-        const int half = (warp - 5) >> 2;              // 0: conv px 0..127 (pooled 0..63), 1: conv px 128..255
+        const int half = (warp - 5) >> 2;              // column group: conv px [half*kGroupCols, +kGroupCols)
         const int c = q * 32 + lane;                   // channel within the head pair (lane of the accumulator)
         const int hh = c >> 6;                         // head within the pair
         const int cc = c & 63;                         // channel within the head
-        const int et = threadIdx.x - 5 * 32;           // 0..255 within the epilogue group
+        const int et = threadIdx.x - 5 * 32;           // 0 .. kEpiThreads-1 within the epilogue warps
         uint32_t arow = 0, nemit = 0;
-        uint32_t carry[32];                            // running vertical max: 64 pooled px as packed bf16 pairs
+        uint32_t carry[kGroupCols / 4];                // running vertical max: kGroupCols/2 pooled px as packed bf16 pairs
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
             const int g = u / units_per_group;
             const int r0 = u % units_per_group;
@@ -210,17 +214,17 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                 const int eb = nemit & 1;
                 if (emit) {
                     if (et == 0) tma_store_wait_read<1>();         // staging buffer `eb` has been read out
-                    named_bar_sync(1, 256);
+                    named_bar_sync(1, kEpiThreads);
                 }
                 mbar_wait(&tmem_full[b], (arow >> 1) & 1);
                 tc_fence_after();
-                const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * 256 + half * 128;
+                const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * 256 + half * kGroupCols;
                 uint8_t* stage = out_sm + (eb * 2 + hh) * kHeadTile + (cc & 7) * 2;   // + swizzled (px, chunk cc/8)
                 uint32_t va[32], vb[32];
                 float prev = -INFINITY;                            // conv pixel 2p-1 of the first pooled px
                 if (half) {
                     uint32_t pv;
-                    tmem_ld1(tbase - 1, pv);                       // conv px 127 belongs to the other half
+                    tmem_ld1(tbase - 1, pv);                       // the conv px just left of this group's columns
                     tmem_ld32(tbase, va);
                     tmem_ld_wait_dep(va);
                     asm volatile("" : "+r"(pv));
@@ -230,9 +234,9 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                     tmem_ld_wait_dep(va);
                 }
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb) {                   // 32 conv pixels -> 16 pooled pixels
+                for (int cb = 0; cb < kChunks; ++cb) {             // 32 conv pixels -> 16 pooled pixels
                     const uint32_t* v = (cb & 1) ? vb : va;
-                    if (cb < 3) {                                    // next chunk in flight while this one is pooled
+                    if (cb < kChunks - 1) {                          // next chunk in flight while this one is pooled
                         if (cb & 1) tmem_ld32(tbase + (cb + 1) * 32, va);
                         else tmem_ld32(tbase + (cb + 1) * 32, vb);
                     }
@@ -259,16 +263,16 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                         for (int j = 0; j < 8; ++j) {
                             const uint32_t o = bf16x2_max(bf16x2_max(carry[cb * 8 + j], hb[j]), 0u);
                             carry[cb * 8 + j] = hb[j];
-                            const int px = half * 64 + cb * 16 + 2 * j;
+                            const int px = half * (kGroupCols / 2) + cb * 16 + 2 * j;
                             *reinterpret_cast<uint16_t*>(stage + sw128_offset(px, cc >> 3)) = static_cast<uint16_t>(o & 0xFFFFu);
                             *reinterpret_cast<uint16_t*>(stage + sw128_offset(px + 1, cc >> 3)) = static_cast<uint16_t>(o >> 16);
                         }
                     }
-                    if (cb < 3) {
+                    if (cb < kChunks - 1) {
                         if (cb & 1) tmem_ld_wait_dep(va);
                         else tmem_ld_wait_dep(vb);
                     }
-                    if (cb == 2) {                                  // last chunk is in registers: release the TMEM buffer
+                    if (cb == kChunks - 2) {                        // last chunk is in registers: release the TMEM buffer
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty[b]);
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                 }
                 if (emit) {
                     fence_proxy_async();
-                    named_bar_sync(1, 256);
+                    named_bar_sync(1, kEpiThreads);
                     if (et == 0) {
                         const int py = py0 + (t >> 1) - 1;
 #pragma unroll
