@@ -280,6 +280,8 @@ def run_native(args):
                  for i in range(20)}
     fe_ms = prof_ms[20]
     fe_gbs = (B * K * 512000 / 1e9) / (fe_ms / 1e3) if fe_ms > 0 else 0.0
+    fe_tflops = (B * K * 16.0e6 / 1e12) / (fe_ms / 1e3) if fe_ms > 0 else 0.0
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # SMs x FMA lanes x 2 x max SM clock
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -288,7 +290,7 @@ def run_native(args):
                                "per GPU; per-clip decisions (32-segment clips) reduced and gathered",
                    "batch_per_gpu": B, "heads": H, "outputs": H + 1, "internal_chunk": args.max_batch,
                    "l2": "inputs larger than L2 (1.05 GB PCM per step, activations ~%d MB per chunk); no flush"
-                         % int(args.max_batch * H * 15),
+                         % int(args.max_batch * H * 7),
                    "weights": "random-init resnet18 x heads (seed 0)", "parallelism": f"segment-sharded x{world}"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -302,7 +304,11 @@ def run_native(args):
                      "per_conv_tflops": per_layer},
         "roofline_frontend": {"bound": "hbm", "achieved": fe_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                               "frac": fe_gbs / pk["hbm_gbs"], "bytes_model": "512000 B/segment (PCM in; log-mel "
-                              "stays on the device for the fused path)", "kernel_ms_per_step": fe_ms / K},
+                              "stays on the device for the fused path)", "kernel_ms_per_step": fe_ms / K,
+                              # the front end is above the CUDA-core ridge: compute-side view
+                              "compute": {"flops_model": "16 MFLOP fp32/segment (126 packed 2048-pt FFTs + window, "
+                                          "power, mel, log)", "achieved_tflops": fe_tflops,
+                                          "fp32_peak_tflops": fp32_peak, "frac": fe_tflops / fp32_peak}},
         "other_ms_per_step": {"image_im2col": prof_ms[21] / K, "maxpool": prof_ms[22] / K, "head_merge": prof_ms[23] / K},
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -293,13 +293,8 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
 template <int N_TILE, int MT>
 cudaError_t launch_t(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
     using C = Cfg<N_TILE, MT>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<N_TILE, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             C::kSmemBytes);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    cudaError_t e = ensure_dynamic_smem(conv_umma_kernel<N_TILE, MT>, C::kSmemBytes);
+    if (e != cudaSuccess) return e;
     const int groups = p.total_tiles / MT;
     int grid = groups < num_sms ? groups : num_sms;
     conv_umma_kernel<N_TILE, MT><<<grid, C::kThreadsCfg, C::kSmemBytes, stream>>>(p);

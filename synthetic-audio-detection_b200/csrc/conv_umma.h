@@ -29,6 +29,21 @@ struct alignas(64) ConvLaunch {
     int k2_blocks;          // Cin2 / 64 extra K blocks read through a2_map / b2_map (0 = none)
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per (kernel, device).
+template <typename K>
+inline cudaError_t ensure_dynamic_smem(K kernel, int bytes) {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    return cudaSuccess;
+}
+
 int conv_n_tile(int Cout);
 cudaError_t conv_umma_launch(const ConvLaunch& p, int num_sms, cudaStream_t stream);
 

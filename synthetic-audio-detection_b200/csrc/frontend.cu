@@ -341,12 +341,17 @@ size_t stft_smem_bytes() { return sizeof(StftSmem); }
 
 cudaError_t frontend_logmel_launch(const float* pcm, int B, const float* window, const MelTable* mel, float* db_work,
                                    unsigned* segmax, float* out_db, float* mu_sigma, cudaStream_t stream, long long* launches) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(sizeof(StftSmem)));
+    {
+        static bool done[64] = {false};
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev < 0 || dev >= 64 || !done[dev]) {
+            e = cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(sizeof(StftSmem)));
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
     }
     fill_u32_kernel<<<(B + 255) / 256, 256, 0, stream>>>(segmax, 0u, B);   // 0 orders below every float
     stft_mel_kernel<<<dim3(kFrameGroups, B), kFftThreads, sizeof(StftSmem), stream>>>(pcm, window, mel, db_work, segmax);

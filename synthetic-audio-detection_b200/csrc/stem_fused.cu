@@ -26,6 +26,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include "conv_umma.h"
 #include "ptx.cuh"
 #include "stem_fused.h"
 
@@ -308,12 +309,8 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
 }  // namespace
 
 cudaError_t stem_fused_launch(const StemLaunch& p_in, int num_sms, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    cudaError_t e = ensure_dynamic_smem(stem_fused_kernel, kSmemBytes);
+    if (e != cudaSuccess) return e;
     StemLaunch p = p_in;
     p.G = (p.H + 1) / 2;
     p.total_units = p.G * p.B * kStrips;
