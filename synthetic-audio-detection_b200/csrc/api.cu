@@ -168,6 +168,7 @@ struct sad_ctx {
     std::vector<sad::ConvLaunch> plan_launch;
     std::vector<Step> plan;
     bool stem3_ready = false;
+    int two_cta = 1;                    // 1: N=256 layers (layers 3-4) run on CTA pairs (conv_umma2.cu, cta_group::2); 2: N=128 too (slower)
     int fuse_ds = 1;                    // fold each block's 1x1/s2 downsample conv into conv2 as extra K blocks
     float* d_bias_fused[20] = {nullptr}; // [H][Cout] = bias(conv2) + bias(downsample) for conv indices 6, 11, 16
     int rows_mode = 2;                  // layer1 row-stationary kernel: 0 off, 2 on (1 = probe: descriptor base-offset field set, WRONG on sm_100a)
@@ -386,6 +387,13 @@ bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const b
     L->k2_blocks = 0;
     L->a2_map = L->a_map[0];
     L->b2_map = L->b_map;
+    if (n_tile >= 128) {
+        if (!sad::encode_weight_map(&L->bh_map, c->d_w[ci], K, 1LL * c->H * s.cout, n_tile / 2, c->err, sizeof(c->err)))
+            return false;
+    } else {
+        L->bh_map = L->b_map;
+    }
+    L->b2h_map = L->bh_map;
     if (fused_ds >= 0) {
         const ConvSpec& d = convs()[fused_ds];         // 1x1, stride 2, pad 0, same Cout and output size as `s`
         if (d.cout != s.cout || d.hout != s.hout || d.k != 1 || d.stride != 2) {
@@ -396,6 +404,9 @@ bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const b
                                  1LL * d.hin * d.hin * d.cin, Wo, rows, c->err, sizeof(c->err)))
             return false;
         if (!sad::encode_weight_map(&L->b2_map, c->d_w[fused_ds], d.cin, 1LL * c->H * d.cout, n_tile, c->err, sizeof(c->err)))
+            return false;
+        if (!sad::encode_weight_map(&L->b2h_map, c->d_w[fused_ds], d.cin, 1LL * c->H * d.cout, n_tile / 2, c->err,
+                                    sizeof(c->err)))
             return false;
         L->k2_blocks = d.cin / 64;
         L->bias = c->d_bias_fused[ci];
@@ -439,6 +450,8 @@ bool is_rows_layer(int ci);
 cudaError_t launch_conv(sad_ctx* c, int ci, const sad::ConvLaunch& L, int heads, cudaStream_t st) {
     if (ci > 0 && c->rows_mode && is_rows_layer(ci))
         return sad::conv_rows_launch(L, heads, c->rows_mode == 1 ? 1 : 0, c->num_sms, st);
+    if (c->two_cta && L.n_tile >= (c->two_cta >= 2 ? 128 : 256) && L.m_tiles_per_img % 2 == 0)
+        return sad::conv_umma2_launch(L, c->num_sms, st);
     return sad::conv_umma_launch(L, c->num_sms, st);
 }
 
@@ -588,6 +601,7 @@ int sad_create(sad_ctx** out, int device, int n_heads, int max_batch) {
     c->loaded.assign(n_heads, 0);
     if (const char* e = getenv("SAD_CONV_ROWS")) c->rows_mode = atoi(e);
     if (const char* e = getenv("SAD_FUSE_DS")) c->fuse_ds = atoi(e);
+    if (const char* e = getenv("SAD_2CTA")) c->two_cta = atoi(e);
     *out = c;   // returned even on failure so the caller can read sad_last_error, then sad_destroy
     CU_OK(c, cudaSetDevice(device));
 
@@ -965,6 +979,10 @@ int sad_debug_conv(sad_ctx* c, int head, int layer, const void* in, const void* 
     const ConvSpec& s = convs()[layer];
     const long long K = 1LL * s.k * s.k * s.cin;
     if (!sad::encode_weight_map(&L.b_map, c->d_w[layer] + static_cast<size_t>(head) * s.cout * K, K, s.cout, L.n_tile, c->err,
+                                sizeof(c->err)))
+        return SAD_ECUDA;
+    if (L.n_tile >= 128 &&
+        !sad::encode_weight_map(&L.bh_map, c->d_w[layer] + static_cast<size_t>(head) * s.cout * K, K, s.cout, L.n_tile / 2, c->err,
                                 sizeof(c->err)))
         return SAD_ECUDA;
     L.bias = c->d_bias[layer] + static_cast<size_t>(head) * s.cout;

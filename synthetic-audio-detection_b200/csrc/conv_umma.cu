@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
 template <int N_TILE, int MT>
 cudaError_t launch_t(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
     using C = Cfg<N_TILE, MT>;
-    cudaError_t e = ensure_dynamic_smem(conv_umma_kernel<N_TILE, MT>, C::kSmemBytes);
+    cudaError_t e = ensure_dynamic_smem<conv_umma_kernel<N_TILE, MT>>(C::kSmemBytes);
     if (e != cudaSuccess) return e;
     const int groups = p.total_tiles / MT;
     int grid = groups < num_sms ? groups : num_sms;

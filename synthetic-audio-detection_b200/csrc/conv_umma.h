@@ -13,6 +13,8 @@ struct alignas(64) ConvLaunch {
     CUtensorMap res_map;    // residual viewed as {Cout, pixels}: box {64 ch, 128 px} (TMA load); valid iff residual
     CUtensorMap a2_map;     // optional second input (fused 1x1/stride-2 downsample branch): parity-(0,0) view of the block input
     CUtensorMap b2_map;     // its weights [heads*Cout][Cin2] bf16; the extra k2_blocks K-steps accumulate into the same tile
+    CUtensorMap bh_map;     // b_map / b2_map with box {64, n_tile/2}: each CTA of a 2-CTA pair loads half of the N rows
+    CUtensorMap b2h_map;
     const float* bias;      // [heads*Cout] fp32 (folded BN shift)
     const __nv_bfloat16* residual;   // NHWC [heads*imgs][Ho*Wo][Cout] or nullptr
     __nv_bfloat16* out;     // NHWC [heads*imgs][Ho*Wo][Cout]
@@ -29,15 +31,16 @@ struct alignas(64) ConvLaunch {
     int k2_blocks;          // Cin2 / 64 extra K blocks read through a2_map / b2_map (0 = none)
 };
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per (kernel, device).
-template <typename K>
-inline cudaError_t ensure_dynamic_smem(K kernel, int bytes) {
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per (kernel, device).  The kernel is a
+// non-type template parameter so every kernel gets its own flags (kernels with the same signature share one TYPE).
+template <auto Kernel>
+inline cudaError_t ensure_dynamic_smem(int bytes) {
     static bool done[64] = {false};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64 || !done[dev]) {
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) done[dev] = true;
     }
@@ -46,6 +49,8 @@ inline cudaError_t ensure_dynamic_smem(K kernel, int bytes) {
 
 int conv_n_tile(int Cout);
 cudaError_t conv_umma_launch(const ConvLaunch& p, int num_sms, cudaStream_t stream);
+// 2-CTA (cta_group::2) variant: M = 256 per CTA pair, B split across the pair.  Requires an even m_tiles_per_img.
+cudaError_t conv_umma2_launch(const ConvLaunch& p, int num_sms, cudaStream_t stream);
 
 // Tensor-map construction (api.cu): resolves cuTensorMapEncodeTiled through the runtime so that the
 // library does not link against libcuda and still loads on a machine without a driver.

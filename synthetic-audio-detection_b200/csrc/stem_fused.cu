@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
 }  // namespace
 
 cudaError_t stem_fused_launch(const StemLaunch& p_in, int num_sms, cudaStream_t stream) {
-    cudaError_t e = ensure_dynamic_smem(stem_fused_kernel, kSmemBytes);
+    cudaError_t e = ensure_dynamic_smem<stem_fused_kernel>(kSmemBytes);
     if (e != cudaSuccess) return e;
     StemLaunch p = p_in;
     p.G = (p.H + 1) / 2;
