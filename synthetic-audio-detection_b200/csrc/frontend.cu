@@ -208,10 +208,12 @@ template <>
 __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 // Standardise + separable 2-tap resize (horizontal first, taps accumulated with one fma each, as ATen does).
-// grid (512 rows, B), 256 threads (2 output columns each).
+// grid (512 rows, B), 256 threads.  The two source rows of an output row are standardised ONCE into shared memory
+// (502 IEEE divisions per CTA instead of 4 per output pixel), then every thread produces two output columns.
 template <typename T>
 __global__ void __launch_bounds__(256) image_kernel(const float* __restrict__ db, const float* __restrict__ mu_sigma,
                                                     const ResizeTable* __restrict__ rt, T* __restrict__ img) {
+    __shared__ float rows[2][256];
     const int b = blockIdx.y, y = blockIdx.x;
     const float mu = mu_sigma[2 * b];
     const float den = mu_sigma[2 * b + 1] + 1e-6f;
@@ -219,16 +221,17 @@ __global__ void __launch_bounds__(256) image_kernel(const float* __restrict__ db
     const int y0 = rt->h_idx[y];
     const int y1 = min(y0 + 1, kMels - 1);
     const float wy0 = rt->h_w[2 * y], wy1 = rt->h_w[2 * y + 1];
-    const float* r0 = src + y0 * kFrames;
-    const float* r1 = src + y1 * kFrames;
+    if (threadIdx.x < kFrames) {
+        rows[0][threadIdx.x] = __fdiv_rn(src[y0 * kFrames + threadIdx.x] - mu, den);
+        rows[1][threadIdx.x] = __fdiv_rn(src[y1 * kFrames + threadIdx.x] - mu, den);
+    }
+    __syncthreads();
     for (int x = threadIdx.x; x < 512; x += 256) {
         const int x0 = rt->w_idx[x];
         const int x1 = min(x0 + 1, kFrames - 1);
         const float wx0 = rt->w_w[2 * x], wx1 = rt->w_w[2 * x + 1];
-        const float a00 = __fdiv_rn(r0[x0] - mu, den), a01 = __fdiv_rn(r0[x1] - mu, den);
-        const float a10 = __fdiv_rn(r1[x0] - mu, den), a11 = __fdiv_rn(r1[x1] - mu, den);
-        const float t0 = __fmaf_rn(a01, wx1, __fmul_rn(a00, wx0));
-        const float t1 = __fmaf_rn(a11, wx1, __fmul_rn(a10, wx0));
+        const float t0 = __fmaf_rn(rows[0][x1], wx1, __fmul_rn(rows[0][x0], wx0));
+        const float t1 = __fmaf_rn(rows[1][x1], wx1, __fmul_rn(rows[1][x0], wx0));
         const float v = __fmaf_rn(t1, wy1, __fmul_rn(t0, wy0));
         img[(static_cast<size_t>(b) * 512 + y) * 512 + x] = to_out<T>(v);
     }
