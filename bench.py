@@ -278,7 +278,7 @@ def run_native(args):
             traffic = tj["dram_bytes_per_launch_mean"]
     per_layer = {str(i): round(flops[i] * 1e9 * H * B * K / 1e12 / (prof_ms[i] / 1e3), 1) if prof_ms[i] > 0 else None
                  for i in range(20)}
-    fe_ms = prof_ms[20]
+    fe_ms = prof_ms[eng.PROF_FRONTEND]
     fe_gbs = (B * K * 512000 / 1e9) / (fe_ms / 1e3) if fe_ms > 0 else 0.0
     fe_tflops = (B * K * 16.0e6 / 1e12) / (fe_ms / 1e3) if fe_ms > 0 else 0.0
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # SMs x FMA lanes x 2 x max SM clock
@@ -309,7 +309,7 @@ def run_native(args):
                               "compute": {"flops_model": "16 MFLOP fp32/segment (126 packed 2048-pt FFTs + window, "
                                           "power, mel, log)", "achieved_tflops": fe_tflops,
                                           "fp32_peak_tflops": fp32_peak, "frac": fe_tflops / fp32_peak}},
-        "other_ms_per_step": {"image_im2col": prof_ms[21] / K, "maxpool": prof_ms[22] / K, "head_merge": prof_ms[23] / K},
+        "other_ms_per_step": {"image": prof_ms[eng.PROF_IMAGE] / K, "head_merge": prof_ms[eng.PROF_HEAD] / K},
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

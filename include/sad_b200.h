@@ -47,6 +47,11 @@ typedef struct sad_ctx sad_ctx;
  * (ModularMultiHeadClassifier, inference_runner.py:53-73); `max_batch` = segments processed per
  * internal pass (workspace is sized for it; larger batches are chunked).                        */
 int sad_create(sad_ctx** out, int device, int n_heads, int max_batch);
+/* Same with the backbone named explicitly: "resnet18" (default) or "resnet34" -- the BasicBlock ResNets that
+ * `--model-name` / `backbone_name` may select (model_merger.py:101, inference_runner.py:77).  Bottleneck variants
+ * (resnet50+) return SAD_EINVAL.                                                                          */
+int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const char* backbone);
+const char* sad_backbone(const sad_ctx* ctx);
 int sad_destroy(sad_ctx* ctx);
 const char* sad_last_error(const sad_ctx* ctx);
 const char* sad_version(void);
@@ -55,9 +60,12 @@ const char* sad_version(void);
 /* The library describes the fp32 tensors it needs for ONE BinaryClassifier (inference_runner.py:28-51),
  * in state_dict order without the int64 num_batches_tracked entries: name i is the key suffix after
  * "sub_models.<h>." (e.g. "base.layer1.0.conv1.weight", "head.3.running_var").                    */
-int sad_weight_count(void);
+int sad_weight_count(void);                 /* resnet18 */
 const char* sad_weight_name(int i);
 long long sad_weight_numel(int i);
+int sad_backbone_weight_count(const char* backbone);      /* -1 for an unsupported backbone */
+const char* sad_backbone_weight_name(const char* backbone, int i);
+long long sad_backbone_weight_numel(const char* backbone, int i);
 /* host_tensors[i] points at sad_weight_numel(i) contiguous fp32 values.  Eval-mode BatchNorm is folded
  * into the preceding conv / Linear in fp64 and the conv weights are rounded once to bf16.          */
 int sad_load_weights(sad_ctx* ctx, int head, const float* const* host_tensors, int n_tensors);
@@ -114,14 +122,15 @@ int sad_max_batch(const sad_ctx* ctx);
 /* Number of kernels this library has launched on the context since creation. */
 long long sad_launch_count(const sad_ctx* ctx);
 /* Live profiling (bench.py): when enabled, every kernel class launched by sad_forward* is bracketed by CUDA events
- * on the launching stream.  Kinds 0..19 = the 20 convolutions in state_dict order (0 = stem), then the classes
+ * on the launching stream.  Kinds 0..39 = the convolutions in state_dict order (0 = stem; 20 for resnet18), then the classes
  * below.  sad_profile_read synchronises on the recorded events and returns accumulated milliseconds and the number
  * of bracketed launch groups per kind (arrays of SAD_PROF_KINDS).  Enabling resets the counters.              */
-#define SAD_PROF_FRONTEND 20 /* fill + stft_mel + db_clamp_stats                  */
-#define SAD_PROF_IMAGE 21    /* standardise/resize image + stem im2col            */
-#define SAD_PROF_POOL 22     /* 3x3/2 max pool                                    */
-#define SAD_PROF_HEAD 23     /* avg-pool + MLP + merge + decision                 */
-#define SAD_PROF_KINDS 24
+#define SAD_PROF_CONV_SLOTS 40 /* kinds 0..39: convolutions in state_dict order      */
+#define SAD_PROF_FRONTEND 40   /* fill + stft_mel + db_clamp_stats                  */
+#define SAD_PROF_IMAGE 41      /* standardise/resize image (+ stem im2col, 3-ch)    */
+#define SAD_PROF_POOL 42       /* 3x3/2 max pool (3-channel path only)              */
+#define SAD_PROF_HEAD 43       /* avg-pool + MLP + merge + decision                 */
+#define SAD_PROF_KINDS 44
 int sad_profile_enable(sad_ctx* ctx, int on);
 int sad_profile_read(sad_ctx* ctx, double* ms_by_kind, long long* launches_by_kind);
 /* Run ONE convolution layer of one head on caller buffers (NHWC bf16): layer = index into the 20 convs in

@@ -43,8 +43,10 @@ def backbone_bf16(img1: torch.Tensor, sd: Dict[str, torch.Tensor], p: str, taps:
     if taps is not None:
         taps.append(("stem", x))
     for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
-        for blk in range(2):
+        for blk in range(64):
             q = f"{p}layer{li}.{blk}"
+            if (q + ".conv1.weight") not in sd:
+                break
             s = stride if blk == 0 else 1
             w, b = fold_bn(sd[q + ".conv1.weight"], sd, q + ".bn1")
             o = _q(F.relu(F.conv2d(x, _q(w), b, stride=s, padding=1)))

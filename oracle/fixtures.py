@@ -76,11 +76,14 @@ def synth_clip(n_samples: int, seed: int, silent_spans=()) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # weights
 # --------------------------------------------------------------------------------------
-def _layer_plan():
-    """(kind, name, ...) in the order timm/torchvision ResNet-18 registers its modules."""
+DEPTHS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3)}
+
+
+def _layer_plan(backbone: str = "resnet18"):
+    """(kind, name, ...) in the order timm/torchvision BasicBlock ResNets register their modules."""
     plan = [("conv", "conv1", 64, 3, 7), ("bn", "bn1", 64)]
     for li, (cin, cout) in enumerate(((64, 64), (64, 128), (128, 256), (256, 512)), start=1):
-        for b in range(2):
+        for b in range(DEPTHS[backbone][li - 1]):
             p = f"layer{li}.{b}"
             c0 = cin if b == 0 else cout
             plan += [("conv", f"{p}.conv1", cout, c0, 3), ("bn", f"{p}.bn1", cout),
@@ -104,10 +107,10 @@ def _rand_linear(sd, key, fin, fout, g):
     sd[key + ".bias"] = (2 * torch.rand(fout, generator=g) - 1) * bound
 
 
-def random_head_state(g: torch.Generator) -> "OrderedDict[str, torch.Tensor]":
-    """One BinaryClassifier's state_dict (136 keys: 120 base + 16 head), fp32, module order."""
+def random_head_state(g: torch.Generator, backbone: str = "resnet18") -> "OrderedDict[str, torch.Tensor]":
+    """One BinaryClassifier's state_dict (resnet18: 136 keys = 120 base + 16 head), fp32, module order."""
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
-    for item in _layer_plan():
+    for item in _layer_plan(backbone):
         if item[0] == "conv":
             _, name, cout, cin, k = item
             std = math.sqrt(2.0 / (cout * k * k))        # kaiming_normal_(fan_out, relu)
@@ -141,8 +144,10 @@ def _calibrate(sd: Dict[str, torch.Tensor], images: torch.Tensor, head_index: in
         x = F.relu(R._bn(x, sd, p + "bn1"))
         x = F.max_pool2d(x, 3, 2, 1)
         for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
-            for b in range(2):
+            for b in range(64):
                 q = f"{p}layer{li}.{b}"
+                if (q + ".conv1.weight") not in sd:
+                    break
                 s = stride if b == 0 else 1
                 o = F.conv2d(x, sd[q + ".conv1.weight"], None, stride=s, padding=1)
                 stat(o, q + ".bn1", (0, 2, 3))
@@ -193,7 +198,7 @@ _CAL_CACHE = {}
 
 
 def merged_state_dict(n_heads: int, seed: int = WEIGHT_SEED, calibrate: bool = True,
-                      n_cal: int = N_CAL) -> "OrderedDict[str, torch.Tensor]":
+                      n_cal: int = N_CAL, backbone: str = "resnet18") -> "OrderedDict[str, torch.Tensor]":
     """Merged ModularMultiHeadClassifier.state_dict() with keys ``sub_models.<i>.*`` (MM:154-159)."""
     imgs = None
     if calibrate:
@@ -203,7 +208,7 @@ def merged_state_dict(n_heads: int, seed: int = WEIGHT_SEED, calibrate: bool = T
     merged: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     for i in range(n_heads):
         g = torch.Generator().manual_seed(seed * 1000 + i)
-        sd = random_head_state(g)
+        sd = random_head_state(g, backbone)
         if calibrate:
             _calibrate(sd, imgs, head_index=i)
         for k, v in sd.items():
@@ -215,8 +220,9 @@ def class_names(n_heads: int) -> List[str]:
     return [f"Synthetic{chr(ord('A') + i)}" for i in range(n_heads)] + ["Real"]
 
 
-def save_merged_checkpoint(path: str, n_heads: int, seed: int = WEIGHT_SEED, calibrate: bool = True):
+def save_merged_checkpoint(path: str, n_heads: int, seed: int = WEIGHT_SEED, calibrate: bool = True,
+                           backbone: str = "resnet18"):
     """Write the file MM:154-159 writes: {'state_dict', 'metadata': {'class_names'}}."""
-    sd = merged_state_dict(n_heads, seed, calibrate)
+    sd = merged_state_dict(n_heads, seed, calibrate, backbone=backbone)
     torch.save({"state_dict": sd, "metadata": {"class_names": class_names(n_heads)}}, path)
     return sd

@@ -92,15 +92,15 @@ def golden_frontend(IR, seg_ids):
     return x
 
 
-def golden_ensemble(IR, MM, n_heads, seg_ids, tag):
+def golden_ensemble(IR, MM, n_heads, seg_ids, tag, backbone="resnet18"):
     """load_merged_model + ModularMultiHeadClassifier.forward + interpret_multihead_logits."""
     x = torch.cat([FX.synth_segments(1, first=i) for i in seg_ids])
     cfg = IR.SpectrogramConfig(2048, 512, 128, 20, 12000, 80, "slaney")
     imgs = torch.cat([IR.waveform_to_spectrogram(x[i], 32000, cfg) for i in range(x.shape[0])])
     with tempfile.TemporaryDirectory() as d:
         path = os.path.join(d, "merged.pth")
-        FX.save_merged_checkpoint(path, n_heads)
-        model, meta = IR.load_merged_model(path, torch.device("cpu"))                  # IR:77-123
+        FX.save_merged_checkpoint(path, n_heads, backbone=backbone)
+        model, meta = IR.load_merged_model(path, torch.device("cpu"), backbone_name=backbone)      # IR:77-123
     names = meta["class_names"]
     with torch.no_grad():
         merged = model(imgs)                                                            # IR:62-73
@@ -133,6 +133,7 @@ def main():
     golden_frontend(IR, [0, 1, 2, 3, 4, 5, 6, 13])
     golden_ensemble(IR, MM, 2, [0, 1, 2, 3, 4, 5, FX.CAL_FIRST, FX.CAL_FIRST + 1], "n2")
     golden_ensemble(IR, MM, 5, [0, 1, FX.CAL_FIRST, FX.CAL_FIRST + 1], "n5")
+    golden_ensemble(IR, MM, 2, [0, 1, FX.CAL_FIRST], "r34_n2", backbone="resnet34")
 
 
 if __name__ == "__main__":

@@ -244,13 +244,15 @@ def _basic_block(x, sd, p, stride):
 
 
 def backbone_features(x: torch.Tensor, sd: Dict[str, torch.Tensor], p: str) -> torch.Tensor:
-    """timm ResNet.forward_features for resnet18: [B,3,512,512] -> [B,512,16,16] (IR:50)."""
+    """timm ResNet.forward_features for a BasicBlock ResNet (resnet18/34): [B,3,512,512] -> [B,512,16,16] (IR:50)."""
     x = F.conv2d(x, sd[p + "conv1.weight"], None, stride=2, padding=3)
     x = F.relu(_bn(x, sd, p + "bn1"))
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
     for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
-        x = _basic_block(x, sd, f"{p}layer{li}.0", stride)
-        x = _basic_block(x, sd, f"{p}layer{li}.1", 1)
+        b = 0
+        while f"{p}layer{li}.{b}.conv1.weight" in sd:          # 2 blocks per layer for resnet18; 3,4,6,3 for resnet34
+            x = _basic_block(x, sd, f"{p}layer{li}.{b}", stride if b == 0 else 1)
+            b += 1
     return x
 
 

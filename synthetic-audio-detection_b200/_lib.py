@@ -15,12 +15,17 @@ _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 # name -> (restype, argtypes): every symbol include/sad_b200.h declares
 SIGNATURES = {
     "sad_create": (_i, [C.POINTER(_vp), _i, _i, _i]),
+    "sad_create_ex": (_i, [C.POINTER(_vp), _i, _i, _i, C.c_char_p]),
+    "sad_backbone": (C.c_char_p, [_vp]),
     "sad_destroy": (_i, [_vp]),
     "sad_last_error": (C.c_char_p, [_vp]),
     "sad_version": (C.c_char_p, []),
     "sad_weight_count": (_i, []),
     "sad_weight_name": (C.c_char_p, [_i]),
     "sad_weight_numel": (_ll, [_i]),
+    "sad_backbone_weight_count": (_i, [C.c_char_p]),
+    "sad_backbone_weight_name": (C.c_char_p, [C.c_char_p, _i]),
+    "sad_backbone_weight_numel": (_ll, [C.c_char_p, _i]),
     "sad_load_weights": (_i, [_vp, _i, C.POINTER(_vp), _i]),
     "sad_set_frontend_constants": (_i, [_vp, _vp, _vp]),
     "sad_frontend_logmel": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),

@@ -3,13 +3,14 @@ downsample.{0,1}}), so state_dicts written by the reference (model_merger.py:154
 
 The reference builds this trunk with ``timm.create_model(name, pretrained=True, num_classes=0)``
 (inference_runner.py:35), which needs the network; here the modules are only parameter holders -- the arithmetic
-runs in the sm_100a kernels -- so construction is offline and cheap.  Only resnet18 is wired to kernels (SURVEY 8f4
-lists the deeper variants as "next").
+runs in the sm_100a kernels -- so construction is offline and cheap.  resnet18 and resnet34 (the BasicBlock members
+of the family) are wired to kernels; the Bottleneck variants are not.
 """
 import torch
 import torch.nn as nn
 
-SUPPORTED = ("resnet18",)
+DEPTHS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3)}
+SUPPORTED = tuple(DEPTHS)
 
 
 class _BasicBlock(nn.Module):
@@ -27,21 +28,25 @@ class _BasicBlock(nn.Module):
 
 
 class ResNetTrunk(nn.Module):
-    """resnet18 feature trunk; ``forward_features`` is served by the CUDA engine of the owning classifier."""
+    """BasicBlock ResNet feature trunk (resnet18 / resnet34); ``forward_features`` is served by the CUDA engine of
+    the owning classifier."""
 
     def __init__(self, model_name: str = "resnet18"):
         super().__init__()
         if model_name not in SUPPORTED:
             raise NotImplementedError(
-                f"backbone {model_name!r}: only {SUPPORTED} has sm_100a kernels in this build (SURVEY.md 8f4)")
+                f"backbone {model_name!r}: only {SUPPORTED} have sm_100a kernels in this build (Bottleneck ResNets, "
+                "SURVEY.md 8f4, are not wired up)")
+        self.model_name = model_name
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         self.act1 = nn.ReLU(inplace=True)
         self.maxpool = nn.MaxPool2d(3, 2, 1)
         cin = 64
-        for li, cout in enumerate((64, 128, 256, 512), start=1):
+        for li, (cout, depth) in enumerate(zip((64, 128, 256, 512), DEPTHS[model_name]), start=1):
             stride = 1 if li == 1 else 2
-            setattr(self, f"layer{li}", nn.Sequential(_BasicBlock(cin, cout, stride), _BasicBlock(cout, cout, 1)))
+            blocks = [_BasicBlock(cin, cout, stride)] + [_BasicBlock(cout, cout, 1) for _ in range(depth - 1)]
+            setattr(self, f"layer{li}", nn.Sequential(*blocks))
             cin = cout
         self.num_features = 512
         for m in self.modules():                      # timm's init: kaiming-normal convs, unit BN

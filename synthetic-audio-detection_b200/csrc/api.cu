@@ -34,14 +34,14 @@ struct ConvSpec {
     int cin, cout, k, stride, pad, hin, hout;
 };
 
-std::vector<ConvSpec> build_convs() {
+std::vector<ConvSpec> build_convs(const int depths[4]) {
     std::vector<ConvSpec> v;
     v.push_back({"base.conv1", "base.bn1", 3, 64, 7, 2, 3, 512, 256});
     const int chans[4] = {64, 128, 256, 512};
     int cin = 64, h = 128;
     for (int li = 0; li < 4; ++li) {
         const int cout = chans[li];
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < depths[li]; ++b) {
             const std::string p = "base.layer" + std::to_string(li + 1) + "." + std::to_string(b);
             const int stride = (b == 0 && li > 0) ? 2 : 1;
             const int c0 = b == 0 ? cin : cout;
@@ -53,7 +53,7 @@ std::vector<ConvSpec> build_convs() {
         }
         cin = cout;
     }
-    return v;   // 20 entries, state_dict order
+    return v;   // state_dict order: 20 entries for resnet18, 36 for resnet34
 }
 
 struct TensorSpec {
@@ -81,17 +81,30 @@ std::vector<TensorSpec> build_tensor_list(const std::vector<ConvSpec>& convs) {
     bn("head.7", 256);
     t.push_back({"head.10.weight", 2 * 256});
     t.push_back({"head.10.bias", 2});
-    return t;   // 20*5 + 14 = 114
+    return t;   // 5 per conv + 14
 }
 
-const std::vector<ConvSpec>& convs() {
-    static const std::vector<ConvSpec> v = build_convs();
-    return v;
+// BasicBlock ResNets served by the same kernels: the trunk differs only in block counts.
+struct NetSpec {
+    std::string name;
+    int depths[4];
+    std::vector<ConvSpec> convs;
+    std::vector<TensorSpec> tensors;
+};
+
+const NetSpec* get_net(const char* name) {
+    static const NetSpec nets[2] = {
+        [] { NetSpec n; n.name = "resnet18"; const int d[4] = {2, 2, 2, 2}; memcpy(n.depths, d, sizeof(d));
+             n.convs = build_convs(n.depths); n.tensors = build_tensor_list(n.convs); return n; }(),
+        [] { NetSpec n; n.name = "resnet34"; const int d[4] = {3, 4, 6, 3}; memcpy(n.depths, d, sizeof(d));
+             n.convs = build_convs(n.depths); n.tensors = build_tensor_list(n.convs); return n; }()};
+    if (!name) return &nets[0];
+    for (const auto& n : nets)
+        if (n.name == name) return &n;
+    return nullptr;
 }
-const std::vector<TensorSpec>& tensors() {
-    static const std::vector<TensorSpec> v = build_tensor_list(convs());
-    return v;
-}
+
+constexpr int kMaxConvs = SAD_PROF_CONV_SLOTS;
 
 // launch plan over the activation buffers: X (block input / output), Y, T (mid), D (downsample branch)
 enum Buf { BX = 0, BY = 1, BT = 2, BD = 3, BNONE = -1 };
@@ -101,29 +114,31 @@ struct Step {
     int relu;
     int fused_ds;   // conv index of a downsample branch accumulated into this conv (reads buffer X), or -1
 };
-std::vector<Step> build_plan(bool fuse_ds) {
+// Walk the blocks: `cur` holds the block input, conv1 -> T, conv2 (+identity or downsample branch) -> the other of X/Y.
+std::vector<Step> build_plan(const NetSpec& net, bool fuse_ds, int* final_buf) {
     std::vector<Step> p;
-    int ci = 1;
+    int ci = 1, cur = BX;
     for (int li = 0; li < 4; ++li) {
-        if (li == 0) {
-            p.push_back({ci + 0, BX, BNONE, BT, 1, -1});
-            p.push_back({ci + 1, BT, BX, BY, 1, -1});
-            ci += 2;
-        } else if (fuse_ds) {
-            p.push_back({ci + 0, BX, BNONE, BT, 1, -1});
-            p.push_back({ci + 1, BT, BNONE, BY, 1, ci + 2});   // conv2 + downsample(X) accumulated in one tile
-            ci += 3;
-        } else {
-            p.push_back({ci + 0, BX, BNONE, BT, 1, -1});
-            p.push_back({ci + 2, BX, BNONE, BD, 0, -1});
-            p.push_back({ci + 1, BT, BD, BY, 1, -1});
-            ci += 3;
+        for (int b = 0; b < net.depths[li]; ++b) {
+            const int other = cur == BX ? BY : BX;
+            const bool has_ds = (b == 0 && li > 0);
+            p.push_back({ci + 0, cur, BNONE, BT, 1, -1});
+            if (!has_ds) {
+                p.push_back({ci + 1, BT, cur, other, 1, -1});
+                ci += 2;
+            } else if (fuse_ds) {
+                p.push_back({ci + 1, BT, BNONE, other, 1, ci + 2});   // conv2 + downsample(cur) accumulated in one tile
+                ci += 3;
+            } else {
+                p.push_back({ci + 2, cur, BNONE, BD, 0, -1});
+                p.push_back({ci + 1, BT, BD, other, 1, -1});
+                ci += 3;
+            }
+            cur = other;
         }
-        p.push_back({ci + 0, BY, BNONE, BT, 1, -1});
-        p.push_back({ci + 1, BT, BY, BX, 1, -1});
-        ci += 2;
     }
-    return p;   // 19 (16 with fused downsamples) steps; the trunk output ends in X
+    *final_buf = cur;
+    return p;
 }
 
 constexpr double kBnEps = 1e-5;
@@ -135,13 +150,15 @@ constexpr double kBnEps = 1e-5;
 // ------------------------------------------------------------------------------------------------
 struct sad_ctx {
     int device = 0, H = 0, Bc = 0, num_sms = 0;
+    const NetSpec* net = nullptr;
+    int final_buf = 0;                  // activation buffer that holds the trunk output (X or Y)
     char err[512] = {0};
     long long launches = 0;
     std::vector<char> loaded;
 
     // weights
-    bf16* d_w[20] = {nullptr};          // [H][Cout][taps*Cin]; index 0 unused (stem has its own two packings)
-    float* d_bias[20] = {nullptr};      // [H][Cout]
+    bf16* d_w[kMaxConvs] = {nullptr};          // [H][Cout][taps*Cin]; index 0 unused (stem has its own two packings)
+    float* d_bias[kMaxConvs] = {nullptr};      // [H][Cout]
     bf16* d_w_stem1 = nullptr;          // [H][64][64]   1-channel (summed) stem: k = ky*8+kx, k=56..58 bias hi/mid/lo
     bf16* d_w_stem3 = nullptr;          // [H][64][192]  3-channel stem, K = 147 -> 192
     float *d_w1t = nullptr, *d_b1 = nullptr, *d_w2t = nullptr, *d_b2 = nullptr, *d_w3 = nullptr, *d_b3 = nullptr;
@@ -170,7 +187,7 @@ struct sad_ctx {
     bool stem3_ready = false;
     int two_cta = 1;                    // 1: N=256 layers (layers 3-4) run on CTA pairs (conv_umma2.cu, cta_group::2); 2: N=128 too (slower)
     int fuse_ds = 1;                    // fold each block's 1x1/s2 downsample conv into conv2 as extra K blocks
-    float* d_bias_fused[20] = {nullptr}; // [H][Cout] = bias(conv2) + bias(downsample) for conv indices 6, 11, 16
+    float* d_bias_fused[kMaxConvs] = {nullptr}; // [H][Cout] = bias(conv2) + bias(downsample) for the conv2 that absorbs it
     int rows_mode = 2;                  // layer1 row-stationary kernel: 0 off, 2 on (1 = probe: descriptor base-offset field set, WRONG on sm_100a)
 
     // end-to-end path
@@ -334,18 +351,18 @@ namespace {
 cudaError_t launch_conv(sad_ctx* c, int ci, const sad::ConvLaunch& L, int heads, cudaStream_t st);
 
 // Fill one ConvLaunch for conv `ci` reading `in` (NHWC [n_imgs][hin][hin][cin]) and writing `out`.
-bool is_rows_layer(int ci) {
-    const ConvSpec& s = convs()[ci];
+bool is_rows_layer(const sad_ctx* c, int ci) {
+    const ConvSpec& s = c->net->convs[ci];
     return s.cin == 64 && s.cout == 64 && s.k == 3 && s.stride == 1 && s.hin == 128;
 }
 
 bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const bf16* res, bf16* out, long long n_imgs,
                  int relu, int fused_ds = -1, const bf16* ds_in = nullptr) {
-    const ConvSpec& s = convs()[ci];
+    const ConvSpec& s = c->net->convs[ci];
     memset(L, 0, sizeof(*L));
     const int Wo = s.hout, Hi = s.hin, C = s.cin;
     const int rows = 128 / Wo;
-    if (c->rows_mode && is_rows_layer(ci)) {
+    if (c->rows_mode && is_rows_layer(c, ci)) {
         // row-stationary kernel (conv_rows.cu): one box = a whole halo'd input row {64 ch, 130 px, 1 row}
         if (!sad::encode_act_map(&L->a_map[0], in, C, Hi, Hi, n_imgs, C, 1LL * Hi * C, 1LL * Hi * Hi * C, Wo + 2, 1, c->err,
                                  sizeof(c->err)))
@@ -395,7 +412,7 @@ bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const b
     }
     L->b2h_map = L->bh_map;
     if (fused_ds >= 0) {
-        const ConvSpec& d = convs()[fused_ds];         // 1x1, stride 2, pad 0, same Cout and output size as `s`
+        const ConvSpec& d = c->net->convs[fused_ds];         // 1x1, stride 2, pad 0, same Cout and output size as `s`
         if (d.cout != s.cout || d.hout != s.hout || d.k != 1 || d.stride != 2) {
             snprintf(c->err, sizeof(c->err), "conv %d cannot absorb downsample %d", ci, fused_ds);
             return false;
@@ -446,9 +463,9 @@ void set_batch(sad::ConvLaunch* L, int B, int H) {
     L->total_tiles = H * B * L->m_tiles_per_img * L->n_tiles;
 }
 
-bool is_rows_layer(int ci);
+bool is_rows_layer(const sad_ctx* c, int ci);
 cudaError_t launch_conv(sad_ctx* c, int ci, const sad::ConvLaunch& L, int heads, cudaStream_t st) {
-    if (ci > 0 && c->rows_mode && is_rows_layer(ci))
+    if (ci > 0 && c->rows_mode && is_rows_layer(c, ci))
         return sad::conv_rows_launch(L, heads, c->rows_mode == 1 ? 1 : 0, c->num_sms, st);
     if (c->two_cta && L.n_tile >= (c->two_cta >= 2 ? 128 : 256) && L.m_tiles_per_img % 2 == 0)
         return sad::conv_umma2_launch(L, c->num_sms, st);
@@ -558,15 +575,24 @@ extern "C" {
 
 const char* sad_version(void) { return "sad_b200 0.1 (sm_100a)"; }
 
-int sad_weight_count(void) { return static_cast<int>(tensors().size()); }
-const char* sad_weight_name(int i) {
-    if (i < 0 || i >= sad_weight_count()) return nullptr;
-    return tensors()[i].name.c_str();
+int sad_backbone_weight_count(const char* backbone) {
+    const NetSpec* n = get_net(backbone);
+    return n ? static_cast<int>(n->tensors.size()) : -1;
 }
-long long sad_weight_numel(int i) {
-    if (i < 0 || i >= sad_weight_count()) return -1;
-    return tensors()[i].numel;
+const char* sad_backbone_weight_name(const char* backbone, int i) {
+    const NetSpec* n = get_net(backbone);
+    if (!n || i < 0 || i >= static_cast<int>(n->tensors.size())) return nullptr;
+    return n->tensors[i].name.c_str();
 }
+long long sad_backbone_weight_numel(const char* backbone, int i) {
+    const NetSpec* n = get_net(backbone);
+    if (!n || i < 0 || i >= static_cast<int>(n->tensors.size())) return -1;
+    return n->tensors[i].numel;
+}
+int sad_weight_count(void) { return sad_backbone_weight_count("resnet18"); }
+const char* sad_weight_name(int i) { return sad_backbone_weight_name("resnet18", i); }
+long long sad_weight_numel(int i) { return sad_backbone_weight_numel("resnet18", i); }
+const char* sad_backbone(const sad_ctx* ctx) { return ctx && ctx->net ? ctx->net->name.c_str() : nullptr; }
 
 const char* sad_last_error(const sad_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 int sad_n_heads(const sad_ctx* ctx) { return ctx ? ctx->H : 0; }
@@ -582,9 +608,15 @@ long long sad_slice_count(long long n_samples, long long window, long long hop) 
 }
 
 int sad_create(sad_ctx** out, int device, int n_heads, int max_batch) {
+    return sad_create_ex(out, device, n_heads, max_batch, "resnet18");
+}
+
+int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const char* backbone) {
     if (!out) return SAD_EINVAL;
     *out = nullptr;
     if (n_heads < 1 || n_heads > 31 || max_batch < 1 || max_batch > 4096) return SAD_EINVAL;
+    const NetSpec* net = get_net(backbone);
+    if (!net || static_cast<int>(net->convs.size()) > kMaxConvs) return SAD_EINVAL;
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0 || device < 0 || device >= n_dev) {
         cudaGetLastError();
@@ -599,6 +631,7 @@ int sad_create(sad_ctx** out, int device, int n_heads, int max_batch) {
     c->Bc = max_batch;
     c->num_sms = prop.multiProcessorCount;
     c->loaded.assign(n_heads, 0);
+    c->net = net;
     if (const char* e = getenv("SAD_CONV_ROWS")) c->rows_mode = atoi(e);
     if (const char* e = getenv("SAD_FUSE_DS")) c->fuse_ds = atoi(e);
     if (const char* e = getenv("SAD_2CTA")) c->two_cta = atoi(e);
@@ -606,13 +639,15 @@ int sad_create(sad_ctx** out, int device, int n_heads, int max_batch) {
     CU_OK(c, cudaSetDevice(device));
 
     const long long H = n_heads, Bc = max_batch, HB = H * Bc;
-    for (int i = 1; i < 20; ++i) {
-        const ConvSpec& s = convs()[i];
+    const int n_convs = static_cast<int>(net->convs.size());
+    for (int i = 1; i < n_convs; ++i) {
+        const ConvSpec& s = net->convs[i];
         CU_OK(c, dalloc(&c->d_w[i], H * s.cout * s.k * s.k * s.cin));
         CU_OK(c, dalloc(&c->d_bias[i], H * s.cout));
     }
     CU_OK(c, dalloc(&c->d_bias[0], H * 64));
-    for (int ci : {6, 11, 16}) CU_OK(c, dalloc(&c->d_bias_fused[ci], H * convs()[ci].cout));
+    for (int i = 1; i + 1 < n_convs; ++i)       // conv2 (index i) directly followed by its block's downsample conv
+        if (net->convs[i + 1].k == 1) CU_OK(c, dalloc(&c->d_bias_fused[i], H * net->convs[i].cout));
     CU_OK(c, dalloc(&c->d_w_stem1, H * 64 * 64));
     CU_OK(c, dalloc(&c->d_w_stem3, H * 64 * 192));
     CU_OK(c, dalloc(&c->d_w1t, H * 512 * 512));
@@ -652,12 +687,12 @@ int sad_create(sad_ctx** out, int device, int n_heads, int max_batch) {
     if (!sad::encode_pix_map(&c->stem1.out_map, c->d_buf[BX], 64, HB * 128 * 128, 128, c->err, sizeof(c->err))) return SAD_ECUDA;
     c->stem1.img = c->d_img;
     c->stem1.H = n_heads;
-    c->plan = build_plan(c->fuse_ds != 0);
+    c->plan = build_plan(*net, c->fuse_ds != 0, &c->final_buf);
     c->plan_launch.resize(c->plan.size());
     for (size_t i = 0; i < c->plan.size(); ++i) {
         const Step& s = c->plan[i];
         if (!make_launch(c, &c->plan_launch[i], s.conv, c->d_buf[s.in], s.res == BNONE ? nullptr : c->d_buf[s.res],
-                         c->d_buf[s.out], HB, s.relu, s.fused_ds, c->d_buf[BX]))
+                         c->d_buf[s.out], HB, s.relu, s.fused_ds, c->d_buf[s.fused_ds >= 0 ? c->plan[i - 1].in : BX]))
             return SAD_ECUDA;
     }
 
@@ -674,11 +709,11 @@ int sad_destroy(sad_ctx* c) {
     if (!c) return SAD_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 20; ++i) {
+    for (int i = 0; i < kMaxConvs; ++i) {
         cudaFree(c->d_w[i]);
         cudaFree(c->d_bias[i]);
     }
-    for (int i = 0; i < 20; ++i) cudaFree(c->d_bias_fused[i]);
+    for (int i = 0; i < kMaxConvs; ++i) cudaFree(c->d_bias_fused[i]);
     void* ptrs[] = {c->d_w_stem1, c->d_w_stem3, c->d_w1t, c->d_b1, c->d_w2t, c->d_b2, c->d_w3, c->d_b3, c->d_window,
                     c->d_mel, c->d_resize, c->d_db, c->d_segmax, c->d_musig, c->d_img, c->d_A3, c->d_stem,
                     c->d_buf[0], c->d_buf[1], c->d_buf[2], c->d_buf[3], c->d_head_logits, c->d_pcm[0], c->d_pcm[1],
@@ -709,16 +744,19 @@ int sad_set_frontend_constants(sad_ctx* c, const float* host_window, const float
 int sad_load_weights(sad_ctx* c, int head, const float* const* T, int n_tensors) {
     if (!c) return SAD_EINVAL;
     if (head < 0 || head >= c->H) return fail(c, SAD_EINVAL, "head %d out of range [0,%d)", head, c->H);
-    if (n_tensors != sad_weight_count())
-        return fail(c, SAD_EINVAL, "expected %d tensors, got %d", sad_weight_count(), n_tensors);
+    const NetSpec& net = *c->net;
+    const int n_convs = static_cast<int>(net.convs.size());
+    if (n_tensors != static_cast<int>(net.tensors.size()))
+        return fail(c, SAD_EINVAL, "expected %d tensors for %s, got %d", static_cast<int>(net.tensors.size()), net.name.c_str(),
+                    n_tensors);
     for (int i = 0; i < n_tensors; ++i)
-        if (!T[i]) return fail(c, SAD_EINVAL, "tensor %d (%s) is null", i, sad_weight_name(i));
+        if (!T[i]) return fail(c, SAD_EINVAL, "tensor %d (%s) is null", i, net.tensors[i].name.c_str());
     CU_OK(c, cudaSetDevice(c->device));
     std::vector<double> s, t;
-    std::vector<std::vector<float>> host_bias(20);
+    std::vector<std::vector<float>> host_bias(n_convs);
     int ti = 0;
-    for (int ci = 0; ci < 20; ++ci) {
-        const ConvSpec& cs = convs()[ci];
+    for (int ci = 0; ci < n_convs; ++ci) {
+        const ConvSpec& cs = net.convs[ci];
         const float* w = T[ti];
         bn_scale_shift(T[ti + 1], T[ti + 2], T[ti + 3], T[ti + 4], cs.cout, s, t);
         ti += 5;
@@ -768,7 +806,8 @@ int sad_load_weights(sad_ctx* c, int head, const float* const* T, int n_tensors)
                                 cudaMemcpyHostToDevice));
         }
     }
-    for (int ci : {6, 11, 16}) {   // conv2 of the first block of layers 2-4 absorbs the downsample branch (index ci+1)
+    for (int ci = 1; ci + 1 < n_convs; ++ci) {   // conv2 of the first block of layers 2-4 absorbs the downsample branch (ci+1)
+        if (net.convs[ci + 1].k != 1) continue;
         std::vector<float> fb(host_bias[ci].size());
         for (size_t o = 0; o < fb.size(); ++o) fb[o] = host_bias[ci][o] + host_bias[ci + 1][o];
         CU_OK(c, cudaMemcpy(c->d_bias_fused[ci] + static_cast<size_t>(head) * fb.size(), fb.data(), fb.size() * sizeof(float),
@@ -967,7 +1006,8 @@ int sad_clip_reduce(sad_ctx* c, const float* probs, const int32_t* clip_id, int 
 int sad_debug_conv(sad_ctx* c, int head, int layer, const void* in, const void* residual, void* out, int B, int relu,
                    void* stream) {
     if (!c || !in || !out || B < 1) return SAD_EINVAL;
-    if (layer < 1 || layer >= 20) return fail(c, SAD_EINVAL, "layer %d out of range [1,20)", layer);
+    if (layer < 1 || layer >= static_cast<int>(c->net->convs.size()))
+        return fail(c, SAD_EINVAL, "layer %d out of range [1,%d)", layer, static_cast<int>(c->net->convs.size()));
     if (head < 0 || head >= c->H) return fail(c, SAD_EINVAL, "head out of range");
     if (!c->loaded[head]) return fail(c, SAD_ESTATE, "weights of head %d not loaded", head);
     CU_OK(c, cudaSetDevice(c->device));
@@ -976,7 +1016,7 @@ int sad_debug_conv(sad_ctx* c, int head, int layer, const void* in, const void* 
                      B, relu))
         return SAD_ECUDA;
     // single head: offset the weight / bias views to `head` by re-encoding the weight map on that slice
-    const ConvSpec& s = convs()[layer];
+    const ConvSpec& s = c->net->convs[layer];
     const long long K = 1LL * s.k * s.k * s.cin;
     if (!sad::encode_weight_map(&L.b_map, c->d_w[layer] + static_cast<size_t>(head) * s.cout * K, K, s.cout, L.n_tile, c->err,
                                 sizeof(c->err)))
@@ -1043,7 +1083,7 @@ long long sad_debug_read(sad_ctx* c, int which, void* dst, long long capacity, v
     switch (which) {
         case 0: src = c->d_img; bytes = B * 512 * 512 * 2; break;
         case 1: src = c->d_stem; bytes = 0; break;
-        case 2: src = c->d_buf[BX]; bytes = H * B * 16 * 16 * 512 * 2; break;
+        case 2: src = c->d_buf[c->final_buf]; bytes = H * B * 16 * 16 * 512 * 2; break;
         case 3: src = c->d_head_logits; bytes = H * B * 2 * 4; break;
         case 4: src = c->d_db; bytes = B * 128 * 251 * 4; break;
         default: return fail(c, SAD_EINVAL, "unknown buffer id %d", which);
@@ -1106,7 +1146,7 @@ int run_chunk(sad_ctx* c, const float* pcm, const float* x_nchw, int B, float th
     }
     sad::HeadWeights hw{c->d_w1t, c->d_b1, c->d_w2t, c->d_b2, c->d_w3, c->d_b3};
     ProfScope ps(c, SAD_PROF_HEAD, st);
-    CU_OK(c, sad::head_mlp_launch(c->d_buf[BX], hw, B, H, c->d_head_logits, st, &c->launches));
+    CU_OK(c, sad::head_mlp_launch(c->d_buf[c->final_buf], hw, B, H, c->d_head_logits, st, &c->launches));
     CU_OK(c, sad::merge_decide_launch(c->d_head_logits, B, H, thr, logits, probs, labels, st, &c->launches));
     return SAD_OK;
 }

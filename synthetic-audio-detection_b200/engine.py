@@ -40,7 +40,8 @@ def _frontend_constants() -> Tuple[torch.Tensor, torch.Tensor]:
 class Engine:
     """Owns a sad_ctx.  Tensors passed in must be CUDA fp32 contiguous on this engine's device."""
 
-    def __init__(self, n_heads: int, device: Optional[torch.device] = None, max_batch: int = 64):
+    def __init__(self, n_heads: int, device: Optional[torch.device] = None, max_batch: int = 64,
+                 backbone: str = "resnet18"):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.SadError("no CUDA device: the sm_100a kernels cannot run and there is no CPU fallback")
@@ -52,8 +53,11 @@ class Engine:
         self.n_heads = int(n_heads)
         self.max_batch = int(max_batch)
         self.ctx = C.c_void_p(0)
+        self.backbone = backbone
+        if self.lib.sad_backbone_weight_count(backbone.encode()) < 0:
+            raise NotImplementedError(f"backbone {backbone!r} has no sm_100a kernels (BasicBlock ResNets only: resnet18, resnet34)")
         torch.cuda.init()
-        code = self.lib.sad_create(C.byref(self.ctx), idx, self.n_heads, self.max_batch)
+        code = self.lib.sad_create_ex(C.byref(self.ctx), idx, self.n_heads, self.max_batch, backbone.encode())
         if code != 0:
             msg = self.lib.sad_last_error(self.ctx).decode() if self.ctx else ""
             if self.ctx:
@@ -62,8 +66,10 @@ class Engine:
             raise _lib.SadError(f"sad_create failed ({code}): {msg}")
         w, fb = _frontend_constants()
         _lib.check(self.ctx, self.lib.sad_set_frontend_constants(self.ctx, _ptr(w), _ptr(fb)), "sad_set_frontend_constants")
-        self._names = [self.lib.sad_weight_name(i).decode() for i in range(self.lib.sad_weight_count())]
-        self._numel = [self.lib.sad_weight_numel(i) for i in range(self.lib.sad_weight_count())]
+        bb = backbone.encode()
+        n = self.lib.sad_backbone_weight_count(bb)
+        self._names = [self.lib.sad_backbone_weight_name(bb, i).decode() for i in range(n)]
+        self._numel = [self.lib.sad_backbone_weight_numel(bb, i) for i in range(n)]
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -218,14 +224,15 @@ class Engine:
         _lib.check(self.ctx, int(n), "sad_debug_read")
         return out
 
-    PROF_KINDS = 24
+    PROF_KINDS = 44
+    PROF_FRONTEND, PROF_IMAGE, PROF_POOL, PROF_HEAD = 40, 41, 42, 43
 
     def profile_enable(self, on: bool = True):
         _lib.check(self.ctx, self.lib.sad_profile_enable(self.ctx, int(on)), "sad_profile_enable")
 
     def profile_read(self):
-        """(ms_by_kind[24], launches_by_kind[24]); kinds 0..19 = convolutions (0 = stem), 20 front end,
-        21 image+im2col, 22 max pool, 23 head/merge."""
+        """(ms_by_kind[44], launches_by_kind[44]); kinds 0..39 = convolutions in state_dict order (0 = stem), 40 front
+        end, 41 image (+im2col), 42 max pool (3-channel path), 43 head/merge."""
         ms = (C.c_double * self.PROF_KINDS)()
         n = (C.c_longlong * self.PROF_KINDS)()
         _lib.check(self.ctx, self.lib.sad_profile_read(self.ctx, ms, n), "sad_profile_read")

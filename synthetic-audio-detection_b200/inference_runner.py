@@ -57,6 +57,7 @@ class BinaryClassifier(nn.Module):
     def __init__(self, model_name: str = "resnet18"):
         super().__init__()
         self.base = ResNetTrunk(model_name)
+        self.model_name = model_name
         self.head = nn.Sequential(
             nn.AdaptiveAvgPool2d(1), nn.Flatten(),
             nn.Linear(self.base.num_features, 512), nn.BatchNorm1d(512), nn.ReLU(), nn.Dropout(0.5),
@@ -71,7 +72,7 @@ class BinaryClassifier(nn.Module):
         if self._engine is None or self._engine_key != key:
             if self._engine is not None:
                 self._engine.close()
-            self._engine = Engine(1, device, max_batch=16)
+            self._engine = Engine(1, device, max_batch=16, backbone=self.model_name)
             self._engine.load_head(0, self.state_dict())
             self._engine_key = key
         return self._engine
@@ -114,7 +115,10 @@ class ModularMultiHeadClassifier(nn.Module):
         if self._engine is None or self._engine_key != key:
             if self._engine is not None:
                 self._engine.close()
-            self._engine = Engine(len(self.sub_models), dev, max_batch=self.max_batch)
+            names = {getattr(m, "model_name", "resnet18") for m in self.sub_models}
+            if len(names) != 1:
+                raise ValueError(f"all sub-models must share one backbone, got {sorted(names)}")
+            self._engine = Engine(len(self.sub_models), dev, max_batch=self.max_batch, backbone=names.pop())
             self._engine.load_merged_state_dict(self.state_dict())
             self._engine_key = key
         return self._engine

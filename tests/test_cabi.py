@@ -36,6 +36,12 @@ def test_weight_manifest_matches_checkpoint_layout():
     got = [(lib.sad_weight_name(i).decode(), lib.sad_weight_numel(i)) for i in range(lib.sad_weight_count())]
     assert got == want
     assert lib.sad_weight_name(-1) is None and lib.sad_weight_numel(10 ** 6) == -1
+    sd34 = FX.merged_state_dict(1, calibrate=False, backbone="resnet34")
+    want34 = [(k[len("sub_models.0."):], v.numel()) for k, v in sd34.items() if not k.endswith("num_batches_tracked")]
+    got34 = [(lib.sad_backbone_weight_name(b"resnet34", i).decode(), lib.sad_backbone_weight_numel(b"resnet34", i))
+             for i in range(lib.sad_backbone_weight_count(b"resnet34"))]
+    assert got34 == want34 and len(got34) == 36 * 5 + 14
+    assert lib.sad_backbone_weight_count(b"resnet50") == -1
 
 
 def test_slice_count_is_len_of_python_range():

@@ -93,7 +93,7 @@ def test_cli_json_matches_oracle_pipeline(merged_ckpt, tmp_path, smooth):
     labels, probs = R.interpret(logits, 0.5)
     if smooth:
         probs, labels = R.smooth_probs(probs, 0.5)
-    margin = np.abs(logits.numpy()).min(axis=1)
+    margin = G.decision_margin(logits.numpy())
     assert [s["start_sec"] for s in res["segments"]] == [s / 32000 for s in ks]
     assert all(s["end_sec"] == s["start_sec"] + 4.0 for s in res["segments"])
     if not smooth:
@@ -129,3 +129,20 @@ def test_batch_folder_driver(merged_ckpt, tmp_path):
     IR.main(["--merged-model", merged_ckpt, "--audio", str(folder / "c0.wav"), "--output-json", str(single)])
     assert json.loads(single.read_text()) == json.loads((out / "c0.json").read_text())
     assert summary[0]["label"] in FX.class_names(2)
+
+
+def test_resnet34_backbone_through_the_python_api(tmp_path, capsys):
+    """backbone_name / --model-name = resnet34 (IR:77, MM:101): same kernels, deeper trunk."""
+    p = tmp_path / "m34.pth"
+    sd = FX.save_merged_checkpoint(str(p), 2, backbone="resnet34")
+    model, meta = IR.load_merged_model(str(p), torch.device("cuda"), backbone_name="resnet34")
+    assert "dummy output shape: torch.Size([2, 3])" in capsys.readouterr().out
+    x = FX.synth_segments(2, first=70)
+    img3 = R.waveform_to_image(x).unsqueeze(1).repeat(1, 3, 1, 1).contiguous()
+    want = R.ensemble_forward(img3, sd)
+    got = model(img3.cuda())
+    lo, _, _ = model.forward_pcm(x.cuda(), 0.5)
+    print("resnet34: max |logit diff| images", (got.cpu() - want).abs().max().item(), "pcm", (lo.cpu() - want).abs().max().item())
+    assert (got.cpu() - want).abs().max() <= LOGIT_TOL and (lo.cpu() - want).abs().max() <= LOGIT_TOL
+    with pytest.raises(NotImplementedError):
+        IR.BinaryClassifier("resnet50")

@@ -14,8 +14,8 @@ from tests import gpu_common as G
 
 pytestmark = pytest.mark.gpu
 
-LAYERS = [l for l in FX._layer_plan() if l[0] == "conv"]      # 20 convs in state_dict order
-BNS = [l for l in FX._layer_plan() if l[0] == "bn"]
+LAYERS = [l for l in FX._layer_plan("resnet18") if l[0] == "conv"]      # 20 convs in state_dict order
+BNS = [l for l in FX._layer_plan("resnet18") if l[0] == "bn"]
 
 
 def _geometry(idx):

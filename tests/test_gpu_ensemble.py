@@ -17,11 +17,12 @@ pytestmark = pytest.mark.gpu
 LOGIT_TOL = 2e-2
 
 
-@pytest.mark.parametrize("tag", ["n2", "n5"])
+@pytest.mark.parametrize("tag", ["n2", "n5", "r34_n2"])
 def test_fused_forward_vs_reference_golden(tag):
+    """r34_n2: the resnet34 backbone through the same kernels (depths 3-4-6-3)."""
     g = G.golden(f"ensemble_{tag}.npz")
     n = int(g["n_heads"])
-    e = G.engine(n)
+    e = G.engine(n, backbone="resnet34" if tag.startswith("r34") else "resnet18")
     x = G.segs(g["seg_ids"]).cuda()
     logits, probs, labels = e.forward_pcm(x, 0.5)
     torch.cuda.synchronize()
@@ -32,7 +33,7 @@ def test_fused_forward_vs_reference_golden(tag):
     names = [str(s) for s in g["class_names"]]
     mine = [R.label_name(int(l), n, names[:-1], names[-1]) for l in labels.cpu().numpy()]
     want = [str(s) for s in g["labels"]]
-    margin = np.abs(g["merged_logits"]).min(axis=1)
+    margin = G.decision_margin(g["merged_logits"])
     for a, b, m in zip(mine, want, margin):
         assert a == b or m <= LOGIT_TOL, (a, b, m)
 
@@ -76,7 +77,7 @@ def test_decisions_and_logits_on_corpus():
     d = (lo - want).abs()
     lab_want, probs_want = R.interpret(want, 0.5)
     agree = la.cpu().numpy() == lab_want
-    margin = want.abs().min(dim=1).values.numpy()
+    margin = G.decision_margin(want.numpy())
     print(f"corpus: max |logit diff| {d.max():.4f} mean {d.mean():.4f}; agreement {agree.mean():.4f} "
           f"(cal {agree[:FX.N_CAL].mean():.4f}, held-out {agree[FX.N_CAL:].mean():.4f}); "
           f"min margin {margin.min():.4f}; disagreements' margins {margin[~agree]}")
