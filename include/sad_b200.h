@@ -143,8 +143,9 @@ int sad_debug_conv(sad_ctx* ctx, int head, int layer, const void* in_dev, const 
  * bf16 image the stem consumed.                                                                                  */
 int sad_debug_stem(sad_ctx* ctx, const float* pcm_dev, int B, void* out_dev, void* stream);
 /* Copy an internal activation of the last sad_forward* chunk to the caller (tests only).
- * which: 0 = image bf16 [B,512,512]; 1 = pooled stem out bf16 [H*B,128,128,64]; 2 = layer4 out bf16
- * [H*B,16,16,512]; 3 = per-head logits fp32 [H*B,2].  Returns the number of bytes written.         */
+ * which: 0 = image bf16 [B,512,512]; 2 = trunk (layer4) output bf16 NHWC [H*B,16,16,512]; 3 = per-head logits fp32
+ * [H*B,2] (index 0 Real, 1 Synthetic); 4 = log-mel dB fp32 [B,128,251].  (1 is reserved: the pooled stem output is
+ * overwritten by the trunk -- use sad_debug_stem.)  Returns the number of bytes written or a negative SAD_E* code. */
 long long sad_debug_read(sad_ctx* ctx, int which, void* dst_dev, long long capacity_bytes, void* stream);
 
 #ifdef __cplusplus

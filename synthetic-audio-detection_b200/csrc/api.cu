@@ -188,7 +188,7 @@ struct sad_ctx {
     int two_cta = 1;                    // 1: N=256 layers (layers 3-4) run on CTA pairs (conv_umma2.cu, cta_group::2); 2: N=128 too (slower)
     int fuse_ds = 1;                    // fold each block's 1x1/s2 downsample conv into conv2 as extra K blocks
     float* d_bias_fused[kMaxConvs] = {nullptr}; // [H][Cout] = bias(conv2) + bias(downsample) for the conv2 that absorbs it
-    int rows_mode = 2;                  // layer1 row-stationary kernel: 0 off, 2 on (1 = probe: descriptor base-offset field set, WRONG on sm_100a)
+    int rows_mode = 1;                  // layer1 row-stationary kernel (conv_rows.cu): 0 = use the generic kernel instead
 
     // end-to-end path
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
@@ -343,7 +343,7 @@ bool encode_weight_map(CUtensorMap* m, const void* base, long long K, long long 
 }  // namespace sad
 
 namespace sad {
-cudaError_t conv_rows_launch(const ConvLaunch& p, int heads, int base_offset_mode, int num_sms, cudaStream_t stream);
+cudaError_t conv_rows_launch(const ConvLaunch& p, int heads, int num_sms, cudaStream_t stream);
 }
 
 namespace {
@@ -466,7 +466,7 @@ void set_batch(sad::ConvLaunch* L, int B, int H) {
 bool is_rows_layer(const sad_ctx* c, int ci);
 cudaError_t launch_conv(sad_ctx* c, int ci, const sad::ConvLaunch& L, int heads, cudaStream_t st) {
     if (ci > 0 && c->rows_mode && is_rows_layer(c, ci))
-        return sad::conv_rows_launch(L, heads, c->rows_mode == 1 ? 1 : 0, c->num_sms, st);
+        return sad::conv_rows_launch(L, heads, c->num_sms, st);
     if (c->two_cta && L.n_tile >= (c->two_cta >= 2 ? 128 : 256) && L.m_tiles_per_img % 2 == 0)
         return sad::conv_umma2_launch(L, c->num_sms, st);
     return sad::conv_umma_launch(L, c->num_sms, st);

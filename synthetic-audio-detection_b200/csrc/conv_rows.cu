@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_rows_kernel(const __grid_con
 
 // `p` as built for the generic kernel, except: a_map[0] must have box {64, 130, 1, 1}; total_tiles is recomputed
 // here as the number of (head, image, strip) units.
-cudaError_t conv_rows_launch(const ConvLaunch& p_in, int heads, int /*unused*/, int num_sms, cudaStream_t stream) {
+cudaError_t conv_rows_launch(const ConvLaunch& p_in, int heads, int num_sms, cudaStream_t stream) {
     cudaError_t e = ensure_dynamic_smem<conv_rows_kernel>(kSmemBytes);
     if (e != cudaSuccess) return e;
     ConvLaunch p = p_in;
