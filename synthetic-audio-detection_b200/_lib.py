@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsad_b200.so")
+LIB_PATH = os.environ.get("SAD_LIB") or os.path.join(_HERE, "libsad_b200.so")   # SAD_LIB: A/B a differently built library
 
 SAD_OK, SAD_EINVAL, SAD_ENODEVICE, SAD_ECUDA, SAD_ESTATE = 0, -1, -2, -3, -4
 _CODES = {SAD_EINVAL: "SAD_EINVAL", SAD_ENODEVICE: "SAD_ENODEVICE", SAD_ECUDA: "SAD_ECUDA", SAD_ESTATE: "SAD_ESTATE"}

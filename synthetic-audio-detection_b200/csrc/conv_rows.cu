@@ -34,7 +34,10 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kW = 128;                       // output / input width and height of layer1
-constexpr int kStripRows = 32;
+#ifndef SAD_ROWS_STRIP
+#define SAD_ROWS_STRIP 32
+#endif
+constexpr int kStripRows = SAD_ROWS_STRIP;
 constexpr int kStripsPerImg = kW / kStripRows;
 constexpr int kInRows = kStripRows + 2;       // input rows per unit
 constexpr int kRowBox = kW + 2;               // 130 pixels incl. the halo

@@ -6,106 +6,102 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdint>
+
 #include "head.h"
 
 namespace sad {
 
 namespace {
 
-// grid (ceil(B / kSegPerCta), H), 256 threads.  feats: NHWC bf16 [H*B][256 px][512]; weights transposed [in][out] fp32.
-// Each CTA serves kSegPerCta segments of one head.  Measured on B200 (768 head-segments per launch): 1 segment per
-// CTA (768 CTAs, full occupancy) 3.2 ms/step, 4 per CTA 6.2 ms, 8 per CTA 7.9 ms -- the kernel is latency-bound, so
-// thread-level parallelism beats re-using the 1.5 MB of weights that sit in L2 anyway.
-constexpr int kSegPerCta = 1;
-
+// grid (B, H), 256 threads: one CTA per (segment, head) -- the kernel is latency-bound, so it wants many CTAs
+// (measured: batching 4 or 8 segments per CTA to re-use the 1.5 MB of L2-resident weights was 2x slower).
+// feats: NHWC bf16 [H*B][256 px][512]; weights transposed [in][out] fp32 so a thread reads 4 consecutive outputs with
+// one 16-byte load; the K dimension is split over thread groups and reduced through shared memory.
 __global__ void __launch_bounds__(256) head_mlp_kernel(const __nv_bfloat16* __restrict__ feats, HeadWeights hw, int B,
                                                        float* __restrict__ head_logits) {
-    __shared__ float pooled[kSegPerCta][512];
-    __shared__ float h1[kSegPerCta][512];
-    __shared__ float h2[kSegPerCta][256];
-    __shared__ float red[kSegPerCta][2][8];
-    const int b0 = blockIdx.x * kSegPerCta, h = blockIdx.y, t = threadIdx.x;
-    const int nseg = min(kSegPerCta, B - b0);
-    for (int s = 0; s < nseg; ++s) {            // global average pool over the 16x16 map, two channels per thread
-        const size_t n = static_cast<size_t>(h) * B + b0 + s;
-        const __nv_bfloat162* f = reinterpret_cast<const __nv_bfloat162*>(feats + n * 256 * 512);
-        float s0 = 0.f, s1 = 0.f;
+    __shared__ __align__(16) float part[4][512];   // partial sums (pool: 4 pixel groups; layers: K splits)
+    __shared__ __align__(16) float pooled[512];
+    __shared__ __align__(16) float h1[512];
+    __shared__ __align__(16) float h2[256];
+    __shared__ float red[2][8];
+    const int b = blockIdx.x, h = blockIdx.y, t = threadIdx.x;
+    const size_t n = static_cast<size_t>(h) * B + b;
+
+    // ---- global average pool over the 16x16 map: thread = (pixel group g of 64 px, 8 channels c8)
+    {
+        const int c8 = t & 63, g = t >> 6;
+        const uint4* f = reinterpret_cast<const uint4*>(feats + n * 256 * 512) + c8;   // 64 uint4 per pixel
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
-        for (int p = 0; p < 256; ++p) {
-            const float2 v = __bfloat1622float2(f[p * 256 + t]);
-            s0 += v.x;
-            s1 += v.y;
+        for (int p = 0; p < 64; ++p) {
+            const uint4 v = __ldg(f + (g * 64 + p) * 64);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[2 * j] += __uint_as_float(w[j] << 16);
+                acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+            }
         }
-        pooled[s][2 * t] = s0 * (1.0f / 256.0f);
-        pooled[s][2 * t + 1] = s1 * (1.0f / 256.0f);
-    }
-    for (int s = nseg; s < kSegPerCta; ++s) {
-        pooled[s][2 * t] = 0.f;
-        pooled[s][2 * t + 1] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part[g][c8 * 8 + j] = acc[j];
     }
     __syncthreads();
+    for (int c = t; c < 512; c += 256)
+        pooled[c] = (((part[0][c] + part[1][c]) + part[2][c]) + part[3][c]) * (1.0f / 256.0f);
+    __syncthreads();
 
-    const float* w1 = hw.w1t + static_cast<size_t>(h) * 512 * 512;
-    float a0[kSegPerCta], a1[kSegPerCta];
-#pragma unroll
-    for (int s = 0; s < kSegPerCta; ++s) {
-        a0[s] = hw.b1[h * 512 + t];
-        a1[s] = hw.b1[h * 512 + t + 256];
-    }
-#pragma unroll 2
-    for (int i = 0; i < 512; ++i) {
-        const float wa = __ldg(w1 + i * 512 + t), wb = __ldg(w1 + i * 512 + t + 256);
-#pragma unroll
-        for (int s = 0; s < kSegPerCta; ++s) {
-            const float x = pooled[s][i];
-            a0[s] = fmaf(x, wa, a0[s]);
-            a1[s] = fmaf(x, wb, a1[s]);
+    // ---- Linear(512,512)+BN folded, ReLU: thread = (K half kh, 4 outputs o4)
+    {
+        const int o4 = t & 127, kh = t >> 7;
+        const float4* w1 = reinterpret_cast<const float4*>(hw.w1t + static_cast<size_t>(h) * 512 * 512) + o4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int i = kh * 256; i < kh * 256 + 256; ++i) {
+            const float x = pooled[i];
+            const float4 w = __ldg(w1 + i * 128);
+            a.x = fmaf(x, w.x, a.x); a.y = fmaf(x, w.y, a.y); a.z = fmaf(x, w.z, a.z); a.w = fmaf(x, w.w, a.w);
         }
-    }
-#pragma unroll
-    for (int s = 0; s < kSegPerCta; ++s) {
-        h1[s][t] = fmaxf(a0[s], 0.f);
-        h1[s][t + 256] = fmaxf(a1[s], 0.f);
+        *reinterpret_cast<float4*>(&part[kh][o4 * 4]) = a;
     }
     __syncthreads();
-
-    const float* w2 = hw.w2t + static_cast<size_t>(h) * 512 * 256;
-    float c[kSegPerCta];
-#pragma unroll
-    for (int s = 0; s < kSegPerCta; ++s) c[s] = hw.b2[h * 256 + t];
-#pragma unroll 2
-    for (int i = 0; i < 512; ++i) {
-        const float w = __ldg(w2 + i * 256 + t);
-#pragma unroll
-        for (int s = 0; s < kSegPerCta; ++s) c[s] = fmaf(h1[s][i], w, c[s]);
-    }
-#pragma unroll
-    for (int s = 0; s < kSegPerCta; ++s) h2[s][t] = fmaxf(c[s], 0.f);
+    for (int c = t; c < 512; c += 256) h1[c] = fmaxf(part[0][c] + part[1][c] + hw.b1[h * 512 + c], 0.f);
     __syncthreads();
 
+    // ---- Linear(512,256)+BN folded, ReLU: thread = (K quarter kq, 4 outputs o4)
+    {
+        const int o4 = t & 63, kq = t >> 6;
+        const float4* w2 = reinterpret_cast<const float4*>(hw.w2t + static_cast<size_t>(h) * 512 * 256) + o4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int i = kq * 128; i < kq * 128 + 128; ++i) {
+            const float x = h1[i];
+            const float4 w = __ldg(w2 + i * 64);
+            a.x = fmaf(x, w.x, a.x); a.y = fmaf(x, w.y, a.y); a.z = fmaf(x, w.z, a.z); a.w = fmaf(x, w.w, a.w);
+        }
+        *reinterpret_cast<float4*>(&part[kq][o4 * 4]) = a;
+    }
+    __syncthreads();
+    h2[t] = fmaxf(((part[0][t] + part[1][t]) + part[2][t]) + part[3][t] + hw.b2[h * 256 + t], 0.f);
+    __syncthreads();
+
+    // ---- Linear(256,2): block reduction
     const float* w3 = hw.w3 + static_cast<size_t>(h) * 2 * 256;   // [2][256] as in nn.Linear
-    const float w30 = w3[t], w31 = w3[256 + t];
+    float z0 = h2[t] * w3[t], z1 = h2[t] * w3[256 + t];
 #pragma unroll
-    for (int s = 0; s < kSegPerCta; ++s) {
-        float z0 = h2[s][t] * w30, z1 = h2[s][t] * w31;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            z0 += __shfl_xor_sync(0xffffffffu, z0, o);
-            z1 += __shfl_xor_sync(0xffffffffu, z1, o);
-        }
-        if ((t & 31) == 0) {
-            red[s][0][t >> 5] = z0;
-            red[s][1][t >> 5] = z1;
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+        z0 += __shfl_xor_sync(0xffffffffu, z0, o);
+        z1 += __shfl_xor_sync(0xffffffffu, z1, o);
+    }
+    if ((t & 31) == 0) {
+        red[0][t >> 5] = z0;
+        red[1][t >> 5] = z1;
     }
     __syncthreads();
-    if (t < 2 * kSegPerCta) {
-        const int s = t >> 1, j = t & 1;
-        if (s < nseg) {
-            float z = hw.b3[h * 2 + j];
-            for (int i = 0; i < 8; ++i) z += red[s][j][i];
-            head_logits[(static_cast<size_t>(h) * B + b0 + s) * 2 + j] = z;   // index 0 = Real, 1 = Synthetic
-        }
+    if (t < 2) {
+        float z = hw.b3[h * 2 + t];
+        for (int i = 0; i < 8; ++i) z += red[t][i];
+        head_logits[n * 2 + t] = z;   // index 0 = Real, 1 = Synthetic
     }
 }
 
@@ -195,7 +191,7 @@ __global__ void __launch_bounds__(256) clip_reduce_kernel(const float* __restric
 
 cudaError_t head_mlp_launch(const __nv_bfloat16* feats, const HeadWeights& hw, int B, int H, float* head_logits,
                             cudaStream_t stream, long long* launches) {
-    head_mlp_kernel<<<dim3((B + kSegPerCta - 1) / kSegPerCta, H), 256, 0, stream>>>(feats, hw, B, head_logits);
+    head_mlp_kernel<<<dim3(B, H), 256, 0, stream>>>(feats, hw, B, head_logits);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -39,7 +39,10 @@ constexpr int kEpiThreads = 128 * kEpiGroups;
 constexpr int kGroupCols = 256 / kEpiGroups;   // conv pixels (TMEM columns) per group
 constexpr int kChunks = kGroupCols / 32;       // tcgen05.ld chunks of 32 columns per group and row
 constexpr int kThreads = 32 + 128 + kEpiThreads;   // warp 0: MMA + TMA; warps 1-4: builders; then the epilogue warps
-constexpr int kStripRows = 32;                 // pooled rows per unit
+#ifndef SAD_STEM_STRIP
+#define SAD_STEM_STRIP 32
+#endif
+constexpr int kStripRows = SAD_STEM_STRIP;     // pooled rows per unit
 constexpr int kStrips = 128 / kStripRows;
 constexpr int kConvRowsPerUnit = 2 * kStripRows + 1;
 constexpr int kPixTile = 256 * 128;            // pixel tile: 256 rows x 128 B

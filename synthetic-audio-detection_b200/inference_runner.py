@@ -295,6 +295,8 @@ def window_and_hop(sr: int, cfg: AudioConfig) -> Tuple[int, int]:
     """IR:180-181, python float arithmetic truncated with int()."""
     window_samples = int(cfg.window_size * sr)
     hop_samples = int((1 - cfg.overlap) * window_samples)
+    if hop_samples == 0:
+        raise ValueError("range() arg 3 must not be zero")        # what the reference's range(...) raises (IR:184)
     return window_samples, hop_samples
 
 
