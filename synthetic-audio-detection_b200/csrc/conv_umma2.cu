@@ -28,23 +28,25 @@ constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
 constexpr int kThreads2 = 192;
 
-template <int N_TILE>
+template <int N_TILE, int MT>
 struct Cfg2 {
     static constexpr int kBHalfBytes = (N_TILE / 2) * kBlockK * 2;
-    static constexpr int kStageBytes = kABytes + kBHalfBytes;             // per CTA
+    static constexpr int kStageBytes = MT * kABytes + kBHalfBytes;        // per CTA: MT M tiles share one weight stage
     static constexpr int kOutBufs = 2;
     static constexpr int kOutBytes = 4 * kOutBufs * 4096;
     static constexpr int kBudget = 224 * 1024;
     static constexpr int kStages = ((kBudget - kOutBytes) / kStageBytes) > 8 ? 8 : ((kBudget - kOutBytes) / kStageBytes);
-    static constexpr int kTmemCols = 2 * N_TILE;                          // double-buffered accumulator (own 128 rows)
+    static constexpr int kAccCols = MT * N_TILE;
+    static constexpr int kTmemCols = 2 * kAccCols;                        // double-buffered accumulators (own rows)
+    static_assert(kTmemCols <= 512, "accumulators do not fit TMEM");
     static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + 256;
     static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
-template <int N_TILE>
+template <int N_TILE, int MT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
     conv_umma2_kernel(const __grid_constant__ ConvLaunch p) {
-    using C = Cfg2<N_TILE>;
+    using C = Cfg2<N_TILE, MT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* tiles = smem;
@@ -90,9 +92,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
     const int taps = p.ksize * p.ksize;
     const int cblocks = p.Cin / kBlockK;
     const int ksteps = taps * cblocks + p.k2_blocks;
-    const int m_groups = p.m_tiles_per_img / 2;
+    const int m_groups = p.m_tiles_per_img / (2 * MT);       // a pair tile = 2*MT consecutive M tiles of one image
     const int tiles_per_head = p.imgs_per_head * m_groups * p.n_tiles;
-    const int total_groups = p.total_tiles / 2;
+    const int total_groups = p.total_tiles / (2 * MT);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -104,7 +106,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
                 int r = tile - head * tiles_per_head;
                 const int n_t = r % p.n_tiles;
                 r /= p.n_tiles;
-                const int m_t = (r % m_groups) * 2 + static_cast<int>(rank);
+                const int m_t = ((r % m_groups) * 2 + static_cast<int>(rank)) * MT;
                 const int img = r / m_groups;
                 const int img_in = p.shared_input ? img : head * p.imgs_per_head + img;
                 const int oy0 = m_t * p.rows_per_tile;
@@ -122,8 +124,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* a_dst = tiles + stage * C::kStageBytes;
                         if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
-                        tma_load_4d_2sm(a_dst, &p.a_map[map], &full_bar[stage], cb * kBlockK, x0, y0, img_in);
-                        tma_load_2d_2sm(a_dst + kABytes, &p.bh_map, &full_bar[stage], tap * p.Cin + cb * kBlockK, wrow);
+#pragma unroll
+                        for (int m = 0; m < MT; ++m)
+                            tma_load_4d_2sm(a_dst + m * kABytes, &p.a_map[map], &full_bar[stage], cb * kBlockK, x0,
+                                            y0 + m * p.rows_per_tile, img_in);
+                        tma_load_2d_2sm(a_dst + MT * kABytes, &p.bh_map, &full_bar[stage], tap * p.Cin + cb * kBlockK, wrow);
                         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -131,8 +136,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* a_dst = tiles + stage * C::kStageBytes;
                     if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
-                    tma_load_4d_2sm(a_dst, &p.a2_map, &full_bar[stage], cb * kBlockK, 0, oy0, img_in);
-                    tma_load_2d_2sm(a_dst + kABytes, &p.b2h_map, &full_bar[stage], cb * kBlockK, wrow);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+                        tma_load_4d_2sm(a_dst + m * kABytes, &p.a2_map, &full_bar[stage], cb * kBlockK, 0,
+                                        oy0 + m * p.rows_per_tile, img_in);
+                    tma_load_2d_2sm(a_dst + MT * kABytes, &p.b2h_map, &full_bar[stage], cb * kBlockK, wrow);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -148,16 +156,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
                 const int acc = it & 1;
                 mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * N_TILE;
+                const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(tiles + stage * C::kStageBytes);
-                    const uint64_t adesc = umma_desc_sw128(a_addr);
-                    const uint64_t bdesc = umma_desc_sw128(a_addr + kABytes);
+                    const uint64_t bdesc = umma_desc_sw128(a_addr + MT * kABytes);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k)
-                        umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+                    for (int m = 0; m < MT; ++m) {
+                        const uint64_t adesc = umma_desc_sw128(a_addr + m * kABytes);
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16_2sm(d_tmem + m * N_TILE, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+                    }
                     umma_commit_2sm(&empty_bar[stage]);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -176,18 +187,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
             int r = tile - head * tiles_per_head;
             const int n_t = r % p.n_tiles;
             r /= p.n_tiles;
-            const int m_t = (r % m_groups) * 2 + static_cast<int>(rank);
+            const int m_t = ((r % m_groups) * 2 + static_cast<int>(rank)) * MT;
             const int img = r / m_groups;
             const int acc = it & 1;
             const int co0 = n_t * N_TILE;
             const float4* bias4 = reinterpret_cast<const float4*>(p.bias + head * p.Cout + co0);
-            const long long pix0 = (static_cast<long long>(head) * p.imgs_per_head + img) * (p.m_tiles_per_img * kBlockM) +
-                                   m_t * kBlockM;
-            const __nv_bfloat16* res = p.residual ? p.residual + (pix0 + row) * p.Cout + co0 : nullptr;
 
             mbar_wait(&tmem_full[acc], (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * N_TILE;
+#pragma unroll 1
+            for (int m = 0; m < MT; ++m) {
+            const long long pix0 = (static_cast<long long>(head) * p.imgs_per_head + img) * (p.m_tiles_per_img * kBlockM) +
+                                   (m_t + m) * kBlockM;
+            const __nv_bfloat16* res = p.residual ? p.residual + (pix0 + row) * p.Cout + co0 : nullptr;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::kAccCols + m * N_TILE;
 #pragma unroll 1
             for (int c0 = 0; c0 < N_TILE; c0 += 64, ++nstore) {
                 uint32_t v0[32], v1[32];
@@ -199,7 +212,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
                     for (int q = 0; q < 8; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(res + c0) + q);
                 }
                 tmem_ld_wait();
-                if (c0 + 64 >= N_TILE) {              // accumulator is in registers: hand TMEM back to the leader's MMA warp
+                if (c0 + 64 >= N_TILE && m == MT - 1) {   // accumulators are in registers: hand TMEM back to the leader's MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -244,6 +257,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
                     tma_store_commit();
                 }
             }
+            }
         }
         if (lane == 0) tma_store_wait<0>();
     }
@@ -254,15 +268,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
     if (warp == 1) tmem_dealloc_2sm<C::kTmemCols>(tmem_base);
 }
 
-template <int N_TILE>
+template <int N_TILE, int MT>
 cudaError_t launch2_t(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
-    using C = Cfg2<N_TILE>;
-    cudaError_t e = ensure_dynamic_smem<conv_umma2_kernel<N_TILE>>(C::kSmemBytes);
+    using C = Cfg2<N_TILE, MT>;
+    cudaError_t e = ensure_dynamic_smem<conv_umma2_kernel<N_TILE, MT>>(C::kSmemBytes);
     if (e != cudaSuccess) {
         fprintf(stderr, "conv_umma2<%d>: cudaFuncSetAttribute(%d B) -> %s\n", N_TILE, C::kSmemBytes, cudaGetErrorString(e));
         return e;
     }
-    const int groups = p.total_tiles / 2;
+    const int groups = p.total_tiles / (2 * MT);
     int pairs = num_sms / 2;
     if (groups < pairs) pairs = groups;
     cudaLaunchConfig_t cfg = {};
@@ -270,7 +284,7 @@ cudaError_t launch2_t(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
     cfg.blockDim = dim3(kThreads2);
     cfg.dynamicSmemBytes = C::kSmemBytes;
     cfg.stream = stream;
-    e = cudaLaunchKernelEx(&cfg, conv_umma2_kernel<N_TILE>, p);
+    e = cudaLaunchKernelEx(&cfg, conv_umma2_kernel<N_TILE, MT>, p);
     if (e != cudaSuccess)
         fprintf(stderr, "conv_umma2<%d>: launch grid %d smem %d -> %s\n", N_TILE, 2 * pairs, C::kSmemBytes, cudaGetErrorString(e));
     return e;
@@ -281,8 +295,8 @@ cudaError_t launch2_t(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
 cudaError_t conv_umma2_launch(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
     if (p.m_tiles_per_img % 2 != 0) return cudaErrorInvalidValue;
     switch (p.n_tile) {
-        case 128: return launch2_t<128>(p, num_sms, stream);
-        case 256: return launch2_t<256>(p, num_sms, stream);
+        case 128: return (p.m_tiles_per_img % 4 == 0) ? launch2_t<128, 2>(p, num_sms, stream) : launch2_t<128, 1>(p, num_sms, stream);
+        case 256: return launch2_t<256, 1>(p, num_sms, stream);
         default: return cudaErrorInvalidValue;
     }
 }
