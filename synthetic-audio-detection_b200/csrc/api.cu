@@ -846,7 +846,9 @@ int sad_load_weights(sad_ctx* c, int head, const float* const* T, int n_tensors)
 }
 
 int sad_frontend_logmel(sad_ctx* c, const float* pcm, int B, float* logmel_db, float* mu_sigma, void* stream) {
-    if (!c || !pcm || B < 0) return SAD_EINVAL;
+    if (!c) return SAD_EINVAL;
+    if (B == 0) return SAD_OK;   // an empty batch is a no-op (its buffers may be null)
+    if (!pcm || B < 0) return fail(c, SAD_EINVAL, "null pcm or negative batch");
     CU_OK(c, cudaSetDevice(c->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     for (int b0 = 0; b0 < B; b0 += c->Bc) {
@@ -863,7 +865,9 @@ int sad_frontend_logmel(sad_ctx* c, const float* pcm, int B, float* logmel_db, f
 }
 
 int sad_frontend_image(sad_ctx* c, const float* pcm, int B, float* image, void* stream) {
-    if (!c || !pcm || !image || B < 0) return SAD_EINVAL;
+    if (!c) return SAD_EINVAL;
+    if (B == 0) return SAD_OK;
+    if (!pcm || !image || B < 0) return fail(c, SAD_EINVAL, "null buffer or negative batch");
     CU_OK(c, cudaSetDevice(c->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     for (int b0 = 0; b0 < B; b0 += c->Bc) {
@@ -896,7 +900,9 @@ int sad_gather_windows(sad_ctx* c, const float* wf, const long long* starts, int
 
 int sad_forward(sad_ctx* c, const float* pcm, int B, float thr, float* logits, float* probs, int32_t* labels,
                 void* stream) {
-    if (!c || !pcm || B < 0) return SAD_EINVAL;
+    if (!c) return SAD_EINVAL;
+    if (B == 0) return SAD_OK;
+    if (!pcm || B < 0) return fail(c, SAD_EINVAL, "null pcm or negative batch");
     CU_OK(c, cudaSetDevice(c->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int n1 = c->H + 1;
@@ -912,7 +918,9 @@ int sad_forward(sad_ctx* c, const float* pcm, int B, float thr, float* logits, f
 
 int sad_forward_images(sad_ctx* c, const float* x, int B, float thr, float* logits, float* probs, int32_t* labels,
                        void* stream) {
-    if (!c || !x || B < 0) return SAD_EINVAL;
+    if (!c) return SAD_EINVAL;
+    if (B == 0) return SAD_OK;
+    if (!x || B < 0) return fail(c, SAD_EINVAL, "null images or negative batch");
     CU_OK(c, cudaSetDevice(c->device));
     if (!c->stem3_ready) {
         CU_OK(c, dalloc(&c->d_A3, static_cast<size_t>(c->Bc) * 65536 * 192));
@@ -934,7 +942,9 @@ int sad_forward_images(sad_ctx* c, const float* x, int B, float thr, float* logi
 
 int sad_forward_host(sad_ctx* c, const float* pcm_host, int B, float thr, float* logits_host, float* probs_host,
                      int32_t* labels_host) {
-    if (!c || !pcm_host || B < 0) return SAD_EINVAL;
+    if (!c) return SAD_EINVAL;
+    if (B == 0) return SAD_OK;
+    if (!pcm_host || B < 0) return fail(c, SAD_EINVAL, "null pcm or negative batch");
     CU_OK(c, cudaSetDevice(c->device));
     const size_t seg = SAD_SEGMENT_SAMPLES;
     const int n1 = c->H + 1;
@@ -996,7 +1006,10 @@ int sad_forward_host(sad_ctx* c, const float* pcm_host, int B, float thr, float*
 
 int sad_clip_reduce(sad_ctx* c, const float* probs, const int32_t* clip_id, int B, int n_clips, float thr,
                     float* clip_probs, int32_t* clip_label, void* stream) {
-    if (!c || !probs || !clip_id || !clip_probs || !clip_label || B < 0 || n_clips < 0) return SAD_EINVAL;
+    if (!c) return SAD_EINVAL;
+    if (n_clips == 0) return SAD_OK;
+    if (!clip_probs || !clip_label || B < 0 || n_clips < 0 || (B > 0 && (!probs || !clip_id)))
+        return fail(c, SAD_EINVAL, "null buffer or negative count");
     CU_OK(c, cudaSetDevice(c->device));
     CU_OK(c, sad::clip_reduce_launch(probs, clip_id, B, n_clips, c->H, thr, clip_probs, clip_label,
                                      static_cast<cudaStream_t>(stream), &c->launches));
