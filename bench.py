@@ -264,6 +264,10 @@ def run_native(args):
         if prof_ms[c2 + 1] == 0:
             flops[c2] += flops[c2 + 1]
             flops[c2 + 1] = 0.0
+    for c1 in (1, 3):                           # layer1 BasicBlocks run as ONE launch (block_rows.cu), timed under conv2
+        if prof_ms[c1] == 0:
+            flops[c1 + 1] += flops[c1]
+            flops[c1] = 0.0
     conv_ms = sum(prof_ms[i] for i in range(20))
     conv_launches = sum(prof_n[i] for i in range(20))
     conv_tflop = sum(flops[i] for i in range(20)) * 1e9 * H * B * K / 1e12
@@ -276,6 +280,10 @@ def run_native(args):
             tj = json.load(f)
         if tj.get("chunk") == args.max_batch and tj.get("heads") == H:
             traffic = tj["dram_bytes_per_launch_mean"]
+    n_conv_launches = sum(1 for i in range(20) if prof_n[i] > 0)
+    # activation bytes per (head, segment): 40 MB with one launch per conv; a fused layer1 block keeps its
+    # intermediate and residual on chip: -3 x 2.1 MB per block
+    alg_mb = 40.0 - sum(6.3 for c1 in (1, 3) if prof_ms[c1] == 0)
     per_layer = {str(i): round(flops[i] * 1e9 * H * B * K / 1e12 / (prof_ms[i] / 1e3), 1) if prof_ms[i] > 0 else None
                  for i in range(20)}
     fe_ms = prof_ms[eng.PROF_FRONTEND]
@@ -295,8 +303,9 @@ def run_native(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "kernel": "conv_umma_kernel<128,2|256,1> + conv_rows_kernel + stem_fused_kernel (17 launches per chunk)",
-                     "algorithmic_bytes_per_launch": (H * args.max_batch * 40.0e6) / 17.0,
+                     "kernel": "conv_umma_kernel<128,2> + conv_umma2_kernel<256> + block_rows_kernel + stem_fused_kernel "
+                               "(%d launches per chunk)" % n_conv_launches,
+                     "algorithmic_bytes_per_launch": (H * args.max_batch * alg_mb * 1e6) / n_conv_launches,
                      "flops_model": "18.1278 GFLOP/head/segment (channel-folded stem, K=49)",
                      "peak_source": pk["source"] + " bf16_tflops_sustained",
                      "kernel_ms_per_step": conv_ms / K, "kernel_launches": int(conv_launches),

@@ -138,6 +138,9 @@ int sad_profile_read(sad_ctx* ctx, double* ms_by_kind, long long* launches_by_ki
  * [B,Ho,Wo,Cout] or NULL, `out` [B,Ho,Wo,Cout].  Used by the per-layer parity tests.                */
 int sad_debug_conv(sad_ctx* ctx, int head, int layer, const void* in_dev, const void* residual_dev, void* out_dev,
                    int B, int relu, void* stream);
+/* Run ONE whole layer1 BasicBlock of one head (convs `layer` and `layer`+1 + identity, fused on CTA pairs through
+ * peer shared memory): `in` / `out` NHWC bf16 [B,128,128,64].  Must equal two sad_debug_conv calls bit for bit.   */
+int sad_debug_block(sad_ctx* ctx, int head, int layer, const void* in_dev, void* out_dev, int B, void* stream);
 /* Run front end + fused stem/max-pool on pcm [B,128000] (B <= max_batch) and copy the pooled stem output, NHWC bf16
  * [H*B,128,128,64] (head-major), to out_dev.  Used by the stem parity test; sad_debug_read(which=0) then returns the
  * bf16 image the stem consumed.                                                                                  */

@@ -43,6 +43,7 @@ SIGNATURES = {
     "sad_profile_enable": (_i, [_vp, _i]),
     "sad_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_ll)]),
     "sad_debug_conv": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "sad_debug_block": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp]),
     "sad_debug_stem": (_i, [_vp, _vp, _i, _vp, _vp]),
     "sad_debug_read": (_ll, [_vp, _i, _vp, _ll, _vp]),
 }

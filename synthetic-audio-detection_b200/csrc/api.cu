@@ -113,25 +113,32 @@ struct Step {
     int in, res, out;
     int relu;
     int fused_ds;   // conv index of a downsample branch accumulated into this conv (reads buffer X), or -1
+    int block2;     // >= 0: this step is a whole BasicBlock (block_rows.cu): `conv` = conv1, `block2` = conv2, res == in
 };
 // Walk the blocks: `cur` holds the block input, conv1 -> T, conv2 (+identity or downsample branch) -> the other of X/Y.
-std::vector<Step> build_plan(const NetSpec& net, bool fuse_ds, int* final_buf) {
+std::vector<Step> build_plan(const NetSpec& net, bool fuse_ds, bool fuse_block, int* final_buf) {
     std::vector<Step> p;
     int ci = 1, cur = BX;
     for (int li = 0; li < 4; ++li) {
         for (int b = 0; b < net.depths[li]; ++b) {
             const int other = cur == BX ? BY : BX;
             const bool has_ds = (b == 0 && li > 0);
-            p.push_back({ci + 0, cur, BNONE, BT, 1, -1});
+            if (fuse_block && li == 0) {   // layer1: conv1 -> conv2 + identity on a CTA pair, the intermediate stays on chip
+                p.push_back({ci + 0, cur, cur, other, 1, -1, ci + 1});
+                ci += 2;
+                cur = other;
+                continue;
+            }
+            p.push_back({ci + 0, cur, BNONE, BT, 1, -1, -1});
             if (!has_ds) {
-                p.push_back({ci + 1, BT, cur, other, 1, -1});
+                p.push_back({ci + 1, BT, cur, other, 1, -1, -1});
                 ci += 2;
             } else if (fuse_ds) {
-                p.push_back({ci + 1, BT, BNONE, other, 1, ci + 2});   // conv2 + downsample(cur) accumulated in one tile
+                p.push_back({ci + 1, BT, BNONE, other, 1, ci + 2, -1});   // conv2 + downsample(cur) accumulated in one tile
                 ci += 3;
             } else {
-                p.push_back({ci + 2, cur, BNONE, BD, 0, -1});
-                p.push_back({ci + 1, BT, BD, other, 1, -1});
+                p.push_back({ci + 2, cur, BNONE, BD, 0, -1, -1});
+                p.push_back({ci + 1, BT, BD, other, 1, -1, -1});
                 ci += 3;
             }
             cur = other;
@@ -187,6 +194,7 @@ struct sad_ctx {
     bool stem3_ready = false;
     int two_cta = 1;                    // 1: N=256 layers (layers 3-4) run on CTA pairs (conv_umma2.cu, cta_group::2); 2: N=128 too (slower)
     int fuse_ds = 1;                    // fold each block's 1x1/s2 downsample conv into conv2 as extra K blocks
+    int fuse_block = 1;                 // layer1 BasicBlocks run as one launch on CTA pairs (block_rows.cu)
     float* d_bias_fused[kMaxConvs] = {nullptr}; // [H][Cout] = bias(conv2) + bias(downsample) for the conv2 that absorbs it
     int rows_mode = 1;                  // layer1 row-stationary kernel (conv_rows.cu): 0 = use the generic kernel instead
 
@@ -342,13 +350,9 @@ bool encode_weight_map(CUtensorMap* m, const void* base, long long K, long long 
 
 }  // namespace sad
 
-namespace sad {
-cudaError_t conv_rows_launch(const ConvLaunch& p, int heads, int num_sms, cudaStream_t stream);
-}
-
 namespace {
 
-cudaError_t launch_conv(sad_ctx* c, int ci, const sad::ConvLaunch& L, int heads, cudaStream_t st);
+cudaError_t launch_conv(sad_ctx* c, int ci, const sad::ConvLaunch& L, int heads, cudaStream_t st, bool block = false);
 
 // Fill one ConvLaunch for conv `ci` reading `in` (NHWC [n_imgs][hin][hin][cin]) and writing `out`.
 bool is_rows_layer(const sad_ctx* c, int ci) {
@@ -357,12 +361,16 @@ bool is_rows_layer(const sad_ctx* c, int ci) {
 }
 
 bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const bf16* res, bf16* out, long long n_imgs,
-                 int relu, int fused_ds = -1, const bf16* ds_in = nullptr) {
+                 int relu, int fused_ds = -1, const bf16* ds_in = nullptr, int block2 = -1) {
     const ConvSpec& s = c->net->convs[ci];
     memset(L, 0, sizeof(*L));
     const int Wo = s.hout, Hi = s.hin, C = s.cin;
     const int rows = 128 / Wo;
-    if (c->rows_mode && is_rows_layer(c, ci)) {
+    if (block2 >= 0 && !(is_rows_layer(c, ci) && is_rows_layer(c, block2) && res == in)) {
+        snprintf(c->err, sizeof(c->err), "convs %d,%d do not form a fusable 64-channel block", ci, block2);
+        return false;
+    }
+    if ((c->rows_mode || block2 >= 0) && is_rows_layer(c, ci)) {
         // row-stationary kernel (conv_rows.cu): one box = a whole halo'd input row {64 ch, 130 px, 1 row}
         if (!sad::encode_act_map(&L->a_map[0], in, C, Hi, Hi, n_imgs, C, 1LL * Hi * C, 1LL * Hi * Hi * C, Wo + 2, 1, c->err,
                                  sizeof(c->err)))
@@ -411,6 +419,11 @@ bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const b
         L->bh_map = L->b_map;
     }
     L->b2h_map = L->bh_map;
+    if (block2 >= 0) {
+        if (!sad::encode_weight_map(&L->b2_map, c->d_w[block2], K, 1LL * c->H * s.cout, n_tile, c->err, sizeof(c->err)))
+            return false;
+        L->bias2 = c->d_bias[block2];
+    }
     if (fused_ds >= 0) {
         const ConvSpec& d = c->net->convs[fused_ds];         // 1x1, stride 2, pad 0, same Cout and output size as `s`
         if (d.cout != s.cout || d.hout != s.hout || d.k != 1 || d.stride != 2) {
@@ -464,7 +477,8 @@ void set_batch(sad::ConvLaunch* L, int B, int H) {
 }
 
 bool is_rows_layer(const sad_ctx* c, int ci);
-cudaError_t launch_conv(sad_ctx* c, int ci, const sad::ConvLaunch& L, int heads, cudaStream_t st) {
+cudaError_t launch_conv(sad_ctx* c, int ci, const sad::ConvLaunch& L, int heads, cudaStream_t st, bool block) {
+    if (block) return sad::block_rows_launch(L, heads, c->num_sms, st);
     if (ci > 0 && c->rows_mode && is_rows_layer(c, ci))
         return sad::conv_rows_launch(L, heads, c->num_sms, st);
     if (c->two_cta && L.n_tile >= (c->two_cta >= 2 ? 128 : 256) && L.m_tiles_per_img % 2 == 0)
@@ -634,6 +648,7 @@ int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const c
     c->net = net;
     if (const char* e = getenv("SAD_CONV_ROWS")) c->rows_mode = atoi(e);
     if (const char* e = getenv("SAD_FUSE_DS")) c->fuse_ds = atoi(e);
+    if (const char* e = getenv("SAD_FUSE_BLOCK")) c->fuse_block = atoi(e);
     if (const char* e = getenv("SAD_2CTA")) c->two_cta = atoi(e);
     *out = c;   // returned even on failure so the caller can read sad_last_error, then sad_destroy
     CU_OK(c, cudaSetDevice(device));
@@ -687,12 +702,12 @@ int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const c
     if (!sad::encode_pix_map(&c->stem1.out_map, c->d_buf[BX], 64, HB * 128 * 128, 128, c->err, sizeof(c->err))) return SAD_ECUDA;
     c->stem1.img = c->d_img;
     c->stem1.H = n_heads;
-    c->plan = build_plan(*net, c->fuse_ds != 0, &c->final_buf);
+    c->plan = build_plan(*net, c->fuse_ds != 0, c->fuse_block != 0, &c->final_buf);
     c->plan_launch.resize(c->plan.size());
     for (size_t i = 0; i < c->plan.size(); ++i) {
         const Step& s = c->plan[i];
         if (!make_launch(c, &c->plan_launch[i], s.conv, c->d_buf[s.in], s.res == BNONE ? nullptr : c->d_buf[s.res],
-                         c->d_buf[s.out], HB, s.relu, s.fused_ds, c->d_buf[s.fused_ds >= 0 ? c->plan[i - 1].in : BX]))
+                         c->d_buf[s.out], HB, s.relu, s.fused_ds, c->d_buf[s.fused_ds >= 0 ? c->plan[i - 1].in : BX], s.block2))
             return SAD_ECUDA;
     }
 
@@ -1045,6 +1060,30 @@ int sad_debug_conv(sad_ctx* c, int head, int layer, const void* in, const void* 
     return SAD_OK;
 }
 
+int sad_debug_block(sad_ctx* c, int head, int layer, const void* in, void* out, int B, void* stream) {
+    if (!c || !in || !out || B < 1) return SAD_EINVAL;
+    if (layer < 1 || layer + 1 >= static_cast<int>(c->net->convs.size()) || !is_rows_layer(c, layer) || !is_rows_layer(c, layer + 1))
+        return fail(c, SAD_EINVAL, "convs %d,%d are not a 64-channel 128x128 block", layer, layer + 1);
+    if (head < 0 || head >= c->H) return fail(c, SAD_EINVAL, "head out of range");
+    if (!c->loaded[head]) return fail(c, SAD_ESTATE, "weights of head %d not loaded", head);
+    CU_OK(c, cudaSetDevice(c->device));
+    sad::ConvLaunch L;
+    if (!make_launch(c, &L, layer, static_cast<const bf16*>(in), static_cast<const bf16*>(in), static_cast<bf16*>(out), B, 1, -1,
+                     nullptr, layer + 1))
+        return SAD_ECUDA;
+    const long long K = 9LL * 64;
+    if (!sad::encode_weight_map(&L.b_map, c->d_w[layer] + static_cast<size_t>(head) * 64 * K, K, 64, 64, c->err, sizeof(c->err)) ||
+        !sad::encode_weight_map(&L.b2_map, c->d_w[layer + 1] + static_cast<size_t>(head) * 64 * K, K, 64, 64, c->err,
+                                sizeof(c->err)))
+        return SAD_ECUDA;
+    L.bias = c->d_bias[layer] + static_cast<size_t>(head) * 64;
+    L.bias2 = c->d_bias[layer + 1] + static_cast<size_t>(head) * 64;
+    set_batch(&L, B, 1);
+    CU_OK(c, launch_conv(c, layer, L, 1, static_cast<cudaStream_t>(stream), true));
+    c->launches += 1;
+    return SAD_OK;
+}
+
 int sad_profile_enable(sad_ctx* c, int on) {
     if (!c) return SAD_EINVAL;
     cudaSetDevice(c->device);
@@ -1153,8 +1192,9 @@ int run_chunk(sad_ctx* c, const float* pcm, const float* x_nchw, int B, float th
     for (size_t i = 0; i < c->plan.size(); ++i) {
         sad::ConvLaunch L = c->plan_launch[i];
         set_batch(&L, B, H);
-        ProfScope ps(c, c->plan[i].conv, st);
-        CU_OK(c, launch_conv(c, c->plan[i].conv, L, H, st));
+        const bool block = c->plan[i].block2 >= 0;           // a fused block is timed under its conv2 slot
+        ProfScope ps(c, block ? c->plan[i].block2 : c->plan[i].conv, st);
+        CU_OK(c, launch_conv(c, c->plan[i].conv, L, H, st, block));
         c->launches += 1;
     }
     sad::HeadWeights hw{c->d_w1t, c->d_b1, c->d_w2t, c->d_b2, c->d_w3, c->d_b3};

@@ -16,6 +16,7 @@ struct alignas(64) ConvLaunch {
     CUtensorMap bh_map;     // b_map / b2_map with box {64, n_tile/2}: each CTA of a 2-CTA pair loads half of the N rows
     CUtensorMap b2h_map;
     const float* bias;      // [heads*Cout] fp32 (folded BN shift)
+    const float* bias2;     // fused BasicBlock (block_rows.cu): bias of conv2 (its weights are b2_map)
     const __nv_bfloat16* residual;   // NHWC [heads*imgs][Ho*Wo][Cout] or nullptr
     __nv_bfloat16* out;     // NHWC [heads*imgs][Ho*Wo][Cout]
     int Cin, Cout;
@@ -51,6 +52,10 @@ int conv_n_tile(int Cout);
 cudaError_t conv_umma_launch(const ConvLaunch& p, int num_sms, cudaStream_t stream);
 // 2-CTA (cta_group::2) variant: M = 256 per CTA pair, B split across the pair.  Requires an even m_tiles_per_img.
 cudaError_t conv_umma2_launch(const ConvLaunch& p, int num_sms, cudaStream_t stream);
+// Row-stationary 3x3 conv for the 64-channel 128x128 maps (conv_rows.cu) and the whole layer1 BasicBlock on a CTA pair
+// (block_rows.cu: conv1 on the even CTA, conv2 + identity on the odd one, the intermediate goes through peer smem).
+cudaError_t conv_rows_launch(const ConvLaunch& p, int heads, int num_sms, cudaStream_t stream);
+cudaError_t block_rows_launch(const ConvLaunch& p, int heads, int num_sms, cudaStream_t stream);
 
 // Tensor-map construction (api.cu): resolves cuTensorMapEncodeTiled through the runtime so that the
 // library does not link against libcuda and still loads on a machine without a driver.

@@ -209,6 +209,13 @@ class Engine:
                                                      int(relu), _stream(self.device)), "sad_debug_conv")
         return out
 
+    def debug_block(self, head: int, layer: int, x: torch.Tensor) -> torch.Tensor:
+        """One fused layer1 BasicBlock (convs `layer`, `layer`+1 + identity) on x [B,128,128,64] bf16."""
+        out = torch.empty_like(x)
+        _lib.check(self.ctx, self.lib.sad_debug_block(self.ctx, head, layer, _ptr(x), _ptr(out), x.shape[0],
+                                                      _stream(self.device)), "sad_debug_block")
+        return out
+
     def debug_stem(self, pcm: torch.Tensor) -> torch.Tensor:
         """Pooled stem output [H*B,128,128,64] bf16 for pcm [B,128000] (B <= max_batch)."""
         self._check(pcm, (SEGMENT,))

@@ -85,3 +85,50 @@ def test_fused_stem_and_pool():
         print(f"stem head {h}: max abs err {err.max():.4f} (|want| max {want.abs().max():.2f}), "
               f"frac out of tol {(err > tol).float().mean():.2e}")
         assert (err > tol).float().mean() == 0.0
+
+
+@pytest.mark.parametrize("first", [1, 3])
+@pytest.mark.parametrize("B", [1, 5])
+def test_fused_basic_block_equals_two_launches(first, B):
+    """K3c (block_rows.cu): conv1 -> conv2 + identity on a CTA pair through peer shared memory must reproduce the
+    two single-conv launches BIT FOR BIT (same bf16 rounding of the intermediate, same accumulation order), and both
+    must agree with torch fp32 on the same bf16 operands."""
+    head = 1
+    e = G.engine(2)
+    g = torch.Generator().manual_seed(500 + first + B)
+    x = (torch.randn(B, 128, 128, 64, generator=g) * 0.7).to(torch.bfloat16).cuda()
+    mid = e.debug_conv(head, first, x, None, (B, 128, 128, 64), True)
+    two = e.debug_conv(head, first + 1, mid, x, (B, 128, 128, 64), True)
+    one = e.debug_block(head, first, x)
+    torch.cuda.synchronize()
+    assert torch.equal(one.view(torch.int16), two.view(torch.int16)), \
+        f"fused block differs from two launches: {(one.float() - two.float()).abs().max().item()}"
+    # independent check of the fused result (image borders included) against torch fp32 on the CPU
+    sd = G.merged_sd(2)
+    p = f"sub_models.{head}.base."
+    xc = x.float().cpu().permute(0, 3, 1, 2)
+    w1, b1 = E.fold_bn(sd[p + LAYERS[first][1] + ".weight"], sd, p + BNS[first][1])
+    w2, b2 = E.fold_bn(sd[p + LAYERS[first + 1][1] + ".weight"], sd, p + BNS[first + 1][1])
+    m = F.relu(F.conv2d(xc, w1.to(torch.bfloat16).float(), b1, padding=1)).to(torch.bfloat16).float()
+    want = F.relu(F.conv2d(m, w2.to(torch.bfloat16).float(), b2, padding=1) + xc)
+    got = one.float().cpu().permute(0, 3, 1, 2)
+    err = (got - want).abs()
+    tol = 2.0 ** -7 * want.abs() + 3e-2        # one extra bf16 rounding (the intermediate) can flip by one ulp
+    assert (err > tol).float().mean().item() < 1e-5, f"max err {err.max():.4f}"
+
+
+def test_fused_block_switch_gives_identical_logits(monkeypatch):
+    """Whole path with SAD_FUSE_BLOCK=0 and =1: identical logits, and the fused plan launches two kernels fewer."""
+    from sad_b200.engine import Engine
+    x = FX.synth_segments(5, first=40).cuda()
+    outs, launches = [], []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SAD_FUSE_BLOCK", flag)
+        eng = Engine(2, torch.device("cuda", 0), max_batch=4)
+        eng.load_merged_state_dict(G.merged_sd(2))
+        n0 = eng.launches
+        outs.append(eng.forward_pcm(x, 0.5)[0].cpu())
+        launches.append(eng.launches - n0)
+        eng.close()
+    assert torch.equal(outs[0], outs[1])
+    assert launches[0] - launches[1] == 2 * 2                      # two chunks (4 + 1 segments) x two blocks
