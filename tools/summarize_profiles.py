@@ -20,9 +20,9 @@ out = ["# ncu launch list, round 1 final (bench.py --steps 1 --warmup 3 --batch 
 conv = 0.0
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"\"{k[:100]}\",{n},{t:.1f},{t / tot:.4f}")
-    if "conv_" in k or "stem_fused" in k:
+    if "conv_" in k or "stem_fused" in k or "block_rows" in k:
         conv += t
-out.append(f"# share of conv_umma + conv_umma2 + conv_rows + stem_fused kernels: {conv / tot:.4f}")
+out.append(f"# share of conv_umma + conv_umma2 + block_rows + stem_fused kernels: {conv / tot:.4f}")
 open(os.path.join(P, "r01_launches_final.csv"), "w").write("\n".join(out) + "\n")
 print("\n".join(out[:10])); print(out[-1])
 # ---- full capture
@@ -43,11 +43,11 @@ for d in data:
                          g(d, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")[:5],
                          g(d, "sm__throughput.avg.pct_of_peak_sustained_elapsed")[:5], g(d, "launch__registers_per_thread"),
                          g(d, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"), g(d, "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum")]))
-    if "conv_" in name or "stem_fused" in name:
+    if "conv_" in name or "stem_fused" in name or "block_rows" in name:
         cb.append(rd + wr)
 open(os.path.join(P, "r01_ncu_full_summary.csv"), "w").write("\n".join(out) + "\n")
 print("\n".join(out[3:]))
-json.dump({"kernel": "conv_umma_kernel / conv_umma2_kernel / conv_rows_kernel / stem_fused_kernel (launches of one chunk of 128 segments x 6 heads)",
+json.dump({"kernel": "conv_umma_kernel / conv_umma2_kernel / block_rows_kernel / stem_fused_kernel (launches of one chunk of 128 segments x 6 heads)",
            "dram_bytes_per_launch_mean": sum(cb) / len(cb), "launches": len(cb),
            "source": "profiles/r01_ncu_full_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum)", "chunk": 128, "heads": 6},
           open(os.path.join(P, "r01_roofline_traffic.json"), "w"), indent=1)
