@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--max-batch", type=int, default=128, help="segments per internal pass (workspace size)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="segments in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the ingest-stage measurement")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -253,6 +254,24 @@ def run_native(args):
                "h2d_bytes_per_step": world * B * SEGMENT_BYTES, "d2h_bytes_per_step": world * B * ((H + 1) * 8 + 4)}
         del xh
 
+    # ---- ingest stage: 44.1 kHz stereo int16 -> mono 32 kHz float32, stream larger than L2 -----------
+    ingest = None
+    if rank == 0 and not args.no_ingest:
+        sr_in, ch, secs = 44100, 2, 1500
+        pcm16 = torch.randint(-20000, 20000, (sr_in * secs, ch), dtype=torch.int16, device=dev)
+        for _ in range(3):
+            y = eng.ingest(pcm16, sr_in)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            y = eng.ingest(pcm16, sr_in)
+        e1.record()
+        torch.cuda.synchronize()
+        ing_ms = e0.elapsed_time(e1) / 10
+        ing_bytes = pcm16.numel() * 2 + y.numel() * 4
+        ingest = {"ms": ing_ms, "bytes": ing_bytes, "seconds_of_audio": secs, "out_samples": int(y.numel())}
+        del pcm16, y
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -318,6 +337,13 @@ def run_native(args):
                               "compute": {"flops_model": "16 MFLOP fp32/segment (126 packed 2048-pt FFTs + window, "
                                           "power, mel, log)", "achieved_tflops": fe_tflops,
                                           "fp32_peak_tflops": fp32_peak, "frac": fe_tflops / fp32_peak}},
+        "roofline_ingest": None if ingest is None else {
+            "bound": "hbm", "achieved": ingest["bytes"] / 1e9 / (ingest["ms"] / 1e3), "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": ingest["bytes"] / 1e9 / (ingest["ms"] / 1e3) / pk["hbm_gbs"],
+            "workload": "sad_ingest: %d s of 44.1 kHz stereo int16 -> mono 32 kHz fp32 (mix, 18-tap polyphase sinc, pad); "
+                        "%.0f MB in + out per launch (> L2), 10 launches" % (ingest["seconds_of_audio"], ingest["bytes"] / 1e6),
+            "ms_per_launch": ingest["ms"],
+            "audio_seconds_per_second": ingest["seconds_of_audio"] / (ingest["ms"] / 1e3)},
         "other_ms_per_step": {"image": prof_ms[eng.PROF_IMAGE] / K, "head_merge": prof_ms[eng.PROF_HEAD] / K},
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -84,6 +84,17 @@ int sad_frontend_logmel(sad_ctx* ctx, const float* pcm_dev, int B, float* logmel
  * channels are identical copies of it (:172-173).                                                  */
 int sad_frontend_image(sad_ctx* ctx, const float* pcm_dev, int B, float* image_dev, void* stream);
 
+/* ---- ingest: replaces preprocess_waveform (inference_runner.py:144-155) after the container is parsed ----
+ * Interleaved PCM [n_frames][n_channels] on the device -> mono (mean over channels, int16 scaled by 1/32768 as
+ * torchaudio.load does) -> torchaudio.transforms.Resample(sr_in, 32000) (sinc_interp_hann, width 6, rolloff 0.99; skipped
+ * when sr_in == 32000) -> zero-padded to at least one window (128000).  sad_ingest_length gives the output length
+ * (torchaudio's float32 ceil rule); `out_dev` must hold that many floats.  Device -> device, ordered on `stream`. */
+#define SAD_PCM_S16 0
+#define SAD_PCM_F32 1
+long long sad_ingest_length(long long n_frames, int sr_in);
+int sad_ingest(sad_ctx* ctx, const void* pcm_dev, int sample_format, long long n_frames, int n_channels, int sr_in,
+               float* out_dev, void* stream);
+
 /* ---- slicing gate: replaces the silence test of slice_waveform (inference_runner.py:184-188) --- */
 /* For window w starting at w*hop: keep[w] = !(max|x| < silence_threshold).  n_windows as computed by
  * sad_slice_count.                                                                                 */

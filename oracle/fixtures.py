@@ -18,6 +18,7 @@ import math
 from collections import OrderedDict
 from typing import Dict, List
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -71,6 +72,25 @@ def synth_clip(n_samples: int, seed: int, silent_spans=()) -> torch.Tensor:
     for a, b in silent_spans:
         x[a:b] = 0.0
     return torch.clamp(x, -1, 1)
+
+
+def synth_pcm16(n_frames: int, channels: int, sr: int, seed: int) -> np.ndarray:
+    """Interleaved int16 PCM [n_frames, channels] as a WAV data chunk holds it: tones + noise, channels differ."""
+    rs = np.random.RandomState(seed)
+    t = np.arange(n_frames, dtype=np.float64) / sr
+    out = np.empty((n_frames, channels), dtype=np.int16)
+    for c in range(channels):
+        f0 = 180.0 * (c + 1) + 37.0 * (seed % 7)
+        x = 0.35 * np.sin(2 * math.pi * f0 * t) + 0.2 * np.sin(2 * math.pi * (f0 * 7.3) * t + c) + 0.1 * rs.randn(n_frames)
+        out[:, c] = np.clip(np.round(x * 32767.0), -32768, 32767).astype(np.int16)
+    return out
+
+
+INGEST_CASES = [   # (name, sample rate, channels, frames, seed)
+    ("cd_stereo", 44100, 2, 13230, 1), ("dat_mono", 48000, 1, 9600, 2), ("wide_stereo", 16000, 2, 4000, 3),
+    ("half_cd_mono", 22050, 1, 4410, 4), ("phone_3ch", 8000, 3, 1600, 5), ("native_stereo", 32000, 2, 6400, 6),
+    ("studio_mono", 96000, 1, 19201, 7), ("cd_long", 44100, 2, 198450, 8),      # 4.5 s: longer than one window
+]
 
 
 # --------------------------------------------------------------------------------------

@@ -122,6 +122,38 @@ def golden_ensemble(IR, MM, n_heads, seg_ids, tag, backbone="resnet18"):
     print(f"ensemble_{tag}: logits\n", merged.numpy(), "\nlabels", labels)
 
 
+def golden_ingest(IR):
+    """preprocess_waveform (IR:144-155), UNMODIFIED, on seeded int16 PCM.  torchaudio.load cannot decode in this image
+    (it needs torchcodec), so the loader -- and only the loader -- is replaced by what it returns for 16-bit PCM:
+    float32 [channels, frames] = int16 / 32768 and the sample rate."""
+    import torchaudio as TA
+    cfg = IR.AudioConfig(32000, 4.0, 0.0, 1e-3)                                       # IR:258
+    out = {}
+    real_load = TA.load
+    try:
+        for name, sr, ch, frames, seed in FX.INGEST_CASES:
+            pcm = FX.synth_pcm16(frames, ch, sr, seed)
+            TA.load = lambda path, _p=pcm, _sr=sr: (torch.from_numpy(_p.astype(np.float32) / 32768.0).T.contiguous(), _sr)
+            wf, sr_out = IR.preprocess_waveform(f"{name}.wav", cfg)
+            assert sr_out == 32000 and wf.dtype == torch.float32
+            y = wf.numpy()
+            n_real = int(np.ceil(np.float32(32000 * frames / sr))) if sr != 32000 else frames
+            out[f"{name}.length"] = np.array(y.shape[0], dtype=np.int64)
+            out[f"{name}.n_real"] = np.array(n_real, dtype=np.int64)
+            out[f"{name}.pcm_checksum"] = np.array(int(pcm.astype(np.int64).sum()), dtype=np.int64)
+            out[f"{name}.sum"] = np.array(float(y.astype(np.float64).sum()))
+            if n_real <= 16384:
+                out[f"{name}.head"] = y[:n_real].copy()                                # everything that is not padding
+            else:
+                out[f"{name}.head"] = y[:8192].copy()
+                out[f"{name}.tail"] = y[n_real - 8192:n_real].copy()
+                out[f"{name}.strided"] = y[::97].copy()
+    finally:
+        TA.load = real_load
+    np.savez_compressed(os.path.join(OUT, "ingest.npz"), **out)
+    print("ingest:", {k: int(v) for k, v in out.items() if k.endswith(".length")})
+
+
 def main():
     if not reference_api.available():
         raise SystemExit("the reference is not present; goldens can only be made in the build container")
@@ -129,6 +161,7 @@ def main():
     IR, MM = reference_api.load()
     os.makedirs(OUT, exist_ok=True)
     golden_slicing(IR)
+    golden_ingest(IR)
     # segments 0..5 (mixed), plus the first "pure tone" and "pure noise" draws of the stream
     golden_frontend(IR, [0, 1, 2, 3, 4, 5, 6, 13])
     golden_ensemble(IR, MM, 2, [0, 1, 2, 3, 4, 5, FX.CAL_FIRST, FX.CAL_FIRST + 1], "n2")

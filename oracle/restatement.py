@@ -94,6 +94,66 @@ def pad_to_window(wf: torch.Tensor, sr: int = SAMPLE_RATE, window_size: float = 
 
 
 # --------------------------------------------------------------------------------------
+# f1  preprocess_waveform after the container is parsed  (IR:144-155)
+#     torchaudio.load -> float32 in [-1,1) (int16 / 32768), mean over channels, transforms.Resample
+#     (torchaudio/functional/functional.py:1452-1577: sinc_interp_hann, lowpass_filter_width 6,
+#     rolloff 0.99, kernel built in float64 then cast to float32, conv1d with stride orig_freq),
+#     zero-pad to one window.
+# --------------------------------------------------------------------------------------
+RESAMPLE_WIDTH = 6
+RESAMPLE_ROLLOFF = 0.99
+
+
+def resample_kernel(orig_freq: int, new_freq: int) -> Tuple[np.ndarray, int, int, int]:
+    """(kernel [new, 2*width+orig] float32, width, orig, new) with orig/new reduced by their gcd."""
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base = min(orig, new) * RESAMPLE_ROLLOFF
+    width = math.ceil(RESAMPLE_WIDTH * orig / base)
+    idx = np.arange(-width, width + orig, dtype=np.float64)[None, :] / orig
+    # torch.arange(0, -new, -1) is int64 and `/ new_freq` yields the DEFAULT dtype: the phase -p/new is rounded to
+    # float32 before it meets the float64 index grid (exact only when new is a power of two)
+    phase = (np.arange(0, -new, -1).astype(np.float32) / np.float32(new)).astype(np.float64)
+    t = phase[:, None] + idx
+    t = t * base
+    t = np.clip(t, -RESAMPLE_WIDTH, RESAMPLE_WIDTH)
+    window = np.cos(t * math.pi / RESAMPLE_WIDTH / 2) ** 2
+    t = t * math.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        k = np.where(t == 0, 1.0, np.sin(t) / t)
+    k = k * (window * (base / orig))
+    return k.astype(np.float32), width, orig, new
+
+
+def resample_length(length: int, orig: int, new: int) -> int:
+    """target_length of _apply_sinc_resample_kernel: ceil evaluated on a float32 tensor (torch.as_tensor(float))."""
+    return int(np.ceil(np.float32(new * length / orig)))
+
+
+def resample(x: torch.Tensor, orig_freq: int, new_freq: int = SAMPLE_RATE) -> torch.Tensor:
+    """y[m*new + p] = sum_k kernel[p][k] * xpad[m*orig + k], xpad = pad(x, width, width + orig); fp32."""
+    if int(orig_freq) == int(new_freq):
+        return x
+    k, width, orig, new = resample_kernel(orig_freq, new_freq)
+    n = x.shape[0]
+    xp = F.pad(x.float()[None, None], (width, width + orig))
+    y = F.conv1d(xp, torch.from_numpy(k)[:, None, :], stride=orig)         # [1, new, frames]
+    y = y.transpose(1, 2).reshape(-1)
+    return y[:resample_length(n, orig, new)]
+
+
+def ingest(samples: np.ndarray, sr_in: int) -> torch.Tensor:
+    """Interleaved [frames, channels] int16 (or float32) -> mono float32 at 32 kHz, zero-padded to >= one window."""
+    if samples.dtype == np.int16:
+        wf = torch.from_numpy(samples.astype(np.float32) / 32768.0)
+    else:
+        wf = torch.from_numpy(np.asarray(samples, dtype=np.float32))
+    wf = wf.T.contiguous().mean(dim=0)                                      # IR:146
+    wf = resample(wf, sr_in, SAMPLE_RATE)                                   # IR:147-149
+    return pad_to_window(wf)                                                # IR:150-154
+
+
+# --------------------------------------------------------------------------------------
 # a4  waveform_to_spectrogram  (IR:157-174)
 # --------------------------------------------------------------------------------------
 def hann_window() -> torch.Tensor:

@@ -42,6 +42,8 @@ SIGNATURES = {
     "sad_launch_count": (_ll, [_vp]),
     "sad_profile_enable": (_i, [_vp, _i]),
     "sad_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_ll)]),
+    "sad_ingest_length": (_ll, [_ll, _i]),
+    "sad_ingest": (_i, [_vp, _vp, _i, _ll, _i, _i, _vp, _vp]),
     "sad_debug_conv": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "sad_debug_block": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp]),
     "sad_debug_stem": (_i, [_vp, _vp, _i, _vp, _vp]),

@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsad_b200.so")
-SOURCES = ["api.cu", "conv_umma.cu", "conv_umma2.cu", "conv_rows.cu", "block_rows.cu", "stem_fused.cu", "frontend.cu", "head.cu"]
-HEADERS = ["conv_umma.h", "frontend.h", "head.h", "stem_fused.h", "ptx.cuh", "fft2048.cuh", os.path.join("..", "..", "include", "sad_b200.h")]
+SOURCES = ["api.cu", "conv_umma.cu", "conv_umma2.cu", "conv_rows.cu", "block_rows.cu", "stem_fused.cu", "frontend.cu", "ingest.cu", "head.cu"]
+HEADERS = ["conv_umma.h", "frontend.h", "ingest.h", "head.h", "stem_fused.h", "ptx.cuh", "fft2048.cuh", os.path.join("..", "..", "include", "sad_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 

@@ -18,6 +18,7 @@
 
 #include "../../include/sad_b200.h"
 #include "conv_umma.h"
+#include "ingest.h"
 #include "frontend.h"
 #include "head.h"
 #include "stem_fused.h"
@@ -174,6 +175,11 @@ struct sad_ctx {
     float* d_window = nullptr;
     sad::MelTable* d_mel = nullptr;
     sad::ResizeTable* d_resize = nullptr;
+    // ingest (f1): tap bands of the last sample rate seen
+    int ingest_sr = 0;
+    sad::ResamplePlan ingest_plan{};
+    int* d_tap_first = nullptr;
+    float* d_tap_w = nullptr;
 
     // workspace (per chunk)
     float* d_db = nullptr;              // [Bc][128][251]
@@ -732,7 +738,7 @@ int sad_destroy(sad_ctx* c) {
     void* ptrs[] = {c->d_w_stem1, c->d_w_stem3, c->d_w1t, c->d_b1, c->d_w2t, c->d_b2, c->d_w3, c->d_b3, c->d_window,
                     c->d_mel, c->d_resize, c->d_db, c->d_segmax, c->d_musig, c->d_img, c->d_A3, c->d_stem,
                     c->d_buf[0], c->d_buf[1], c->d_buf[2], c->d_buf[3], c->d_head_logits, c->d_pcm[0], c->d_pcm[1],
-                    c->d_res_logits, c->d_res_probs, c->d_res_labels};
+                    c->d_res_logits, c->d_res_probs, c->d_res_labels, c->d_tap_first, c->d_tap_w};
     for (void* p : ptrs) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
         if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
@@ -892,6 +898,49 @@ int sad_frontend_image(sad_ctx* c, const float* pcm, int B, float* image, void* 
         CU_OK(c, sad::image_launch_f32(c->d_db, c->d_musig, c->d_resize, image + static_cast<size_t>(b0) * 512 * 512, nb, st,
                                        &c->launches));
     }
+    return SAD_OK;
+}
+
+long long sad_ingest_length(long long n_frames, int sr_in) { return sad::ingest_length(n_frames, sr_in, nullptr); }
+
+int sad_ingest(sad_ctx* c, const void* pcm, int sample_format, long long n_frames, int n_channels, int sr_in, float* out,
+               void* stream) {
+    if (!c) return SAD_EINVAL;
+    if (!out || n_frames < 0 || (n_frames > 0 && !pcm) || n_channels < 1 || n_channels > 64 || sr_in <= 0 ||
+        (sample_format != SAD_PCM_S16 && sample_format != SAD_PCM_F32))
+        return fail(c, SAD_EINVAL, "bad ingest arguments (frames %lld, channels %d, rate %d, format %d)", n_frames, n_channels,
+                    sr_in, sample_format);
+    CU_OK(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    long long n_real = 0;
+    const long long out_len = sad::ingest_length(n_frames, sr_in, &n_real);
+    if (sr_in == sad::kIngestRate) {
+        CU_OK(c, sad::ingest_launch(pcm, sample_format, n_frames, n_channels, nullptr, nullptr, nullptr, out, n_real, out_len, st,
+                                    &c->launches));
+        return SAD_OK;
+    }
+    if (sr_in != c->ingest_sr) {
+        std::vector<int> first;
+        std::vector<float> w;
+        sad::ResamplePlan plan;
+        if (!sad::build_resample_taps(sr_in, &plan, &first, &w) || sad::ingest_smem_bytes(plan) > 48 * 1024)
+            return fail(c, SAD_EINVAL, "sample rate %d: ratio to 32000 not supported (reduced rates %d:%d)", sr_in,
+                        plan.orig_f, plan.new_f);
+        CU_OK(c, cudaStreamSynchronize(st));                     // a previous ingest may still read the old tables
+        cudaFree(c->d_tap_first);
+        cudaFree(c->d_tap_w);
+        c->d_tap_first = nullptr;
+        c->d_tap_w = nullptr;
+        c->ingest_sr = 0;
+        CU_OK(c, dalloc(&c->d_tap_first, first.size()));
+        CU_OK(c, dalloc(&c->d_tap_w, w.size()));
+        CU_OK(c, cudaMemcpy(c->d_tap_first, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CU_OK(c, cudaMemcpy(c->d_tap_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+        c->ingest_plan = plan;
+        c->ingest_sr = sr_in;
+    }
+    CU_OK(c, sad::ingest_launch(pcm, sample_format, n_frames, n_channels, &c->ingest_plan, c->d_tap_first, c->d_tap_w, out,
+                                n_real, out_len, st, &c->launches));
     return SAD_OK;
 }
 

@@ -1,0 +1,336 @@
+// K0: ingest -- interleaved PCM (int16 or float32, any channel count, any integer sample rate) -> mono float32 at
+// 32 kHz, zero-padded to at least one 4-s window.  HBM-bound: every input sample is read once, every output written once.
+//
+// Replaces preprocess_waveform of the reference after the container is parsed
+// (modular/source/inference_runner.py:144-155): torchaudio.load's int16 -> float32 scaling (x / 32768), `wf.mean(dim=0)`,
+// `torchaudio.transforms.Resample(sr, 32000)` with its defaults (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99)
+// and the zero padding to one window.
+//
+// torchaudio evaluates y[m*new + p] = sum_k K[p][k] * xpad[m*orig + k] with a dense [new][2*width+orig] kernel (conv1d,
+// stride orig).  All but ~12*orig/min(orig,new) of those taps sit where the Hann window argument is clamped and are
+// below 1e-32: build_resample_taps (host) keeps the unclamped band per phase, the kernel below sums only that band.
+//
+//   Fast kernel (`phase` variant): a block owns blockDim * R consecutive outputs, blockDim a multiple of the number of
+//   phases, so a thread keeps ONE phase: its <= T taps live in registers for all R outputs.  The mono-mixed input span
+//   of the block is staged once in shared memory (coalesced reads of the interleaved PCM, each frame converted and mixed
+//   once), so per output the SM does T shared-memory reads and T FMAs and HBM sees every byte once.
+//   Fallback (`generic`): one output per thread, taps from global memory, for ratios with > 1024 phases or > 80 taps.
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "ingest.h"
+
+namespace sad {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+template <typename T>
+__device__ __forceinline__ float pcm_to_float(T v);
+template <>
+__device__ __forceinline__ float pcm_to_float<int16_t>(int16_t v) { return static_cast<float>(v) * (1.0f / 32768.0f); }
+template <>
+__device__ __forceinline__ float pcm_to_float<float>(float v) { return v; }
+
+// mean over channels in channel order, as ATen's sum-then-divide on a [C, T] tensor
+template <typename T>
+__device__ __forceinline__ float mono_mix(const T* __restrict__ pcm, long long frame, int channels) {
+    if (channels == 2) {                                   // one aligned load per stereo frame; x/2 == x*0.5 exactly
+        if constexpr (sizeof(T) == 2) {
+            const short2 v = reinterpret_cast<const short2*>(pcm)[frame];
+            return (static_cast<float>(v.x) * (1.0f / 32768.0f) + static_cast<float>(v.y) * (1.0f / 32768.0f)) * 0.5f;
+        } else {
+            const float2 v = reinterpret_cast<const float2*>(pcm)[frame];
+            return (v.x + v.y) * 0.5f;
+        }
+    }
+    const T* p = pcm + frame * channels;
+    float s = pcm_to_float<T>(p[0]);
+    for (int c = 1; c < channels; ++c) s += pcm_to_float<T>(p[c]);
+    return channels == 1 ? s : s / static_cast<float>(channels);
+}
+
+// Four consecutive mono frames f .. f+3 (f a multiple of 4; frames outside [0, n_frames) read as zero).  Mono and stereo
+// streams whose base is 16-byte aligned use one or two 8/16-byte loads: with 4 bytes per load a staging loop keeps too few
+// bytes in flight to cover HBM latency (ncu: 45% of the stall samples on the first use of the loaded value).
+template <typename T>
+__device__ __forceinline__ float4 mono4(const T* __restrict__ pcm, long long f, int channels, long long n_frames, bool aligned) {
+    if (aligned && f >= 0 && f + 3 < n_frames) {
+        if constexpr (sizeof(T) == 2) {
+            constexpr float s = 1.0f / 32768.0f;
+            if (channels == 2) {
+                const int4 v = *reinterpret_cast<const int4*>(pcm + f * 2);
+                const int r[4] = {v.x, v.y, v.z, v.w};
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    o[i] = (static_cast<float>(static_cast<short>(r[i] & 0xFFFF)) * s + static_cast<float>(static_cast<short>(r[i] >> 16)) * s) * 0.5f;
+                return make_float4(o[0], o[1], o[2], o[3]);
+            }
+            if (channels == 1) {
+                const int2 v = *reinterpret_cast<const int2*>(pcm + f);
+                return make_float4(static_cast<float>(static_cast<short>(v.x & 0xFFFF)) * s, static_cast<float>(static_cast<short>(v.x >> 16)) * s,
+                                   static_cast<float>(static_cast<short>(v.y & 0xFFFF)) * s, static_cast<float>(static_cast<short>(v.y >> 16)) * s);
+            }
+        } else {
+            if (channels == 2) {
+                const float4 a = *reinterpret_cast<const float4*>(pcm + f * 2), b = *reinterpret_cast<const float4*>(pcm + f * 2 + 4);
+                return make_float4((a.x + a.y) * 0.5f, (a.z + a.w) * 0.5f, (b.x + b.y) * 0.5f, (b.z + b.w) * 0.5f);
+            }
+            if (channels == 1) return *reinterpret_cast<const float4*>(pcm + f);
+        }
+    }
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = (f + i >= 0 && f + i < n_frames) ? mono_mix(pcm, f + i, channels) : 0.f;
+    return make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// sr_in == 32000: mix + pad only
+template <typename T>
+__global__ void __launch_bounds__(kBlock) ingest_copy_kernel(const T* __restrict__ pcm, long long n_frames, int channels,
+                                                             float* __restrict__ out, long long out_len, bool aligned) {
+    const long long j = (static_cast<long long>(blockIdx.x) * kBlock + threadIdx.x) * 4;
+    if (j >= out_len) return;
+    const float4 v = mono4(pcm, j, channels, n_frames, aligned);     // frames >= n_frames read as zero: the padding
+    if (j + 3 < out_len && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        *reinterpret_cast<float4*>(out + j) = v;
+    } else {
+        const float o[4] = {v.x, v.y, v.z, v.w};
+        for (int i = 0; i < 4 && j + i < out_len; ++i) out[j + i] = o[i];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) ingest_resample_kernel(const T* __restrict__ pcm, long long n_frames, int channels,
+                                                                 ResamplePlan plan, const int* __restrict__ tap_first,
+                                                                 const float* __restrict__ tap_w, float* __restrict__ out,
+                                                                 long long n_real, long long out_len) {
+    extern __shared__ float span[];
+    const long long j0 = static_cast<long long>(blockIdx.x) * kBlock;
+    long long j_hi = j0 + kBlock - 1;
+    if (j_hi >= n_real) j_hi = n_real - 1;
+    if (j0 < n_real) {
+        const long long m_lo = j0 / plan.new_f, m_hi = j_hi / plan.new_f;
+        const long long a_lo = m_lo * plan.orig_f - plan.width;                       // first input frame of the span
+        const int n_span = static_cast<int>((m_hi - m_lo) * plan.orig_f) + plan.taps_full;
+        for (int i = threadIdx.x; i < n_span; i += kBlock) {
+            const long long f = a_lo + i;
+            span[i] = (f >= 0 && f < n_frames) ? mono_mix(pcm, f, channels) : 0.f;     // conv1d's zero padding
+        }
+        __syncthreads();
+        const long long j = j0 + threadIdx.x;
+        if (j < n_real) {
+            const long long m = j / plan.new_f;
+            const int p = static_cast<int>(j - m * plan.new_f);
+            const float* w = tap_w + static_cast<size_t>(p) * plan.max_taps;
+            const float* x = span + (m - m_lo) * plan.orig_f + tap_first[p];
+            float acc = 0.f;
+            for (int k = 0; k < plan.max_taps; ++k) acc = fmaf(w[k], x[k], acc);
+            out[j] = acc;
+        }
+    }
+    const long long j = j0 + threadIdx.x;
+    if (j >= n_real && j < out_len) out[j] = 0.f;                                      // IR:150-154
+}
+
+
+// One phase per thread: outputs j = j0 + t + i * blockDim (blockDim % new_f == 0), i < rounds.
+template <typename In, int T>
+__global__ void __launch_bounds__(1024) ingest_resample_phase_kernel(const In* __restrict__ pcm, long long n_frames, int channels,
+                                                                      ResamplePlan plan, const int* __restrict__ tap_first,
+                                                                      const float* __restrict__ tap_w, float* __restrict__ out,
+                                                                      long long n_real, long long out_len, int rounds, bool aligned) {
+    extern __shared__ float4 span4[];
+    float* span = reinterpret_cast<float*>(span4);
+    const int nt = blockDim.x;
+    const int q = nt / plan.new_f;                                   // frames (of new_f outputs) per round
+    const long long per_block = static_cast<long long>(nt) * rounds;
+    const long long j0 = static_cast<long long>(blockIdx.x) * per_block;   // a multiple of new_f: phase 0 of frame m_base
+    const long long m_base = static_cast<long long>(blockIdx.x) * q * rounds;
+    long long j_hi = j0 + per_block - 1;
+    if (j_hi >= n_real) j_hi = n_real - 1;
+    if (j0 < n_real) {
+        // first / last input frame any output of the block touches (positions are non-decreasing in j)
+        const long long m1 = j_hi / plan.new_f;
+        const int first0 = tap_first[0];
+        const long long a_need = m_base * plan.orig_f + first0 - plan.width;
+        const long long a_lo = a_need & ~3LL;                        // staged in groups of 4 frames (vector loads)
+        const int lead = static_cast<int>(a_need - a_lo);
+        const int n_span = lead + static_cast<int>((m1 - m_base) * plan.orig_f) + tap_first[j_hi - m1 * plan.new_f] - first0 + T;
+        for (int i = threadIdx.x; i < (n_span + 3) / 4; i += nt)
+            reinterpret_cast<float4*>(span)[i] = mono4(pcm, a_lo + 4LL * i, channels, n_frames, aligned);
+        const int tm = threadIdx.x / plan.new_f;                     // 32-bit: frame of this thread inside a round
+        const int p = threadIdx.x - tm * plan.new_f;
+        float w[T];
+#pragma unroll
+        for (int k = 0; k < T; ++k) w[k] = k < plan.max_taps ? tap_w[static_cast<size_t>(p) * plan.max_taps + k] : 0.f;
+        const int off0 = lead + tm * plan.orig_f + tap_first[p] - first0;   // offset of this thread's band in round 0
+        const int rel_hi = static_cast<int>(j_hi - j0), t = static_cast<int>(threadIdx.x);
+        const int n_mine = rel_hi >= t ? (rel_hi - t) / nt + 1 : 0;   // outputs of this thread that are real samples
+        __syncthreads();
+        for (int i = 0; i < rounds; ++i) {
+            if (i >= n_mine) break;
+            const float* x = span + off0 + i * q * plan.orig_f;
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < T; ++k) acc = fmaf(w[k], x[k], acc);
+            out[j0 + threadIdx.x + static_cast<long long>(i) * nt] = acc;
+        }
+    }
+    for (int i = 0; i < rounds; ++i) {                                                 // IR:150-154
+        const long long j = j0 + threadIdx.x + static_cast<long long>(i) * nt;
+        if (j >= n_real && j < out_len) out[j] = 0.f;
+    }
+}
+
+template <typename In, int T>
+cudaError_t launch_phase(const In* pcm, long long n_frames, int channels, const ResamplePlan& plan, const int* tap_first,
+                         const float* tap_w, float* out, long long n_real, long long out_len, int threads, int rounds,
+                         size_t smem, cudaStream_t stream) {
+    const long long per_block = static_cast<long long>(threads) * rounds;
+    const unsigned grid = static_cast<unsigned>((out_len + per_block - 1) / per_block);
+    const bool aligned = (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
+    ingest_resample_phase_kernel<In, T><<<grid, threads, smem, stream>>>(pcm, n_frames, channels, plan, tap_first, tap_w, out,
+                                                                         n_real, out_len, rounds, aligned);
+    return cudaGetLastError();
+}
+
+template <typename In>
+bool try_phase(const In* pcm, long long n_frames, int channels, const ResamplePlan& plan, const int* tap_first,
+               const float* tap_w, float* out, long long n_real, long long out_len, cudaStream_t stream, cudaError_t* err) {
+    if (plan.new_f > 1024 || plan.max_taps > 80) return false;
+    const int T = plan.max_taps <= 14 ? 14 : plan.max_taps <= 18 ? 18 : plan.max_taps <= 20 ? 20 : plan.max_taps <= 24 ? 24 : plan.max_taps <= 40 ? 40 : 80;
+    int threads = plan.new_f >= 256 ? plan.new_f : plan.new_f * (256 / plan.new_f);
+    // inputs touched by threads*rounds consecutive outputs: ceil(outputs * orig / new) + T (+ slack for the band start)
+    int rounds = 8;
+    size_t smem = 0;
+    for (; rounds >= 1; rounds >>= 1) {
+        smem = (static_cast<size_t>(threads) * rounds * plan.orig_f / plan.new_f + plan.orig_f + 2 * T + 16) * sizeof(float);
+        if (smem <= 46 * 1024) break;
+    }
+    if (rounds < 1) return false;
+    switch (T) {
+        case 14: *err = launch_phase<In, 14>(pcm, n_frames, channels, plan, tap_first, tap_w, out, n_real, out_len, threads, rounds, smem, stream); break;
+        case 18: *err = launch_phase<In, 18>(pcm, n_frames, channels, plan, tap_first, tap_w, out, n_real, out_len, threads, rounds, smem, stream); break;
+        case 20: *err = launch_phase<In, 20>(pcm, n_frames, channels, plan, tap_first, tap_w, out, n_real, out_len, threads, rounds, smem, stream); break;
+        case 24: *err = launch_phase<In, 24>(pcm, n_frames, channels, plan, tap_first, tap_w, out, n_real, out_len, threads, rounds, smem, stream); break;
+        case 40: *err = launch_phase<In, 40>(pcm, n_frames, channels, plan, tap_first, tap_w, out, n_real, out_len, threads, rounds, smem, stream); break;
+        default: *err = launch_phase<In, 80>(pcm, n_frames, channels, plan, tap_first, tap_w, out, n_real, out_len, threads, rounds, smem, stream); break;
+    }
+    return true;
+}
+
+}  // namespace
+
+long long ingest_length(long long n_frames, int sr_in, long long* n_real_out) {
+    if (n_frames < 0 || sr_in <= 0) return -1;
+    long long n_real = n_frames;
+    if (sr_in != kIngestRate) {
+        long long a = sr_in, b = kIngestRate;
+        while (b) { const long long t = a % b; a = b; b = t; }
+        const long long orig = sr_in / a, nw = kIngestRate / a;
+        // torch.ceil(torch.as_tensor(new * length / orig)): the quotient is a Python float (correctly rounded double) that
+        // as_tensor stores as float32 BEFORE the ceil
+        const float q = static_cast<float>(static_cast<double>(nw * n_frames) / static_cast<double>(orig));
+        n_real = static_cast<long long>(std::ceil(q));
+    }
+    if (n_real_out) *n_real_out = n_real;
+    return n_real < kIngestWindow ? kIngestWindow : n_real;
+}
+
+// torchaudio.functional._get_sinc_resample_kernel (functional.py:1452-1538) with the band of unclamped taps only.
+bool build_resample_taps(int sr_in, ResamplePlan* plan, std::vector<int>* first, std::vector<float>* w) {
+    long long a = sr_in, b = kIngestRate;
+    while (b) { const long long t = a % b; a = b; b = t; }
+    const int orig = static_cast<int>(sr_in / a), nw = static_cast<int>(kIngestRate / a);
+    const double base = std::fmin(orig, nw) * 0.99;
+    const int width = static_cast<int>(std::ceil(6.0 * orig / base));
+    const int full = 2 * width + orig;
+    const double scale = base / orig;
+    std::vector<double> row(full);
+    std::vector<int> lo(nw), hi(nw);
+    int max_taps = 1;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            if (nw > 16384 || max_taps > 512) return false;
+            first->assign(nw, 0);
+            w->assign(static_cast<size_t>(nw) * max_taps, 0.f);
+        }
+        for (int p = 0; p < nw; ++p) {
+            // the phase term is an int64 tensor divided by an int: float32 in torch, then promoted to float64
+            const double phase = static_cast<double>(static_cast<float>(-p) / static_cast<float>(nw));
+            int f = full, l = -1;
+            for (int k = 0; k < full; ++k) {
+                double t = (phase + static_cast<double>(k - width) / orig) * base;
+                const bool clamped = t <= -6.0 || t >= 6.0;
+                t = std::fmin(6.0, std::fmax(-6.0, t));
+                const double win = std::cos(t * M_PI / 6.0 / 2.0);
+                t *= M_PI;
+                row[k] = (t == 0.0 ? 1.0 : std::sin(t) / t) * (win * win * scale);
+                if (!clamped) {
+                    if (k < f) f = k;
+                    l = k;
+                }
+            }
+            if (l < f) { f = 0; l = 0; }
+            if (pass == 0) {
+                if (l - f + 1 > max_taps) max_taps = l - f + 1;
+            } else {
+                if (f + max_taps > full) f = full - max_taps;           // keep the band inside the staged span
+                if (f < 0) f = 0;
+                (*first)[p] = f;
+                for (int k = 0; k < max_taps && f + k < full; ++k)
+                    (*w)[static_cast<size_t>(p) * max_taps + k] = static_cast<float>(row[f + k]);
+            }
+        }
+    }
+    plan->orig_f = orig;
+    plan->new_f = nw;
+    plan->width = width;
+    plan->taps_full = full;
+    plan->max_taps = max_taps;
+    return true;
+}
+
+size_t ingest_smem_bytes(const ResamplePlan& plan) {
+    const long long m_span = (kBlock - 1) / plan.new_f + 1;             // m_hi - m_lo <= this
+    return static_cast<size_t>(m_span * plan.orig_f + plan.taps_full) * sizeof(float);
+}
+
+cudaError_t ingest_launch(const void* pcm, int sample_format, long long n_frames, int channels, const ResamplePlan* plan,
+                          const int* tap_first, const float* tap_w, float* out, long long n_real, long long out_len,
+                          cudaStream_t stream, long long* launches) {
+    if (out_len <= 0) return cudaSuccess;
+    const unsigned grid = static_cast<unsigned>((out_len + kBlock - 1) / kBlock);
+    if (!plan) {
+        const unsigned grid4 = static_cast<unsigned>((out_len + 4 * kBlock - 1) / (4 * kBlock));
+        const bool aligned = (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
+        if (sample_format == 0)
+            ingest_copy_kernel<int16_t><<<grid4, kBlock, 0, stream>>>(static_cast<const int16_t*>(pcm), n_frames, channels, out, out_len, aligned);
+        else
+            ingest_copy_kernel<float><<<grid4, kBlock, 0, stream>>>(static_cast<const float*>(pcm), n_frames, channels, out, out_len, aligned);
+    } else {
+        cudaError_t e = cudaSuccess;
+        const bool fast = sample_format == 0
+            ? try_phase(static_cast<const int16_t*>(pcm), n_frames, channels, *plan, tap_first, tap_w, out, n_real, out_len, stream, &e)
+            : try_phase(static_cast<const float*>(pcm), n_frames, channels, *plan, tap_first, tap_w, out, n_real, out_len, stream, &e);
+        if (fast) {
+            if (launches) *launches += 1;
+            return e;
+        }
+        const size_t smem = ingest_smem_bytes(*plan);
+        if (sample_format == 0)
+            ingest_resample_kernel<int16_t><<<grid, kBlock, smem, stream>>>(static_cast<const int16_t*>(pcm), n_frames, channels,
+                                                                            *plan, tap_first, tap_w, out, n_real, out_len);
+        else
+            ingest_resample_kernel<float><<<grid, kBlock, smem, stream>>>(static_cast<const float*>(pcm), n_frames, channels, *plan,
+                                                                          tap_first, tap_w, out, n_real, out_len);
+    }
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace sad

@@ -187,6 +187,23 @@ class Engine:
                                                       _ptr(cl), _stream(self.device)), "sad_clip_reduce")
         return cp, cl
 
+    def ingest(self, pcm: torch.Tensor, sr_in: int) -> torch.Tensor:
+        """Interleaved PCM [frames, channels] (int16 or float32, CUDA) -> mono fp32 at 32 kHz, zero-padded to >= 128000
+        samples: mean over channels, torchaudio-default sinc resampling, padding (reference IR:144-155)."""
+        if not pcm.is_cuda or pcm.device != self.device:
+            raise _lib.SadError(f"pcm must live on {self.device} (got {pcm.device}); there is no CPU fallback")
+        if pcm.dim() != 2 or not pcm.is_contiguous() or pcm.dtype not in (torch.int16, torch.float32):
+            raise ValueError("ingest wants a contiguous [frames, channels] int16 or float32 tensor")
+        frames, ch = pcm.shape
+        n = self.lib.sad_ingest_length(frames, int(sr_in))
+        if n < 0:
+            raise ValueError(f"bad ingest arguments: frames {frames}, sample rate {sr_in}")
+        out = torch.empty(n, device=self.device, dtype=torch.float32)
+        fmt = 0 if pcm.dtype == torch.int16 else 1
+        _lib.check(self.ctx, self.lib.sad_ingest(self.ctx, _ptr(pcm), fmt, frames, ch, int(sr_in), _ptr(out),
+                                                 _stream(self.device)), "sad_ingest")
+        return out
+
     def slice_gate(self, wf: torch.Tensor, window: int, hop: int, silence_threshold: float) -> torch.Tensor:
         n = self.lib.sad_slice_count(wf.shape[0], window, hop)
         keep = torch.zeros(max(n, 0), device=self.device, dtype=torch.uint8)

@@ -215,8 +215,10 @@ def _front_engine(device) -> Engine:
     return _FRONT_ENGINE[str(dev)]
 
 
-def _read_wav(path: str) -> Tuple[torch.Tensor, int]:
-    """RIFF/WAVE PCM (8/16/24/32-bit int, 32-bit float) -> ([channels, T] fp32 in [-1,1], sample rate)."""
+def _read_wav_pcm(path: str) -> Tuple[np.ndarray, int]:
+    """RIFF/WAVE -> (interleaved samples [frames, channels], sample rate).  16-bit PCM stays int16 (the ingest kernel
+    scales by 1/32768 like torchaudio.load); 8/24/32-bit integer PCM is scaled to float32 in [-1, 1) here; 32-bit float
+    stays float32."""
     import struct
     with open(path, "rb") as f:
         data = f.read()
@@ -237,11 +239,11 @@ def _read_wav(path: str) -> Tuple[torch.Tensor, int]:
         raise ValueError(f"{path}: missing fmt/data chunk")
     tag, ch, sr, _, _, bits = fmt
     if tag == 3 and bits == 32:
-        x = np.frombuffer(raw, dtype="<f4").astype(np.float32)
+        x = np.frombuffer(raw[:len(raw) // 4 * 4], dtype="<f4").astype(np.float32)
     elif tag == 1 and bits == 16:
-        x = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+        x = np.frombuffer(raw[:len(raw) // 2 * 2], dtype="<i2").astype(np.int16)
     elif tag == 1 and bits == 32:
-        x = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+        x = np.frombuffer(raw[:len(raw) // 4 * 4], dtype="<i4").astype(np.float32) / 2147483648.0
     elif tag == 1 and bits == 24:
         b = np.frombuffer(raw[:len(raw) // 3 * 3], dtype=np.uint8).reshape(-1, 3).astype(np.int32)
         v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
@@ -250,24 +252,31 @@ def _read_wav(path: str) -> Tuple[torch.Tensor, int]:
         x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
     else:
         raise ValueError(f"{path}: unsupported WAV encoding (format tag {tag}, {bits} bits)")
-    x = x[:len(x) // ch * ch].reshape(-1, ch).T
-    return torch.from_numpy(np.ascontiguousarray(x)), int(sr)
+    return np.ascontiguousarray(x[:len(x) // ch * ch].reshape(-1, ch)), int(sr)
 
 
-def preprocess_waveform(path: str, cfg: AudioConfig):
-    """IR:144-155: load, force mono, resample to cfg.sample_rate, zero-pad to at least one window."""
-    wf, sr = _read_wav(path)                      # torchaudio.load needs torchcodec, absent in this image
-    wf = wf.mean(dim=0)
-    if sr != cfg.sample_rate:
-        import torchaudio
-        wf = torchaudio.transforms.Resample(sr, cfg.sample_rate)(wf)
-        sr = cfg.sample_rate
-    needed = int(cfg.window_size * sr)
-    if wf.shape[0] < needed:
-        temp = torch.zeros(needed)
-        temp[:wf.shape[0]] = wf
-        wf = temp
-    return wf, sr
+def _read_wav(path: str) -> Tuple[torch.Tensor, int]:
+    """What torchaudio.load returns for the file: ([channels, T] fp32 in [-1,1), sample rate)."""
+    x, sr = _read_wav_pcm(path)
+    if x.dtype == np.int16:
+        x = x.astype(np.float32) / 32768.0
+    return torch.from_numpy(np.ascontiguousarray(x.T)), sr
+
+
+def preprocess_waveform(path: str, cfg: AudioConfig, device=None):
+    """IR:144-155: load, force mono, resample to cfg.sample_rate, zero-pad to at least one window.
+
+    The container is parsed on the host (torchaudio.load needs torchcodec, absent in this image); the PCM goes to the GPU
+    as it sits in the file (int16: half the bytes of float32) and channel mix, resampling and padding run there
+    (``sad_ingest``).  The waveform is returned ON THE DEVICE -- slicing, gating and the model consume it there."""
+    if cfg.sample_rate != 32000:
+        raise NotImplementedError(f"the ingest kernel resamples to 32 kHz only (IR:258), got {cfg.sample_rate}")
+    if int(cfg.window_size * cfg.sample_rate) != SEGMENT:
+        raise NotImplementedError("ingest pads to one 4-s window of 128000 samples (IR:258); other windows have no kernels")
+    pcm, sr = _read_wav_pcm(path)
+    eng = _front_engine(device if device is not None else "cuda")
+    wf = eng.ingest(torch.from_numpy(pcm).to(eng.device), sr)
+    return wf, cfg.sample_rate
 
 
 def _check_spec_cfg(sr: int, spec_cfg: SpectrogramConfig):

@@ -125,22 +125,31 @@ def _write_wav(path, x, sr, bits=16, channels=1):
     open(path, "wb").write(hdr + raw)
 
 
-def test_preprocess_waveform(tmp_path):
-    """IR:144-155: mono mix, zero-pad short clips to one window, resample when the rate differs."""
+def test_wav_container_parsing(tmp_path):
+    """The host half of IR:144-145: the container is parsed here, the samples stay as they sit in the file."""
     rng = np.random.default_rng(0)
-    x = np.clip(0.2 * rng.standard_normal(50000), -0.99, 0.99).astype(np.float32)
-    _write_wav(tmp_path / "short.wav", x, 32000, bits=32)
-    wf, sr = IR.preprocess_waveform(str(tmp_path / "short.wav"), IR.AudioConfig())
-    assert sr == 32000 and wf.shape[0] == 128000 and torch.equal(wf[:50000], torch.from_numpy(x)) and float(wf[50000:].abs().max()) == 0
-    _write_wav(tmp_path / "stereo16.wav", x, 32000, bits=16, channels=2)
-    wf2, _ = IR.preprocess_waveform(str(tmp_path / "stereo16.wav"), IR.AudioConfig())
-    assert float((wf2[:50000] - torch.from_numpy(x)).abs().max()) < 1e-4      # 16-bit quantisation
-    _write_wav(tmp_path / "r16k.wav", x[:40000], 16000, bits=32)
-    wf3, sr3 = IR.preprocess_waveform(str(tmp_path / "r16k.wav"), IR.AudioConfig())
-    assert sr3 == 32000 and wf3.shape[0] == 128000
-    import torchaudio
-    want = torchaudio.transforms.Resample(16000, 32000)(torch.from_numpy(x[:40000]))
-    assert torch.equal(wf3[:want.shape[0]], want)
+    x = np.clip(0.2 * rng.standard_normal(5000), -0.99, 0.99).astype(np.float32)
+    _write_wav(tmp_path / "f32.wav", x, 32000, bits=32)
+    pcm, sr = IR._read_wav_pcm(str(tmp_path / "f32.wav"))
+    assert sr == 32000 and pcm.dtype == np.float32 and pcm.shape == (5000, 1) and np.array_equal(pcm[:, 0], x)
+    _write_wav(tmp_path / "stereo16.wav", x, 44100, bits=16, channels=2)
+    pcm, sr = IR._read_wav_pcm(str(tmp_path / "stereo16.wav"))
+    assert sr == 44100 and pcm.dtype == np.int16 and pcm.shape == (5000, 2)
+    np.testing.assert_array_equal(pcm[:, 0], (x * 32767).astype(np.int16))
+    wf, sr = IR._read_wav(str(tmp_path / "stereo16.wav"))            # what torchaudio.load would return
+    assert wf.shape == (2, 5000) and wf.dtype == torch.float32
+    assert torch.equal(wf[1], torch.from_numpy(pcm[:, 1].astype(np.float32) / 32768.0))
     with pytest.raises(ValueError):
         (tmp_path / "bad.wav").write_bytes(b"not a wav file at all")
-        IR.preprocess_waveform(str(tmp_path / "bad.wav"), IR.AudioConfig())
+        IR._read_wav_pcm(str(tmp_path / "bad.wav"))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_preprocess_waveform_fails_loudly_without_gpu(tmp_path):
+    """Mix / resample / pad run in sad_ingest on the device; there is no CPU fallback."""
+    from sad_b200._lib import SadError
+    _write_wav(tmp_path / "a.wav", np.zeros(100, np.float32), 16000)
+    with pytest.raises(SadError, match="no CPU fallback"):
+        IR.preprocess_waveform(str(tmp_path / "a.wav"), IR.AudioConfig())
+    with pytest.raises(NotImplementedError):
+        IR.preprocess_waveform(str(tmp_path / "a.wav"), IR.AudioConfig(sample_rate=16000))

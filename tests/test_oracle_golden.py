@@ -150,3 +150,36 @@ def test_checkpoint_layout_counts():
     f32 = {k: v for k, v in sd.items() if k.startswith("sub_models.0.") and v.dtype == torch.float32}
     assert sum(v.numel() for v in f32.values()) == 11_583_682            # params + BN running stats
     assert sum(v.numel() for k, v in f32.items() if "running" not in k) == 11_572_546
+
+
+# ---------------------------------------------------------------- ingest (IR:144-155)
+def check_ingest_against_golden(g, name, frames, y, atol):
+    """Shared with the GPU test: compare one ingested clip with what the reference's preprocess_waveform returned."""
+    n_real = int(g[f"{name}.n_real"])
+    assert y.shape[0] == int(g[f"{name}.length"]), name
+    head = g[f"{name}.head"]
+    np.testing.assert_allclose(y[:head.shape[0]], head, rtol=0, atol=atol, err_msg=name)
+    if f"{name}.tail" in g.files:
+        np.testing.assert_allclose(y[n_real - 8192:n_real], g[f"{name}.tail"], rtol=0, atol=atol, err_msg=name)
+        np.testing.assert_allclose(y[::97], g[f"{name}.strided"], rtol=0, atol=atol, err_msg=name)
+    assert not y[n_real:].any(), f"{name}: padding must be exact zeros"
+    assert abs(float(y.astype(np.float64).sum()) - float(g[f"{name}.sum"])) <= atol * y.shape[0]
+
+
+def test_ingest_matches_reference(golden_dir):
+    """Mono mix, sinc-Hann resampling to 32 kHz (torchaudio defaults, incl. its float32 phase and float32 length
+    rounding) and zero padding: BIT-identical to the reference function on the same PCM."""
+    g = _load(golden_dir, "ingest.npz")
+    for name, sr, ch, frames, seed in FX.INGEST_CASES:
+        pcm = FX.synth_pcm16(frames, ch, sr, seed)
+        assert int(pcm.astype(np.int64).sum()) == int(g[f"{name}.pcm_checksum"]), "fixture drifted"
+        y = R.ingest(pcm, sr).numpy()
+        check_ingest_against_golden(g, name, frames, y, atol=0.0)
+
+
+def test_resample_length_uses_float32_ceil():
+    # 44.1 kHz, 10 584 013 frames: exact ratio 7 680 009.43 -> float32 spacing 0.5 -> 7 680 009.5 -> ceil 7 680 010 (same
+    # as the true ceil), while 10 584 011 frames give 7 680 007.98 -> float32 7 680 008.0 -> 7 680 008
+    for frames in (10_584_013, 10_584_011, 13230, 1):
+        want = int(torch.ceil(torch.as_tensor(320 * frames / 441)).long())
+        assert R.resample_length(frames, 441, 320) == want
