@@ -915,14 +915,14 @@ int sad_ingest(sad_ctx* c, const void* pcm, int sample_format, long long n_frame
     long long n_real = 0;
     const long long out_len = sad::ingest_length(n_frames, sr_in, &n_real);
     if (sr_in == sad::kIngestRate) {
-        CU_OK(c, sad::ingest_launch(pcm, sample_format, n_frames, n_channels, nullptr, nullptr, nullptr, out, n_real, out_len, st,
+        CU_OK(c, sad::ingest_launch(pcm, sample_format, n_frames, n_channels, nullptr, sad::IngestTables{}, out, n_real, out_len, st,
                                     &c->launches));
         return SAD_OK;
     }
     if (sr_in != c->ingest_sr) {
         std::vector<int> first;
         std::vector<float> w;
-        sad::ResamplePlan plan;
+        sad::ResamplePlan plan{};
         if (!sad::build_resample_taps(sr_in, &plan, &first, &w) || sad::ingest_smem_bytes(plan) > 48 * 1024)
             return fail(c, SAD_EINVAL, "sample rate %d: ratio to 32000 not supported (reduced rates %d:%d)", sr_in,
                         plan.orig_f, plan.new_f);
@@ -939,8 +939,9 @@ int sad_ingest(sad_ctx* c, const void* pcm, int sample_format, long long n_frame
         c->ingest_plan = plan;
         c->ingest_sr = sr_in;
     }
-    CU_OK(c, sad::ingest_launch(pcm, sample_format, n_frames, n_channels, &c->ingest_plan, c->d_tap_first, c->d_tap_w, out,
-                                n_real, out_len, st, &c->launches));
+    const sad::IngestTables tb{c->d_tap_first, c->d_tap_w};
+    CU_OK(c, sad::ingest_launch(pcm, sample_format, n_frames, n_channels, &c->ingest_plan, tb, out, n_real, out_len, st,
+                                &c->launches));
     return SAD_OK;
 }
 

@@ -17,6 +17,11 @@ struct ResamplePlan {
     int max_taps;        // taps kept per phase (the band where the Hann window argument is not clamped)
 };
 
+struct IngestTables {
+    const int* tap_first;    // [new_f] first kept tap of each phase
+    const float* tap_w;      // [new_f][max_taps]
+};
+
 // Output length of the reference's preprocess_waveform (resampled length with torchaudio's float32 ceil, at least one
 // window); *n_real = samples before padding.  < 0 on bad arguments.
 long long ingest_length(long long n_frames, int sr_in, long long* n_real);
@@ -25,7 +30,7 @@ bool build_resample_taps(int sr_in, ResamplePlan* plan, std::vector<int>* first,
 size_t ingest_smem_bytes(const ResamplePlan& plan);
 // plan == nullptr: sr_in is already 32 kHz (mix + pad only).  sample_format 0 = int16, 1 = float32.
 cudaError_t ingest_launch(const void* pcm, int sample_format, long long n_frames, int channels, const ResamplePlan* plan,
-                          const int* tap_first, const float* tap_w, float* out, long long n_real, long long out_len,
-                          cudaStream_t stream, long long* launches);
+                          const IngestTables& tb, float* out, long long n_real, long long out_len, cudaStream_t stream,
+                          long long* launches);
 
 }  // namespace sad
