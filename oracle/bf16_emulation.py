@@ -48,6 +48,22 @@ def backbone_bf16(img1: torch.Tensor, sd: Dict[str, torch.Tensor], p: str, taps:
             if (q + ".conv1.weight") not in sd:
                 break
             s = stride if blk == 0 else 1
+            if (q + ".conv3.weight") in sd:      # Bottleneck: the projection is accumulated into conv3's fp32 tile (one rounding)
+                w, b = fold_bn(sd[q + ".conv1.weight"], sd, q + ".bn1")
+                o = _q(F.relu(F.conv2d(x, _q(w), b)))
+                w, b = fold_bn(sd[q + ".conv2.weight"], sd, q + ".bn2")
+                o = _q(F.relu(F.conv2d(o, _q(w), b, stride=s, padding=1)))
+                w, b = fold_bn(sd[q + ".conv3.weight"], sd, q + ".bn3")
+                o = F.conv2d(o, _q(w), b)
+                if (q + ".downsample.0.weight") in sd:
+                    wd, bd = fold_bn(sd[q + ".downsample.0.weight"], sd, q + ".downsample.1")
+                    o = o + F.conv2d(x, _q(wd), bd, stride=s)
+                else:
+                    o = o + x
+                x = _q(F.relu(o))
+                if taps is not None:
+                    taps.append((f"layer{li}.{blk}.conv3", x))
+                continue
             w, b = fold_bn(sd[q + ".conv1.weight"], sd, q + ".bn1")
             o = _q(F.relu(F.conv2d(x, _q(w), b, stride=s, padding=1)))
             if taps is not None:

@@ -96,12 +96,30 @@ INGEST_CASES = [   # (name, sample rate, channels, frames, seed)
 # --------------------------------------------------------------------------------------
 # weights
 # --------------------------------------------------------------------------------------
-DEPTHS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3)}
+DEPTHS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3),
+          "resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3)}
+BOTTLENECK = ("resnet50", "resnet101", "resnet152")
+
+
+def num_features(backbone: str) -> int:
+    return 2048 if backbone in BOTTLENECK else 512
 
 
 def _layer_plan(backbone: str = "resnet18"):
-    """(kind, name, ...) in the order timm/torchvision BasicBlock ResNets register their modules."""
+    """(kind, name, ...) in the order timm/torchvision ResNets register their modules."""
     plan = [("conv", "conv1", 64, 3, 7), ("bn", "bn1", 64)]
+    if backbone in BOTTLENECK:
+        cin = 64
+        for li, planes in enumerate((64, 128, 256, 512), start=1):
+            for b in range(DEPTHS[backbone][li - 1]):
+                p = f"layer{li}.{b}"
+                plan += [("conv", f"{p}.conv1", planes, cin, 1), ("bn", f"{p}.bn1", planes),
+                         ("conv", f"{p}.conv2", planes, planes, 3), ("bn", f"{p}.bn2", planes),
+                         ("conv", f"{p}.conv3", 4 * planes, planes, 1), ("bn", f"{p}.bn3", 4 * planes)]
+                if b == 0:
+                    plan += [("conv", f"{p}.downsample.0", 4 * planes, cin, 1), ("bn", f"{p}.downsample.1", 4 * planes)]
+                cin = 4 * planes
+        return plan
     for li, (cin, cout) in enumerate(((64, 64), (64, 128), (128, 256), (256, 512)), start=1):
         for b in range(DEPTHS[backbone][li - 1]):
             p = f"layer{li}.{b}"
@@ -137,7 +155,7 @@ def random_head_state(g: torch.Generator, backbone: str = "resnet18") -> "Ordere
             sd[f"base.{name}.weight"] = std * torch.randn(cout, cin, k, k, generator=g)
         else:
             _rand_bn(sd, f"base.{item[1]}", item[2], g)
-    _rand_linear(sd, "head.2", 512, 512, g)
+    _rand_linear(sd, "head.2", num_features(backbone), 512, g)
     _rand_bn(sd, "head.3", 512, g)
     _rand_linear(sd, "head.6", 512, 256, g)
     _rand_bn(sd, "head.7", 256, g)
@@ -169,6 +187,24 @@ def _calibrate(sd: Dict[str, torch.Tensor], images: torch.Tensor, head_index: in
                 if (q + ".conv1.weight") not in sd:
                     break
                 s = stride if b == 0 else 1
+                if (q + ".conv3.weight") in sd:                      # Bottleneck: 1x1, 3x3 (stride), 1x1
+                    o = F.conv2d(x, sd[q + ".conv1.weight"], None)
+                    stat(o, q + ".bn1", (0, 2, 3))
+                    o = F.relu(R._bn(o, sd, q + ".bn1"))
+                    o = F.conv2d(o, sd[q + ".conv2.weight"], None, stride=s, padding=1)
+                    stat(o, q + ".bn2", (0, 2, 3))
+                    o = F.relu(R._bn(o, sd, q + ".bn2"))
+                    o = F.conv2d(o, sd[q + ".conv3.weight"], None)
+                    stat(o, q + ".bn3", (0, 2, 3))
+                    o = R._bn(o, sd, q + ".bn3")
+                    if (q + ".downsample.0.weight") in sd:
+                        idn = F.conv2d(x, sd[q + ".downsample.0.weight"], None, stride=s)
+                        stat(idn, q + ".downsample.1", (0, 2, 3))
+                        idn = R._bn(idn, sd, q + ".downsample.1")
+                    else:
+                        idn = x
+                    x = F.relu(o + idn)
+                    continue
                 o = F.conv2d(x, sd[q + ".conv1.weight"], None, stride=s, padding=1)
                 stat(o, q + ".bn1", (0, 2, 3))
                 o = F.relu(R._bn(o, sd, q + ".bn1"))

@@ -167,6 +167,7 @@ def main():
     golden_ensemble(IR, MM, 2, [0, 1, 2, 3, 4, 5, FX.CAL_FIRST, FX.CAL_FIRST + 1], "n2")
     golden_ensemble(IR, MM, 5, [0, 1, FX.CAL_FIRST, FX.CAL_FIRST + 1], "n5")
     golden_ensemble(IR, MM, 2, [0, 1, FX.CAL_FIRST], "r34_n2", backbone="resnet34")
+    golden_ensemble(IR, MM, 2, [0, 1, FX.CAL_FIRST], "r50_n2", backbone="resnet50")        # SURVEY 8f4, Bottleneck
 
 
 if __name__ == "__main__":

@@ -303,15 +303,29 @@ def _basic_block(x, sd, p, stride):
     return F.relu(out + idn)
 
 
+def _bottleneck_block(x, sd, p, stride):
+    """torchvision/models/resnet.py:108-164 (v1.5: the stride sits on the 3x3 conv, as in timm's resnet50/101/152)."""
+    out = F.relu(_bn(F.conv2d(x, sd[p + ".conv1.weight"], None), sd, p + ".bn1"))
+    out = F.relu(_bn(F.conv2d(out, sd[p + ".conv2.weight"], None, stride=stride, padding=1), sd, p + ".bn2"))
+    out = _bn(F.conv2d(out, sd[p + ".conv3.weight"], None), sd, p + ".bn3")
+    if (p + ".downsample.0.weight") in sd:
+        idn = _bn(F.conv2d(x, sd[p + ".downsample.0.weight"], None, stride=stride), sd, p + ".downsample.1")
+    else:
+        idn = x
+    return F.relu(out + idn)
+
+
 def backbone_features(x: torch.Tensor, sd: Dict[str, torch.Tensor], p: str) -> torch.Tensor:
-    """timm ResNet.forward_features for a BasicBlock ResNet (resnet18/34): [B,3,512,512] -> [B,512,16,16] (IR:50)."""
+    """timm ResNet.forward_features (IR:50): [B,3,512,512] -> [B,512,16,16] for the BasicBlock nets (resnet18/34),
+    [B,2048,16,16] for the Bottleneck nets (resnet50/101/152; a block with a conv3 is a Bottleneck)."""
     x = F.conv2d(x, sd[p + "conv1.weight"], None, stride=2, padding=3)
     x = F.relu(_bn(x, sd, p + "bn1"))
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
     for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
         b = 0
         while f"{p}layer{li}.{b}.conv1.weight" in sd:          # 2 blocks per layer for resnet18; 3,4,6,3 for resnet34
-            x = _basic_block(x, sd, f"{p}layer{li}.{b}", stride if b == 0 else 1)
+            blk = _bottleneck_block if f"{p}layer{li}.{b}.conv3.weight" in sd else _basic_block
+            x = blk(x, sd, f"{p}layer{li}.{b}", stride if b == 0 else 1)
             b += 1
     return x
 

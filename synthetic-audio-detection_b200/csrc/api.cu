@@ -33,13 +33,31 @@ using bf16 = __nv_bfloat16;
 struct ConvSpec {
     std::string conv, bn;
     int cin, cout, k, stride, pad, hin, hout;
+    bool ds = false;   // the 1x1 projection of a block's identity branch
 };
 
-std::vector<ConvSpec> build_convs(const int depths[4]) {
+std::vector<ConvSpec> build_convs(const int depths[4], bool bottleneck) {
     std::vector<ConvSpec> v;
     v.push_back({"base.conv1", "base.bn1", 3, 64, 7, 2, 3, 512, 256});
     const int chans[4] = {64, 128, 256, 512};
     int cin = 64, h = 128;
+    if (bottleneck) {   // timm / torchvision Bottleneck (v1.5: stride on the 3x3): 1x1 -> 3x3/s -> 1x1 (x4), projection in block 0
+        for (int li = 0; li < 4; ++li) {
+            const int planes = chans[li], cout = 4 * planes;
+            for (int b = 0; b < depths[li]; ++b) {
+                const std::string p = "base.layer" + std::to_string(li + 1) + "." + std::to_string(b);
+                const int stride = (b == 0 && li > 0) ? 2 : 1;
+                const int hin = h, hout = h / stride;
+                v.push_back({p + ".conv1", p + ".bn1", cin, planes, 1, 1, 0, hin, hin});
+                v.push_back({p + ".conv2", p + ".bn2", planes, planes, 3, stride, 1, hin, hout});
+                v.push_back({p + ".conv3", p + ".bn3", planes, cout, 1, 1, 0, hout, hout});
+                if (b == 0) v.push_back({p + ".downsample.0", p + ".downsample.1", cin, cout, 1, stride, 0, hin, hout, true});
+                h = hout;
+                cin = cout;
+            }
+        }
+        return v;   // 53 entries for resnet50, 104 for resnet101, 155 for resnet152
+    }
     for (int li = 0; li < 4; ++li) {
         const int cout = chans[li];
         for (int b = 0; b < depths[li]; ++b) {
@@ -49,7 +67,7 @@ std::vector<ConvSpec> build_convs(const int depths[4]) {
             const int hin = h, hout = h / stride;
             v.push_back({p + ".conv1", p + ".bn1", c0, cout, 3, stride, 1, hin, hout});
             v.push_back({p + ".conv2", p + ".bn2", cout, cout, 3, 1, 1, hout, hout});
-            if (b == 0 && li > 0) v.push_back({p + ".downsample.0", p + ".downsample.1", c0, cout, 1, 2, 0, hin, hout});
+            if (b == 0 && li > 0) v.push_back({p + ".downsample.0", p + ".downsample.1", c0, cout, 1, 2, 0, hin, hout, true});
             h = hout;
         }
         cin = cout;
@@ -62,7 +80,7 @@ struct TensorSpec {
     long long numel;
 };
 
-std::vector<TensorSpec> build_tensor_list(const std::vector<ConvSpec>& convs) {
+std::vector<TensorSpec> build_tensor_list(const std::vector<ConvSpec>& convs, int features) {
     std::vector<TensorSpec> t;
     auto bn = [&](const std::string& p, int c) {
         t.push_back({p + ".weight", c});
@@ -74,7 +92,7 @@ std::vector<TensorSpec> build_tensor_list(const std::vector<ConvSpec>& convs) {
         t.push_back({c.conv + ".weight", 1LL * c.cout * c.cin * c.k * c.k});
         bn(c.bn, c.cout);
     }
-    t.push_back({"head.2.weight", 512 * 512});
+    t.push_back({"head.2.weight", 512LL * features});
     t.push_back({"head.2.bias", 512});
     bn("head.3", 512);
     t.push_back({"head.6.weight", 256 * 512});
@@ -89,23 +107,37 @@ std::vector<TensorSpec> build_tensor_list(const std::vector<ConvSpec>& convs) {
 struct NetSpec {
     std::string name;
     int depths[4];
+    bool bottleneck = false;
+    int features = 512;   // channels of the trunk output = inputs of the head's first Linear
     std::vector<ConvSpec> convs;
     std::vector<TensorSpec> tensors;
 };
 
 const NetSpec* get_net(const char* name) {
-    static const NetSpec nets[2] = {
-        [] { NetSpec n; n.name = "resnet18"; const int d[4] = {2, 2, 2, 2}; memcpy(n.depths, d, sizeof(d));
-             n.convs = build_convs(n.depths); n.tensors = build_tensor_list(n.convs); return n; }(),
-        [] { NetSpec n; n.name = "resnet34"; const int d[4] = {3, 4, 6, 3}; memcpy(n.depths, d, sizeof(d));
-             n.convs = build_convs(n.depths); n.tensors = build_tensor_list(n.convs); return n; }()};
+    auto make = [](const char* nm, int d0, int d1, int d2, int d3, bool bottleneck) {
+        NetSpec n;
+        n.name = nm;
+        const int d[4] = {d0, d1, d2, d3};
+        memcpy(n.depths, d, sizeof(d));
+        n.bottleneck = bottleneck;
+        n.features = bottleneck ? 2048 : 512;
+        n.convs = build_convs(n.depths, bottleneck);
+        n.tensors = build_tensor_list(n.convs, n.features);
+        return n;
+    };
+    static const NetSpec nets[5] = {make("resnet18", 2, 2, 2, 2, false), make("resnet34", 3, 4, 6, 3, false),
+                                    make("resnet50", 3, 4, 6, 3, true), make("resnet101", 3, 4, 23, 3, true),
+                                    make("resnet152", 3, 8, 36, 3, true)};
     if (!name) return &nets[0];
     for (const auto& n : nets)
         if (n.name == name) return &n;
     return nullptr;
 }
 
-constexpr int kMaxConvs = SAD_PROF_CONV_SLOTS;
+constexpr int kMaxConvs = 160;   // resnet152: 155
+// profile slots 0..SAD_PROF_CONV_SLOTS-1 are per conv; deeper convs (Bottleneck nets) share the last slot
+inline int prof_slot(int conv) { return conv < SAD_PROF_CONV_SLOTS ? conv : SAD_PROF_CONV_SLOTS - 1; }
+
 
 // launch plan over the activation buffers: X (block input / output), Y, T (mid), D (downsample branch)
 enum Buf { BX = 0, BY = 1, BT = 2, BD = 3, BNONE = -1 };
@@ -115,11 +147,30 @@ struct Step {
     int relu;
     int fused_ds;   // conv index of a downsample branch accumulated into this conv (reads buffer X), or -1
     int block2;     // >= 0: this step is a whole BasicBlock (block_rows.cu): `conv` = conv1, `block2` = conv2, res == in
+    int ds_in = BX; // buffer the fused downsample branch reads (the block input)
 };
 // Walk the blocks: `cur` holds the block input, conv1 -> T, conv2 (+identity or downsample branch) -> the other of X/Y.
 std::vector<Step> build_plan(const NetSpec& net, bool fuse_ds, bool fuse_block, int* final_buf) {
     std::vector<Step> p;
     int ci = 1, cur = BX;
+    if (net.bottleneck) {   // conv1 -> T, conv2 -> D (free: the projection is always folded into conv3), conv3 (+id / +proj) -> other
+        for (int li = 0; li < 4; ++li)
+            for (int b = 0; b < net.depths[li]; ++b) {
+                const int other = cur == BX ? BY : BX;
+                p.push_back({ci + 0, cur, BNONE, BT, 1, -1, -1, cur});
+                p.push_back({ci + 1, BT, BNONE, BD, 1, -1, -1, cur});
+                if (b == 0) {
+                    p.push_back({ci + 2, BD, BNONE, other, 1, ci + 3, -1, cur});
+                    ci += 4;
+                } else {
+                    p.push_back({ci + 2, BD, cur, other, 1, -1, -1, cur});
+                    ci += 3;
+                }
+                cur = other;
+            }
+        *final_buf = cur;
+        return p;
+    }
     for (int li = 0; li < 4; ++li) {
         for (int b = 0; b < net.depths[li]; ++b) {
             const int other = cur == BX ? BY : BX;
@@ -135,7 +186,7 @@ std::vector<Step> build_plan(const NetSpec& net, bool fuse_ds, bool fuse_block, 
                 p.push_back({ci + 1, BT, cur, other, 1, -1, -1});
                 ci += 2;
             } else if (fuse_ds) {
-                p.push_back({ci + 1, BT, BNONE, other, 1, ci + 2, -1});   // conv2 + downsample(cur) accumulated in one tile
+                p.push_back({ci + 1, BT, BNONE, other, 1, ci + 2, -1, cur});   // conv2 + downsample(cur) accumulated in one tile
                 ci += 3;
             } else {
                 p.push_back({ci + 2, cur, BNONE, BD, 0, -1, -1});
@@ -431,13 +482,14 @@ bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const b
         L->bias2 = c->d_bias[block2];
     }
     if (fused_ds >= 0) {
-        const ConvSpec& d = c->net->convs[fused_ds];         // 1x1, stride 2, pad 0, same Cout and output size as `s`
-        if (d.cout != s.cout || d.hout != s.hout || d.k != 1 || d.stride != 2) {
+        const ConvSpec& d = c->net->convs[fused_ds];         // 1x1, stride 1 or 2, pad 0, same Cout and output size as `s`
+        if (d.cout != s.cout || d.hout != s.hout || d.k != 1 || !d.ds || (d.stride != 1 && d.stride != 2)) {
             snprintf(c->err, sizeof(c->err), "conv %d cannot absorb downsample %d", ci, fused_ds);
             return false;
         }
-        if (!sad::encode_act_map(&L->a2_map, ds_in, d.cin, d.hin / 2, d.hin / 2, n_imgs, 2LL * d.cin, 2LL * d.hin * d.cin,
-                                 1LL * d.hin * d.hin * d.cin, Wo, rows, c->err, sizeof(c->err)))
+        const long long ss = d.stride;                       // view of the block input at the output's sampling grid
+        if (!sad::encode_act_map(&L->a2_map, ds_in, d.cin, d.hin / d.stride, d.hin / d.stride, n_imgs, ss * d.cin,
+                                 ss * d.hin * d.cin, 1LL * d.hin * d.hin * d.cin, Wo, rows, c->err, sizeof(c->err)))
             return false;
         if (!sad::encode_weight_map(&L->b2_map, c->d_w[fused_ds], d.cin, 1LL * c->H * d.cout, n_tile, c->err, sizeof(c->err)))
             return false;
@@ -667,11 +719,11 @@ int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const c
         CU_OK(c, dalloc(&c->d_bias[i], H * s.cout));
     }
     CU_OK(c, dalloc(&c->d_bias[0], H * 64));
-    for (int i = 1; i + 1 < n_convs; ++i)       // conv2 (index i) directly followed by its block's downsample conv
-        if (net->convs[i + 1].k == 1) CU_OK(c, dalloc(&c->d_bias_fused[i], H * net->convs[i].cout));
+    for (int i = 1; i + 1 < n_convs; ++i)       // a conv directly followed by its block's projection conv may absorb it
+        if (net->convs[i + 1].ds) CU_OK(c, dalloc(&c->d_bias_fused[i], H * net->convs[i].cout));
     CU_OK(c, dalloc(&c->d_w_stem1, H * 64 * 64));
     CU_OK(c, dalloc(&c->d_w_stem3, H * 64 * 192));
-    CU_OK(c, dalloc(&c->d_w1t, H * 512 * 512));
+    CU_OK(c, dalloc(&c->d_w1t, H * net->features * 512));
     CU_OK(c, dalloc(&c->d_b1, H * 512));
     CU_OK(c, dalloc(&c->d_w2t, H * 512 * 256));
     CU_OK(c, dalloc(&c->d_b2, H * 256));
@@ -698,8 +750,17 @@ int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const c
     CU_OK(c, dalloc(&c->d_segmax, Bc));
     CU_OK(c, dalloc(&c->d_musig, Bc * 2));
     CU_OK(c, dalloc(&c->d_img, Bc * 512 * 512));
-    for (int i = 0; i < 3; ++i) CU_OK(c, dalloc(&c->d_buf[i], HB * 128 * 128 * 64));
-    CU_OK(c, dalloc(&c->d_buf[BD], HB * 64 * 64 * 128));
+    long long act = 128LL * 128 * 64, act_d = 64LL * 64 * 128;   // elements per head-image: block in/out + mid; projection branch
+    if (net->bottleneck) {
+        for (int i = 1; i < n_convs; ++i) {
+            const long long e = 1LL * net->convs[i].cout * net->convs[i].hout * net->convs[i].hout;
+            if (e > act) act = e;
+        }
+        act_d = act;                                              // D holds conv2's output for Bottleneck nets
+        if (!c->fuse_ds) return fail(c, SAD_EINVAL, "SAD_FUSE_DS=0 is not available for Bottleneck backbones");
+    }
+    for (int i = 0; i < 3; ++i) CU_OK(c, dalloc(&c->d_buf[i], HB * act));
+    CU_OK(c, dalloc(&c->d_buf[BD], HB * act_d));
     CU_OK(c, dalloc(&c->d_head_logits, HB * 2));
 
     // launch plan bound to the workspace
@@ -713,7 +774,7 @@ int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const c
     for (size_t i = 0; i < c->plan.size(); ++i) {
         const Step& s = c->plan[i];
         if (!make_launch(c, &c->plan_launch[i], s.conv, c->d_buf[s.in], s.res == BNONE ? nullptr : c->d_buf[s.res],
-                         c->d_buf[s.out], HB, s.relu, s.fused_ds, c->d_buf[s.fused_ds >= 0 ? c->plan[i - 1].in : BX], s.block2))
+                         c->d_buf[s.out], HB, s.relu, s.fused_ds, c->d_buf[s.ds_in], s.block2))
             return SAD_ECUDA;
     }
 
@@ -827,8 +888,8 @@ int sad_load_weights(sad_ctx* c, int head, const float* const* T, int n_tensors)
                                 cudaMemcpyHostToDevice));
         }
     }
-    for (int ci = 1; ci + 1 < n_convs; ++ci) {   // conv2 of the first block of layers 2-4 absorbs the downsample branch (ci+1)
-        if (net.convs[ci + 1].k != 1) continue;
+    for (int ci = 1; ci + 1 < n_convs; ++ci) {   // the conv before a block's projection conv (ci+1) absorbs it: summed shifts
+        if (!net.convs[ci + 1].ds) continue;
         std::vector<float> fb(host_bias[ci].size());
         for (size_t o = 0; o < fb.size(); ++o) fb[o] = host_bias[ci][o] + host_bias[ci + 1][o];
         CU_OK(c, cudaMemcpy(c->d_bias_fused[ci] + static_cast<size_t>(head) * fb.size(), fb.data(), fb.size() * sizeof(float),
@@ -839,12 +900,14 @@ int sad_load_weights(sad_ctx* c, int head, const float* const* T, int n_tensors)
         const float *w1 = T[ti], *b1 = T[ti + 1];
         bn_scale_shift(T[ti + 2], T[ti + 3], T[ti + 4], T[ti + 5], 512, s, t);
         ti += 6;
-        std::vector<float> wt(512 * 512), bb(512);
+        const int F = net.features;
+        std::vector<float> wt(static_cast<size_t>(F) * 512), bb(512);
         for (int o = 0; o < 512; ++o) {
             bb[o] = static_cast<float>(static_cast<double>(b1[o]) * s[o] + t[o]);
-            for (int i = 0; i < 512; ++i) wt[i * 512 + o] = static_cast<float>(static_cast<double>(w1[o * 512 + i]) * s[o]);
+            for (int i = 0; i < F; ++i)
+                wt[static_cast<size_t>(i) * 512 + o] = static_cast<float>(static_cast<double>(w1[static_cast<size_t>(o) * F + i]) * s[o]);
         }
-        CU_OK(c, cudaMemcpy(c->d_w1t + static_cast<size_t>(head) * 512 * 512, wt.data(), wt.size() * sizeof(float),
+        CU_OK(c, cudaMemcpy(c->d_w1t + static_cast<size_t>(head) * F * 512, wt.data(), wt.size() * sizeof(float),
                             cudaMemcpyHostToDevice));
         CU_OK(c, cudaMemcpy(c->d_b1 + head * 512, bb.data(), 512 * sizeof(float), cudaMemcpyHostToDevice));
         const float *w2 = T[ti], *b2 = T[ti + 1];
@@ -1185,7 +1248,7 @@ long long sad_debug_read(sad_ctx* c, int which, void* dst, long long capacity, v
     switch (which) {
         case 0: src = c->d_img; bytes = B * 512 * 512 * 2; break;
         case 1: src = c->d_stem; bytes = 0; break;
-        case 2: src = c->d_buf[c->final_buf]; bytes = H * B * 16 * 16 * 512 * 2; break;
+        case 2: src = c->d_buf[c->final_buf]; bytes = H * B * 16 * 16 * c->net->features * 2; break;
         case 3: src = c->d_head_logits; bytes = H * B * 2 * 4; break;
         case 4: src = c->d_db; bytes = B * 128 * 251 * 4; break;
         default: return fail(c, SAD_EINVAL, "unknown buffer id %d", which);
@@ -1243,13 +1306,13 @@ int run_chunk(sad_ctx* c, const float* pcm, const float* x_nchw, int B, float th
         sad::ConvLaunch L = c->plan_launch[i];
         set_batch(&L, B, H);
         const bool block = c->plan[i].block2 >= 0;           // a fused block is timed under its conv2 slot
-        ProfScope ps(c, block ? c->plan[i].block2 : c->plan[i].conv, st);
+        ProfScope ps(c, prof_slot(block ? c->plan[i].block2 : c->plan[i].conv), st);
         CU_OK(c, launch_conv(c, c->plan[i].conv, L, H, st, block));
         c->launches += 1;
     }
     sad::HeadWeights hw{c->d_w1t, c->d_b1, c->d_w2t, c->d_b2, c->d_w3, c->d_b3};
     ProfScope ps(c, SAD_PROF_HEAD, st);
-    CU_OK(c, sad::head_mlp_launch(c->d_buf[c->final_buf], hw, B, H, c->d_head_logits, st, &c->launches));
+    CU_OK(c, sad::head_mlp_launch(c->d_buf[c->final_buf], hw, B, H, c->net->features, c->d_head_logits, st, &c->launches));
     CU_OK(c, sad::merge_decide_launch(c->d_head_logits, B, H, thr, logits, probs, labels, st, &c->launches));
     return SAD_OK;
 }

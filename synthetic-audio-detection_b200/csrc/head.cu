@@ -16,12 +16,18 @@ namespace {
 
 // grid (B, H), 256 threads: one CTA per (segment, head) -- the kernel is latency-bound, so it wants many CTAs
 // (measured: batching 4 or 8 segments per CTA to re-use the 1.5 MB of L2-resident weights was 2x slower).
-// feats: NHWC bf16 [H*B][256 px][512]; weights transposed [in][out] fp32 so a thread reads 4 consecutive outputs with
+// feats: NHWC bf16 [H*B][256 px][F]; weights transposed [in][out] fp32 so a thread reads 4 consecutive outputs with
 // one 16-byte load; the K dimension is split over thread groups and reduced through shared memory.
+// F = trunk feature width: 512 (resnet18/34) or 2048 (Bottleneck nets).
+template <int F>
 __global__ void __launch_bounds__(256) head_mlp_kernel(const __nv_bfloat16* __restrict__ feats, HeadWeights hw, int B,
                                                        float* __restrict__ head_logits) {
-    __shared__ __align__(16) float part[4][512];   // partial sums (pool: 4 pixel groups; layers: K splits)
-    __shared__ __align__(16) float pooled[512];
+    constexpr int kC8 = F / 8;            // 16-byte channel groups per pixel
+    constexpr int kG = 256 / kC8;         // pixel groups in the pooling phase (4 for F=512, 1 for F=2048)
+    constexpr int kPx = 256 / kG;         // pixels per group
+    __shared__ __align__(16) float part_flat[2048];   // partial sums (pool: kG pixel groups x F; layers: K splits x 512)
+    float (*part)[512] = reinterpret_cast<float (*)[512]>(part_flat);
+    __shared__ __align__(16) float pooled[F];
     __shared__ __align__(16) float h1[512];
     __shared__ __align__(16) float h2[256];
     __shared__ float red[2][8];
@@ -30,12 +36,12 @@ __global__ void __launch_bounds__(256) head_mlp_kernel(const __nv_bfloat16* __re
 
     // ---- global average pool over the 16x16 map: thread = (pixel group g of 64 px, 8 channels c8)
     {
-        const int c8 = t & 63, g = t >> 6;
-        const uint4* f = reinterpret_cast<const uint4*>(feats + n * 256 * 512) + c8;   // 64 uint4 per pixel
+        const int c8 = t % kC8, g = t / kC8;
+        const uint4* f = reinterpret_cast<const uint4*>(feats + n * 256 * F) + c8;   // kC8 uint4 per pixel
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
-        for (int p = 0; p < 64; ++p) {
-            const uint4 v = __ldg(f + (g * 64 + p) * 64);
+        for (int p = 0; p < kPx; ++p) {
+            const uint4 v = __ldg(f + (g * kPx + p) * kC8);
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -44,20 +50,24 @@ __global__ void __launch_bounds__(256) head_mlp_kernel(const __nv_bfloat16* __re
             }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) part[g][c8 * 8 + j] = acc[j];
+        for (int j = 0; j < 8; ++j) part_flat[g * F + c8 * 8 + j] = acc[j];
     }
     __syncthreads();
-    for (int c = t; c < 512; c += 256)
-        pooled[c] = (((part[0][c] + part[1][c]) + part[2][c]) + part[3][c]) * (1.0f / 256.0f);
+    for (int c = t; c < F; c += 256) {
+        float sum = part_flat[c];
+#pragma unroll
+        for (int g = 1; g < kG; ++g) sum += part_flat[g * F + c];
+        pooled[c] = sum * (1.0f / 256.0f);
+    }
     __syncthreads();
 
-    // ---- Linear(512,512)+BN folded, ReLU: thread = (K half kh, 4 outputs o4)
+    // ---- Linear(F,512)+BN folded, ReLU: thread = (K half kh, 4 outputs o4)
     {
         const int o4 = t & 127, kh = t >> 7;
-        const float4* w1 = reinterpret_cast<const float4*>(hw.w1t + static_cast<size_t>(h) * 512 * 512) + o4;
+        const float4* w1 = reinterpret_cast<const float4*>(hw.w1t + static_cast<size_t>(h) * F * 512) + o4;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
-        for (int i = kh * 256; i < kh * 256 + 256; ++i) {
+        for (int i = kh * (F / 2); i < (kh + 1) * (F / 2); ++i) {
             const float x = pooled[i];
             const float4 w = __ldg(w1 + i * 128);
             a.x = fmaf(x, w.x, a.x); a.y = fmaf(x, w.y, a.y); a.z = fmaf(x, w.z, a.z); a.w = fmaf(x, w.w, a.w);
@@ -189,9 +199,11 @@ __global__ void __launch_bounds__(256) clip_reduce_kernel(const float* __restric
 
 }  // namespace
 
-cudaError_t head_mlp_launch(const __nv_bfloat16* feats, const HeadWeights& hw, int B, int H, float* head_logits,
+cudaError_t head_mlp_launch(const __nv_bfloat16* feats, const HeadWeights& hw, int B, int H, int features, float* head_logits,
                             cudaStream_t stream, long long* launches) {
-    head_mlp_kernel<<<dim3(B, H), 256, 0, stream>>>(feats, hw, B, head_logits);
+    if (features == 512) head_mlp_kernel<512><<<dim3(B, H), 256, 0, stream>>>(feats, hw, B, head_logits);
+    else if (features == 2048) head_mlp_kernel<2048><<<dim3(B, H), 256, 0, stream>>>(feats, hw, B, head_logits);
+    else return cudaErrorInvalidValue;
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

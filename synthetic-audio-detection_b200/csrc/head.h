@@ -6,7 +6,7 @@
 namespace sad {
 
 // Folded head MLP of all H heads (device pointers, fp32):
-//   w1t [H][512 in][512 out], b1 [H][512]   Linear(512,512)+BatchNorm1d(512) folded, transposed for coalescing
+//   w1t [H][F in][512 out],   b1 [H][512]   Linear(F,512)+BatchNorm1d(512) folded, transposed for coalescing; F = 512 | 2048
 //   w2t [H][512 in][256 out], b2 [H][256]   Linear(512,256)+BatchNorm1d(256) folded
 //   w3  [H][2][256],          b3 [H][2]     Linear(256,2): row 0 = Real, row 1 = Synthetic
 struct HeadWeights {
@@ -18,7 +18,7 @@ struct HeadWeights {
     const float* b3;
 };
 
-cudaError_t head_mlp_launch(const __nv_bfloat16* feats, const HeadWeights& hw, int B, int H, float* head_logits,
+cudaError_t head_mlp_launch(const __nv_bfloat16* feats, const HeadWeights& hw, int B, int H, int features, float* head_logits,
                             cudaStream_t stream, long long* launches);
 cudaError_t merge_decide_launch(const float* head_logits, int B, int N, float thr, float* logits, float* probs, int* labels,
                                 cudaStream_t stream, long long* launches);

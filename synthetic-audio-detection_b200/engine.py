@@ -55,7 +55,7 @@ class Engine:
         self.ctx = C.c_void_p(0)
         self.backbone = backbone
         if self.lib.sad_backbone_weight_count(backbone.encode()) < 0:
-            raise NotImplementedError(f"backbone {backbone!r} has no sm_100a kernels (BasicBlock ResNets only: resnet18, resnet34)")
+            raise NotImplementedError(f"backbone {backbone!r} has no sm_100a kernels (resnet18/34/50/101/152 only)")
         torch.cuda.init()
         code = self.lib.sad_create_ex(C.byref(self.ctx), idx, self.n_heads, self.max_batch, backbone.encode())
         if code != 0:

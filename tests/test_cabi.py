@@ -41,7 +41,13 @@ def test_weight_manifest_matches_checkpoint_layout():
     got34 = [(lib.sad_backbone_weight_name(b"resnet34", i).decode(), lib.sad_backbone_weight_numel(b"resnet34", i))
              for i in range(lib.sad_backbone_weight_count(b"resnet34"))]
     assert got34 == want34 and len(got34) == 36 * 5 + 14
-    assert lib.sad_backbone_weight_count(b"resnet50") == -1
+    for name, n_convs in (("resnet50", 53), ("resnet101", 104), ("resnet152", 155)):        # Bottleneck nets
+        sdb = FX.merged_state_dict(1, calibrate=False, backbone=name)
+        wantb = [(k[len("sub_models.0."):], v.numel()) for k, v in sdb.items() if not k.endswith("num_batches_tracked")]
+        gotb = [(lib.sad_backbone_weight_name(name.encode(), i).decode(), lib.sad_backbone_weight_numel(name.encode(), i))
+                for i in range(lib.sad_backbone_weight_count(name.encode()))]
+        assert gotb == wantb and len(gotb) == n_convs * 5 + 14, name
+    assert lib.sad_backbone_weight_count(b"resnext50_32x4d") == -1
 
 
 def test_slice_count_is_len_of_python_range():

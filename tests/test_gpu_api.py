@@ -145,4 +145,25 @@ def test_resnet34_backbone_through_the_python_api(tmp_path, capsys):
     print("resnet34: max |logit diff| images", (got.cpu() - want).abs().max().item(), "pcm", (lo.cpu() - want).abs().max().item())
     assert (got.cpu() - want).abs().max() <= LOGIT_TOL and (lo.cpu() - want).abs().max() <= LOGIT_TOL
     with pytest.raises(NotImplementedError):
-        IR.BinaryClassifier("resnet50")
+        IR.BinaryClassifier("resnext50_32x4d")
+
+
+def test_resnet50_backbone_through_the_python_api(tmp_path, capsys):
+    """--model-name resnet50 (MM:101, IR:77): the Bottleneck family runs on the same kernels; BinaryClassifier's first
+    Linear takes the trunk's 2048 features (IR:36-37)."""
+    sd = G.merged_sd(2, "resnet50")
+    p = tmp_path / "m50.pth"
+    torch.save({"state_dict": sd, "metadata": {"class_names": FX.class_names(2)}}, str(p))
+    model, meta = IR.load_merged_model(str(p), torch.device("cuda"), backbone_name="resnet50")
+    assert "dummy output shape: torch.Size([2, 3])" in capsys.readouterr().out
+    assert model.sub_models[0].base.num_features == 2048 and model.sub_models[0].head[2].in_features == 2048
+    x = FX.synth_segments(2, first=70)
+    img3 = R.waveform_to_image(x).unsqueeze(1).repeat(1, 3, 1, 1).contiguous()
+    want = R.ensemble_forward(img3, sd)
+    got = model(img3.cuda())
+    lo, _, _ = model.forward_pcm(x.cuda(), 0.5)
+    f = model.sub_models[1].base.forward_features(img3[:1].cuda())
+    assert f.shape == (1, 2048, 16, 16)
+    print("resnet50: max |logit diff| images", (got.cpu() - want).abs().max().item(), "pcm", (lo.cpu() - want).abs().max().item())
+    tol50 = 6e-2                        # bf16 activations through 53 convs: see tests/test_gpu_ensemble.py (r50_n2)
+    assert (got.cpu() - want).abs().max() <= tol50 and (lo.cpu() - want).abs().max() <= tol50

@@ -132,3 +132,54 @@ def test_fused_block_switch_gives_identical_logits(monkeypatch):
         eng.close()
     assert torch.equal(outs[0], outs[1])
     assert launches[0] - launches[1] == 2 * 2                      # two chunks (4 + 1 segments) x two blocks
+
+
+R50_LAYERS = [l for l in FX._layer_plan("resnet50") if l[0] == "conv"]
+R50_BNS = [l for l in FX._layer_plan("resnet50") if l[0] == "bn"]
+
+
+def _geometry50(idx):
+    name, cout, cin, k = R50_LAYERS[idx][1], R50_LAYERS[idx][2], R50_LAYERS[idx][3], R50_LAYERS[idx][4]
+    li = int(name.split(".")[0][-1])
+    hout = {1: 128, 2: 64, 3: 32, 4: 16}[li]
+    first = name.split(".")[1] == "0" and li > 1
+    stride = 2 if first and (name.endswith("conv2") or "downsample" in name) else 1
+    hin = hout * 2 if first and (name.endswith("conv1") or stride == 2) else hout
+    if first and name.endswith("conv1"):
+        hout = hin                                   # the 1x1 entry conv of a stage still runs at the input resolution
+    return name, cin, cout, k, stride, hin, hout
+
+
+# one of every Bottleneck conv shape: 1x1 64->64 / 64->256 / 256->64 @128, the layer2 entry block (1x1 256->128 @128,
+# 3x3/2, 1x1 128->512), a layer3 1x1 1024->256, the layer4 3x3/2 and the widest 1x1 (512->2048, 2048->512), and the
+# conv3 + identity of non-entry blocks at every width (7: 64->256 @128, 17: 128->512 @64, 30: 256->1024 @32, 52: 512->2048 @16)
+@pytest.mark.parametrize("idx", [1, 2, 3, 4, 5, 7, 11, 12, 13, 14, 17, 28, 30, 44, 45, 47, 48, 52])
+def test_bottleneck_conv_layer(idx):
+    name, cin, cout, k, stride, hin, hout = _geometry50(idx)
+    head = 1
+    sd = G.merged_sd(2, "resnet50")
+    p = f"sub_models.{head}.base."
+    w, b = E.fold_bn(sd[p + name + ".weight"], sd, p + R50_BNS[idx][1])
+    wq = w.to(torch.bfloat16).float()
+    B = 2
+    g = torch.Generator().manual_seed(700 + idx)
+    x = torch.randn(B, cin, hin, hin, generator=g).to(torch.bfloat16)
+    use_res = name.endswith("conv3") and name.split(".")[1] != "0"
+    res = torch.randn(B, cout, hout, hout, generator=g).to(torch.bfloat16) if use_res else None
+    relu = "downsample" not in name
+    want = F.conv2d(x.float(), wq, b, stride=stride, padding=k // 2)
+    if use_res:
+        want = want + res.float()
+    if relu:
+        want = F.relu(want)
+    e = G.engine(2, backbone="resnet50")
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    r_nhwc = res.permute(0, 2, 3, 1).contiguous().cuda() if use_res else None
+    got = e.debug_conv(head, idx, x_nhwc, r_nhwc, (B, hout, hout, cout), relu)
+    torch.cuda.synchronize()
+    got = got.float().cpu().permute(0, 3, 1, 2)
+    err = (got - want).abs()
+    tol = 2.0 ** -7 * want.abs() + 2e-2
+    bad = (err > tol).float().mean().item()
+    print(f"resnet50 {name} [{cin}->{cout} k{k} s{stride} @{hin}]: max abs err {err.max():.4f}, frac out of tol {bad:.2e}")
+    assert bad == 0.0

@@ -58,7 +58,7 @@ def test_call_order_and_argument_errors():
     ctx = C.c_void_p(0)
     assert lib.sad_create(C.byref(ctx), 99, 2, 4) == _lib.SAD_ENODEVICE
     assert lib.sad_create(C.byref(ctx), 0, 40, 4) == _lib.SAD_EINVAL
-    assert lib.sad_create_ex(C.byref(ctx), 0, 2, 4, b"resnet50") == _lib.SAD_EINVAL
+    assert lib.sad_create_ex(C.byref(ctx), 0, 2, 4, b"resnext50_32x4d") == _lib.SAD_EINVAL
     # a filterbank with weight above FFT bin 768 is rejected (the kernel only forms power for bins <= 768)
     fb = torch.zeros(1025, 128)
     fb[900, 5] = 1.0

@@ -17,25 +17,38 @@ pytestmark = pytest.mark.gpu
 LOGIT_TOL = 2e-2
 
 
-@pytest.mark.parametrize("tag", ["n2", "n5", "r34_n2"])
+@pytest.mark.parametrize("tag", ["n2", "n5", "r34_n2", "r50_n2"])
 def test_fused_forward_vs_reference_golden(tag):
-    """r34_n2: the resnet34 backbone through the same kernels (depths 3-4-6-3)."""
+    """r34_n2: the resnet34 backbone through the same kernels (depths 3-4-6-3); r50_n2: resnet50, the
+    Bottleneck member (1x1 - 3x3 - 1x1, 2048 features, projection folded into conv3)."""
     g = G.golden(f"ensemble_{tag}.npz")
     n = int(g["n_heads"])
-    e = G.engine(n, backbone="resnet34" if tag.startswith("r34") else "resnet18")
+    e = G.engine(n, backbone={"r34": "resnet34", "r50": "resnet50"}.get(tag[:3], "resnet18"))
     x = G.segs(g["seg_ids"]).cuda()
     logits, probs, labels = e.forward_pcm(x, 0.5)
     torch.cuda.synchronize()
     d = np.abs(logits.cpu().numpy() - g["merged_logits"])
     print(f"{tag}: max |logit diff| vs reference golden {d.max():.4f}")
-    assert d.max() <= LOGIT_TOL
-    np.testing.assert_allclose(probs.cpu().numpy(), g["probs"], rtol=0, atol=LOGIT_TOL / 4 + 1e-6)
+    tol = LOGIT_TOL
+    if tag.startswith("r50"):
+        # 53 convolutions with bf16 activations: the CPU emulation of the SAME data path (bf16 weights / activations, fp32
+        # accumulation) sits 0.047 from the fp32 reference on these segments, so the 2e-2 bound of the resnet18 ensemble
+        # does not transfer; the implementation is held to the emulation instead (1e-2) and to 6e-2 against fp32.
+        from oracle import bf16_emulation as E
+        with torch.no_grad():
+            emu = E.ensemble_bf16(R.waveform_to_image(x.cpu()).unsqueeze(1), G.merged_sd(n, "resnet50")).numpy()
+        de = np.abs(logits.cpu().numpy() - emu)
+        print(f"{tag}: max |logit diff| vs bf16 emulation {de.max():.4f}; emulation vs fp32 {np.abs(emu - g['merged_logits']).max():.4f}")
+        assert de.max() <= 1e-2
+        tol = 6e-2
+    assert d.max() <= tol
+    np.testing.assert_allclose(probs.cpu().numpy(), g["probs"], rtol=0, atol=tol / 4 + 1e-6)
     names = [str(s) for s in g["class_names"]]
     mine = [R.label_name(int(l), n, names[:-1], names[-1]) for l in labels.cpu().numpy()]
     want = [str(s) for s in g["labels"]]
     margin = G.decision_margin(g["merged_logits"])
     for a, b, m in zip(mine, want, margin):
-        assert a == b or m <= LOGIT_TOL, (a, b, m)
+        assert a == b or m <= tol, (a, b, m)
 
 
 def test_images_entry_matches_fused_entry():

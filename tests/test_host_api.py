@@ -72,7 +72,11 @@ def test_no_cpu_fallback():
     with pytest.raises(NotImplementedError):
         IR.waveform_to_spectrogram(torch.zeros(128000), 16000, IR.SpectrogramConfig())
     with pytest.raises(NotImplementedError):
-        IR.BinaryClassifier("resnet50")
+        IR.BinaryClassifier("resnext50_32x4d")
+    b50 = IR.BinaryClassifier("resnet50")                    # Bottleneck nets build their parameter holders offline
+    assert b50.base.num_features == 2048 and b50.head[2].in_features == 2048
+    assert b50.base.layer3[5].conv3.weight.shape == (1024, 256, 1, 1)
+    assert list(b50.state_dict().keys())[:2] == ["base.conv1.weight", "base.bn1.weight"]
 
 
 def test_interpret_rule():

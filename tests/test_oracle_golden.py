@@ -110,11 +110,11 @@ def test_fp32_reference_noise_floor_vs_fp64(golden_dir):
 
 
 # ---------------------------------------------------------------- ensemble (IR:28-73, 194-214, 328-334)
-@pytest.mark.parametrize("tag", ["n2", "n5", "r34_n2"])
+@pytest.mark.parametrize("tag", ["n2", "n5", "r34_n2", "r50_n2"])
 def test_ensemble_matches_reference(golden_dir, tag):
     g = _load(golden_dir, f"ensemble_{tag}.npz")
     n = int(g["n_heads"])
-    sd = FX.merged_state_dict(n, backbone="resnet34" if tag.startswith("r34") else "resnet18")
+    sd = FX.merged_state_dict(n, backbone={"r34": "resnet34", "r50": "resnet50"}.get(tag[:3], "resnet18"))
     assert R.head_indices(sd) == list(range(n))
     x = torch.cat([FX.synth_segments(1, first=int(i)) for i in g["seg_ids"]])
     img = R.waveform_to_image(x).unsqueeze(1).repeat(1, 3, 1, 1)
