@@ -19,7 +19,9 @@
 //   needed.  The FIR runs on CUDA cores at one shared-memory load per FMA: 18 LDS per output with 2-way conflicts caps the
 //   kernel near 2.4 TB/s.  A variant with two adjacent outputs per thread on 8-byte window loads (4x fewer LDS wavefronts)
 //   measured the SAME 1.8 TB/s at 96 registers / 2 blocks per SM -- stage -> sync -> compute leaves HBM idle while a block
-//   computes -- so it was dropped; a persistent, double-buffered (cp.async.bulk) version is the next step.
+//   computes -- so it was dropped; hoisting four staging loads ahead of their first use (more registers, fewer resident
+//   blocks) was 20% SLOWER: occupancy, not per-thread latency, carries this kernel.  A persistent, double-buffered
+//   (cp.async.bulk) version is the next step.
 #include <cmath>
 #include <cstdint>
 #include <vector>
