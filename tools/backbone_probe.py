@@ -27,3 +27,26 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
 convs = [l for l in FX._layer_plan(name) if l[0] == "conv"]
 print(f"{name}: {H} heads, batch {B} (chunks of {chunk}): {ms:.1f} ms/step = {B / (ms / 1e3):.0f} segments/s, {len(convs)} convs per head")
+
+# per-conv profile (slots >= 39 are aggregated for deep nets)
+eng.profile_enable(True)
+eng.forward_pcm(x, 0.5)
+torch.cuda.synchronize()
+ms_k, n_k = eng.profile_read()
+eng.profile_enable(False)
+plan = [l for l in FX._layer_plan(name) if l[0] == "conv"]
+hw = {1: 128, 2: 64, 3: 32, 4: 16}
+rows = []
+for i, (_, nm, cout, cin, k) in enumerate(plan):
+    if i == 0 or i >= 39:
+        continue
+    li = int(nm.split(".")[0][-1])
+    first = nm.split(".")[1] == "0" and li > 1
+    hout = hw[li] * (2 if (first and nm.endswith("conv1") and name in FX.BOTTLENECK) else 1)
+    fl = 2.0 * hout * hout * cout * cin * k * k * H * B / 1e12
+    rows.append((i, nm, cin, cout, k, hout, ms_k[i], fl / (ms_k[i] / 1e3) if ms_k[i] > 0 else 0.0))
+tot = sum(ms_k[:40])
+print(f"conv time {tot:.1f} ms of {ms:.1f}; front end {ms_k[eng.PROF_FRONTEND]:.1f}, image {ms_k[eng.PROF_IMAGE]:.1f}, head {ms_k[eng.PROF_HEAD]:.1f}; slot 39+ {ms_k[39]:.1f}")
+for r in rows:
+    if r[6] > 0:
+        print("  conv %2d %-22s %4d->%4d k%d @%3d  %6.2f ms  %6.0f TFLOP/s" % r)
