@@ -233,19 +233,6 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(cta_addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d)
-                 : "memory");
-}
-// Fire-and-forget 16-byte store into a peer CTA's shared memory; its 16 bytes are counted (complete_tx) on the mbarrier
-// `cluster_bar` of the SAME peer, so the writer needs neither a fence nor a release-arrive after a burst of stores.
-__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
-                                            uint32_t cluster_bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(
-                     cluster_addr),
-                 "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_bar)
-                 : "memory");
-}
 // Bulk copy own shared memory -> a peer CTA's shared memory (DMA engine; bytes counted on the peer's mbarrier).
 __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
                                                   uint32_t cluster_bar) {
@@ -254,26 +241,8 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uin
                  "r"(src_cta_addr), "r"(bytes), "r"(cluster_bar)
                  : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_all() {   // generic <-> async proxy, every state space (incl. peer smem)
-    asm volatile("fence.proxy.async;\n" ::: "memory");
-}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // release at cluster scope on a (peer) barrier
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
-    uint32_t spins = 0;
-    for (;;) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred P;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, P;\n\t}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (ok) break;
-        if (++spins > (1u << 26)) { __trap(); }
-    }
 }
 
 // Byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a SWIZZLE_128B tile whose rows are 128 B
