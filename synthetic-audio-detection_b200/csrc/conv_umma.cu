@@ -177,14 +177,15 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(tiles + stage * C::kStageBytes);
                     const uint64_t bdesc = umma_desc_sw128(a_addr + MT * kABytes);
+                    // k outer, m inner: consecutive instructions accumulate into DIFFERENT tiles (+0.7 % on layer2 over
+                    // issuing each tile's four k-steps back to back)
 #pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        const uint64_t adesc = umma_desc_sw128(a_addr + m * kABytes);
+                    for (int k = 0; k < kBlockK / 16; ++k) {
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k) {
+                        for (int m = 0; m < MT; ++m)
                             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in >>4 units
-                            umma_bf16(d_tmem + m * N_TILE, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
-                        }
+                            umma_bf16(d_tmem + m * N_TILE, umma_desc_sw128(a_addr + m * kABytes) + 2 * k, bdesc + 2 * k, idesc,
+                                      (ks | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);   // frees this smem stage once the MMAs have read it
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
