@@ -252,6 +252,8 @@ struct sad_ctx {
     int two_cta = 1;                    // 1: N=256 layers (layers 3-4) run on CTA pairs (conv_umma2.cu, cta_group::2); 2: N=128 too (slower)
     int fuse_ds = 1;                    // fold each block's 1x1/s2 downsample conv into conv2 as extra K blocks
     int fuse_block = 1;                 // layer1 BasicBlocks run as one launch on CTA pairs (block_rows.cu)
+    int tr128 = 1;                      // N = 128 layers as weights x pixels with 256-column UMMA (conv_umma.cu, TR)
+    bf16* d_ident128 = nullptr;         // [H][128][128] identity: the residual of a TR conv enters as two extra K blocks
     float* d_bias_fused[kMaxConvs] = {nullptr}; // [H][Cout] = bias(conv2) + bias(downsample) for the conv2 that absorbs it
     int rows_mode = 1;                  // layer1 row-stationary kernel (conv_rows.cu): 0 = use the generic kernel instead
 
@@ -386,6 +388,23 @@ bool encode_pix_map(CUtensorMap* m, const void* base, int C, long long pixels, i
     return encode_weight_map(m, base, C, pixels, box_px, err, errlen);   // same 2-D {inner, rows} geometry
 }
 
+bool encode_pix_map32(CUtensorMap* m, const void* base, int C, long long pixels, char* err, int errlen) {
+    EncodeTiledFn fn = encode_fn(err, errlen);
+    if (!fn) return false;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(pixels)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(C) * 2};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(err, errlen, "cuTensorMapEncodeTiled(pixels C=%d box 32x32) -> CUresult %d", C, static_cast<int>(r));
+        return false;
+    }
+    return true;
+}
+
 bool encode_weight_map(CUtensorMap* m, const void* base, long long K, long long rows, int box_rows, char* err,
                        int errlen) {
     EncodeTiledFn fn = encode_fn(err, errlen);
@@ -452,6 +471,7 @@ bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const b
     const long long pixels = n_imgs * s.hout * s.hout;
     if (!sad::encode_pix_map(&L->out_map, out, s.cout, pixels, 32, c->err, sizeof(c->err))) return false;
     if (!sad::encode_pix_map(&L->res_map, res ? res : out, s.cout, pixels, 128, c->err, sizeof(c->err))) return false;
+    if (!sad::encode_pix_map32(&L->out32_map, out, s.cout, pixels, c->err, sizeof(c->err))) return false;
     L->bias = c->d_bias[ci];
     L->residual = res;
     L->out = out;
@@ -476,6 +496,19 @@ bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const b
         L->bh_map = L->b_map;
     }
     L->b2h_map = L->bh_map;
+    L->transposed = (c->tr128 && n_tile == 128 && s.cout == 128 && (Wo * Wo / 128) % 2 == 0 && block2 < 0) ? 1 : 0;
+    if (L->transposed && res && fused_ds < 0) {
+        // identity branch through the tensor core: out += x * I as Cout/64 extra K blocks (the transposed epilogue has
+        // channels on lanes and no cheap way to read a pixel-major residual); fp32 accumulation, exact for bf16 x
+        if (!sad::encode_act_map(&L->a2_map, res, s.cout, Wo, Wo, n_imgs, s.cout, 1LL * Wo * s.cout, 1LL * Wo * Wo * s.cout, Wo,
+                                 rows, c->err, sizeof(c->err)))
+            return false;
+        if (!sad::encode_weight_map(&L->b2_map, c->d_ident128, 128, 1LL * c->H * 128, n_tile, c->err, sizeof(c->err)) ||
+            !sad::encode_weight_map(&L->b2h_map, c->d_ident128, 128, 1LL * c->H * 128, n_tile / 2, c->err, sizeof(c->err)))
+            return false;
+        L->k2_blocks = s.cout / 64;
+        L->residual = nullptr;
+    }
     if (block2 >= 0) {
         if (!sad::encode_weight_map(&L->b2_map, c->d_w[block2], K, 1LL * c->H * s.cout, n_tile, c->err, sizeof(c->err)))
             return false;
@@ -707,6 +740,7 @@ int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const c
     if (const char* e = getenv("SAD_CONV_ROWS")) c->rows_mode = atoi(e);
     if (const char* e = getenv("SAD_FUSE_DS")) c->fuse_ds = atoi(e);
     if (const char* e = getenv("SAD_FUSE_BLOCK")) c->fuse_block = atoi(e);
+    if (const char* e = getenv("SAD_TR128")) c->tr128 = atoi(e);
     if (const char* e = getenv("SAD_2CTA")) c->two_cta = atoi(e);
     *out = c;   // returned even on failure so the caller can read sad_last_error, then sad_destroy
     CU_OK(c, cudaSetDevice(device));
@@ -762,6 +796,13 @@ int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const c
     for (int i = 0; i < 3; ++i) CU_OK(c, dalloc(&c->d_buf[i], HB * act));
     CU_OK(c, dalloc(&c->d_buf[BD], HB * act_d));
     CU_OK(c, dalloc(&c->d_head_logits, HB * 2));
+    {
+        std::vector<bf16> id(static_cast<size_t>(H) * 128 * 128, to_bf16(0.0));
+        for (long long h = 0; h < H; ++h)
+            for (int i = 0; i < 128; ++i) id[(h * 128 + i) * 128 + i] = to_bf16(1.0);
+        CU_OK(c, dalloc(&c->d_ident128, id.size()));
+        CU_OK(c, cudaMemcpy(c->d_ident128, id.data(), id.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+    }
 
     // launch plan bound to the workspace
     memset(&c->stem1, 0, sizeof(c->stem1));
@@ -799,7 +840,7 @@ int sad_destroy(sad_ctx* c) {
     void* ptrs[] = {c->d_w_stem1, c->d_w_stem3, c->d_w1t, c->d_b1, c->d_w2t, c->d_b2, c->d_w3, c->d_b3, c->d_window,
                     c->d_mel, c->d_resize, c->d_db, c->d_segmax, c->d_musig, c->d_img, c->d_A3, c->d_stem,
                     c->d_buf[0], c->d_buf[1], c->d_buf[2], c->d_buf[3], c->d_head_logits, c->d_pcm[0], c->d_pcm[1],
-                    c->d_res_logits, c->d_res_probs, c->d_res_labels, c->d_tap_first, c->d_tap_w};
+                    c->d_res_logits, c->d_res_probs, c->d_res_labels, c->d_tap_first, c->d_tap_w, c->d_ident128};
     for (void* p : ptrs) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
         if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);

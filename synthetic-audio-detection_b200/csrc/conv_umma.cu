@@ -60,9 +60,21 @@ struct Cfg {
     static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
-template <int N_TILE, int MT>
+// TR ("transposed product", N_TILE = 128, MT = 2 only): the same stages -- two 128-pixel tiles and one 128-channel weight
+// tile per K block -- are multiplied the other way round: A = weights (M = 128 output channels), B = the 256 pixels
+// (N = 256), D[channel][pixel].  A tensor instruction then does 128x256x16 instead of 128x128x16; this part runs a
+// 128-column instruction at ~61 % of the tensor peak whatever feeds it (on layer2 neither halving the operand reads with
+// CTA pairs nor removing 8/9 of the A fetches moved it) and a 256-column one at ~76 %: +19 % on layer2.
+// The price is an epilogue with channels on TMEM lanes: each thread owns one channel and 32 pixels per tcgen05.ld,
+// writes 2-byte elements into a [32 px][32 ch] staging tile (a warp's 32 lanes fill 64 contiguous bytes per pixel) and
+// the tile leaves by TMA.  A residual has no cheap place there (2-byte global loads: 848 instead of 1 023 TFLOP/s; TMA
+// tiles one chunk ahead: 680), so api.cu feeds the identity branch through the tensor core instead: two extra K blocks
+// of the block input against an identity weight tile (the mechanism of the folded downsample conv), and `residual` is
+// null for this kernel.
+template <int N_TILE, int MT, bool TR = false>
 __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_kernel(const __grid_constant__ ConvLaunch p) {
     using C = Cfg<N_TILE, MT>;
+    static_assert(!TR || (N_TILE == 128 && MT == 2), "transposed product: 128 channels x 256 pixels");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* tiles = smem;
@@ -81,6 +93,7 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
         tma_prefetch_desc(&p.b_map);
         tma_prefetch_desc(&p.out_map);
+        if (TR) tma_prefetch_desc(&p.out32_map);
         if (p.k2_blocks) {
             tma_prefetch_desc(&p.a2_map);
             tma_prefetch_desc(&p.b2_map);
@@ -163,7 +176,7 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
     } else if (warp == 1) {
         // ------------------------------------------------------------------ UMMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, N_TILE);
+            constexpr uint32_t idesc = TR ? umma_idesc_bf16(128, 256) : umma_idesc_bf16(kBlockM, N_TILE);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -177,6 +190,13 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(tiles + stage * C::kStageBytes);
                     const uint64_t bdesc = umma_desc_sw128(a_addr + MT * kABytes);
+                    if constexpr (TR) {
+                        // weights [128 co][64 k] as A, the two pixel tiles (contiguous: [256 px][64 k]) as B
+                        const uint64_t pdesc = umma_desc_sw128(a_addr);
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16(d_tmem, bdesc + 2 * k, pdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+                    } else {
                     // k outer, m inner: consecutive instructions accumulate into DIFFERENT tiles (+0.7 % on layer2 over
                     // issuing each tile's four k-steps back to back)
 #pragma unroll
@@ -186,6 +206,7 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
                             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in >>4 units
                             umma_bf16(d_tmem + m * N_TILE, umma_desc_sw128(a_addr + m * kABytes) + 2 * k, bdesc + 2 * k, idesc,
                                       (ks | k) != 0 ? 1u : 0u);
+                    }
                     }
                     umma_commit(&empty_bar[stage]);   // frees this smem stage once the MMAs have read it
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -198,6 +219,56 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
         // Per 64-channel block: TMEM -> registers -> +bias (+residual) -> ReLU -> bf16 -> swizzled smem staging ->
         // one TMA store of [32 px][64 ch] per warp (fully coalesced; a lane writing its own 128-byte pixel row
         // straight to global touches 32 lines per store instruction and made the epilogue the bottleneck).
+        if constexpr (TR) {
+            // ---- transposed product: TMEM lanes are output channels, columns are the 256 pixels of the two M tiles
+            const int quarter = warp & 3;             // channels 32*quarter .. +31 of this 128-channel tile
+            uint8_t* my_out = out_sm + quarter * C::kOutBufs * 4096;       // [32 px][32 ch] bf16 = 2 KB per buffer, no swizzle
+            int it = 0;
+            uint32_t nstore = 0;
+            for (int tile = blockIdx.x; tile < total_groups; tile += gridDim.x, ++it) {
+                const int head = tile / tiles_per_head;
+                int r = tile - head * tiles_per_head;
+                const int n_t = r % p.n_tiles;
+                r /= p.n_tiles;
+                const int m_t = (r % m_groups) * MT;
+                const int img = r / m_groups;
+                const int acc = it % C::kAccBufs;
+                const int co = n_t * N_TILE + quarter * 32 + lane;                 // this thread's output channel
+                const float bias = __ldg(p.bias + head * p.Cout + co);
+                const long long pix_base = (static_cast<long long>(head) * p.imgs_per_head + img) * (p.m_tiles_per_img * kBlockM) +
+                                           static_cast<long long>(m_t) * kBlockM;  // 256 consecutive pixels
+                mbar_wait(&tmem_full[acc], (it / C::kAccBufs) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::kAccCols;
+#pragma unroll 1
+                for (int j = 0; j < MT * kBlockM / 32; ++j, ++nstore) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + 32 * j, v);
+                    tmem_ld_wait();
+                    if (j == MT * kBlockM / 32 - 1) {  // accumulators are in registers: hand TMEM back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    }
+                    if (lane == 0) tma_store_wait_read<C::kOutBufs - 1>();
+                    __syncwarp();
+                    uint8_t* stage = my_out + (nstore % C::kOutBufs) * 4096;
+#pragma unroll
+                    for (int px = 0; px < 32; ++px) {
+                        float f = __uint_as_float(v[px]) + bias;
+                        if (p.relu) f = fmaxf(f, 0.f);
+                        *reinterpret_cast<uint16_t*>(stage + px * 64 + lane * 2) = __bfloat16_as_ushort(__float2bfloat16_rn(f));
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&p.out32_map, stage, n_t * N_TILE + quarter * 32, static_cast<int>(pix_base) + 32 * j);
+                        tma_store_commit();
+                    }
+                }
+            }
+            if (lane == 0) tma_store_wait<0>();
+        } else {
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;          // pixel inside the 128-pixel tile
         const int egroup = (warp - 2) >> 2;           // which epilogue warp group (0 unless kEpiGroups == 2)
@@ -284,6 +355,7 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
             }
         }
         if (lane == 0) tma_store_wait<0>();
+        }
     }
 
     tc_fence_before();
@@ -291,14 +363,14 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
     if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
-template <int N_TILE, int MT>
+template <int N_TILE, int MT, bool TR = false>
 cudaError_t launch_t(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
     using C = Cfg<N_TILE, MT>;
-    cudaError_t e = ensure_dynamic_smem<conv_umma_kernel<N_TILE, MT>>(C::kSmemBytes);
+    cudaError_t e = ensure_dynamic_smem<conv_umma_kernel<N_TILE, MT, TR>>(C::kSmemBytes);
     if (e != cudaSuccess) return e;
     const int groups = p.total_tiles / MT;
     int grid = groups < num_sms ? groups : num_sms;
-    conv_umma_kernel<N_TILE, MT><<<grid, C::kThreadsCfg, C::kSmemBytes, stream>>>(p);
+    conv_umma_kernel<N_TILE, MT, TR><<<grid, C::kThreadsCfg, C::kSmemBytes, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -309,7 +381,10 @@ int conv_n_tile(int Cout) { return Cout >= 256 ? 256 : Cout; }
 cudaError_t conv_umma_launch(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
     switch (p.n_tile) {
         case 64: return launch_t<64, 1>(p, num_sms, stream);
-        case 128: return (p.m_tiles_per_img % 2 == 0) ? launch_t<128, 2>(p, num_sms, stream) : launch_t<128, 1>(p, num_sms, stream);
+        case 128:
+            if (p.m_tiles_per_img % 2 != 0) return launch_t<128, 1>(p, num_sms, stream);
+            if (p.transposed && !p.residual) return launch_t<128, 2, true>(p, num_sms, stream);   // 256-column UMMA
+            return launch_t<128, 2>(p, num_sms, stream);
         case 256: return (p.m_tiles_per_img % 2 == 0 && getenv("SAD_MT256") && atoi(getenv("SAD_MT256")) == 2)
                              ? launch_t<256, 2>(p, num_sms, stream) : launch_t<256, 1>(p, num_sms, stream);
         default: return cudaErrorInvalidValue;

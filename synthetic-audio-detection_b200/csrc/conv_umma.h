@@ -10,6 +10,7 @@ struct alignas(64) ConvLaunch {
     CUtensorMap a_map[4];   // input views; stride 1 uses [0] (all four equal), stride 2 uses parity (py*2+px)
     CUtensorMap b_map;      // packed weights [heads*Cout][taps*Cin] bf16, K-major
     CUtensorMap out_map;    // output viewed as {Cout, pixels}: box {64 ch, 32 px}, SWIZZLE_128B (TMA store)
+    CUtensorMap out32_map;  // output as {Cout, pixels} with box {32 ch, 32 px}, no swizzle (transposed-product epilogue)
     CUtensorMap res_map;    // residual viewed as {Cout, pixels}: box {64 ch, 128 px} (TMA load); valid iff residual
     CUtensorMap a2_map;     // optional second input (fused 1x1/stride-2 downsample branch): parity-(0,0) view of the block input
     CUtensorMap b2_map;     // its weights [heads*Cout][Cin2] bf16; the extra k2_blocks K-steps accumulate into the same tile
@@ -30,6 +31,7 @@ struct alignas(64) ConvLaunch {
     int relu;
     int shared_input;       // 1: every head reads image `img` (stem); 0: head h reads image h*B+img
     int k2_blocks;          // Cin2 / 64 extra K blocks read through a2_map / b2_map (0 = none)
+    int transposed;         // N = 128 layers: multiply as weights x pixels (conv_umma.cu, TR); needs residual == nullptr
 };
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per (kernel, device).  The kernel is a
@@ -64,6 +66,8 @@ bool encode_act_map(CUtensorMap* m, const void* base, int C, int W, int H, long 
                     long long sn, int box_w, int box_h, char* err, int errlen);
 // 2-D pixel-major view of an NHWC tensor: dims {C, pixels}; box {64 ch, box_px}.
 bool encode_pix_map(CUtensorMap* m, const void* base, int C, long long pixels, int box_px, char* err, int errlen);
+// The same view with box {32 ch, 32 px} and no swizzle (dense 64-byte rows in shared memory).
+bool encode_pix_map32(CUtensorMap* m, const void* base, int C, long long pixels, char* err, int errlen);
 // 2-D weight view: dims {K, rows}; box {64, box_rows}.
 bool encode_weight_map(CUtensorMap* m, const void* base, long long K, long long rows, int box_rows, char* err,
                        int errlen);
