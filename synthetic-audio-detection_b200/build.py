@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsad_b200.so")
 SOURCES = ["api.cu", "conv_umma.cu", "conv_umma2.cu", "conv_rows.cu", "block_rows.cu", "stem_fused.cu", "frontend.cu", "ingest.cu", "head.cu"]
-HEADERS = ["conv_umma.h", "frontend.h", "ingest.h", "head.h", "stem_fused.h", "ptx.cuh", "fft2048.cuh", os.path.join("..", "..", "include", "sad_b200.h")]
+HEADERS = ["conv_umma.h", "frontend.h", "ingest.h", "ingest_taps.h", "head.h", "stem_fused.h", "ptx.cuh", "fft2048.cuh", os.path.join("..", "..", "include", "sad_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 
@@ -39,6 +39,15 @@ def build_fft_host_check() -> str:
     if not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out) or \
             os.path.getmtime(os.path.join(CSRC, "fft2048.cuh")) > os.path.getmtime(out):
         subprocess.run(["g++", "-O2", "-std=c++17", "-o", out, src], check=True)
+    return out
+
+
+def build_ingest_host_check() -> str:
+    """CPU test helper for the ingest stage's host arithmetic (see csrc/ingest_host_check.cpp)."""
+    out = os.path.join(HERE, "ingest_host_check.bin")
+    srcs = [os.path.join(CSRC, "ingest_host_check.cpp"), os.path.join(CSRC, "ingest_taps.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(f) > os.path.getmtime(out) for f in srcs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-o", out, srcs[0]], check=True)
     return out
 
 

@@ -234,76 +234,6 @@ bool try_phase(const In* pcm, long long n_frames, int channels, const ResamplePl
 
 }  // namespace
 
-long long ingest_length(long long n_frames, int sr_in, long long* n_real_out) {
-    if (n_frames < 0 || sr_in <= 0) return -1;
-    long long n_real = n_frames;
-    if (sr_in != kIngestRate) {
-        long long a = sr_in, b = kIngestRate;
-        while (b) { const long long t = a % b; a = b; b = t; }
-        const long long orig = sr_in / a, nw = kIngestRate / a;
-        // torch.ceil(torch.as_tensor(new * length / orig)): the quotient is a Python float (correctly rounded double) that
-        // as_tensor stores as float32 BEFORE the ceil
-        const float q = static_cast<float>(static_cast<double>(nw * n_frames) / static_cast<double>(orig));
-        n_real = static_cast<long long>(std::ceil(q));
-    }
-    if (n_real_out) *n_real_out = n_real;
-    return n_real < kIngestWindow ? kIngestWindow : n_real;
-}
-
-// torchaudio.functional._get_sinc_resample_kernel (functional.py:1452-1538) with the band of unclamped taps only.
-bool build_resample_taps(int sr_in, ResamplePlan* plan, std::vector<int>* first, std::vector<float>* w) {
-    long long a = sr_in, b = kIngestRate;
-    while (b) { const long long t = a % b; a = b; b = t; }
-    const int orig = static_cast<int>(sr_in / a), nw = static_cast<int>(kIngestRate / a);
-    const double base = std::fmin(orig, nw) * 0.99;
-    const int width = static_cast<int>(std::ceil(6.0 * orig / base));
-    const int full = 2 * width + orig;
-    const double scale = base / orig;
-    std::vector<double> row(full);
-    std::vector<int> lo(nw), hi(nw);
-    int max_taps = 1;
-    for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 1) {
-            if (nw > 16384 || max_taps > 512) return false;
-            first->assign(nw, 0);
-            w->assign(static_cast<size_t>(nw) * max_taps, 0.f);
-        }
-        for (int p = 0; p < nw; ++p) {
-            // the phase term is an int64 tensor divided by an int: float32 in torch, then promoted to float64
-            const double phase = static_cast<double>(static_cast<float>(-p) / static_cast<float>(nw));
-            int f = full, l = -1;
-            for (int k = 0; k < full; ++k) {
-                double t = (phase + static_cast<double>(k - width) / orig) * base;
-                const bool clamped = t <= -6.0 || t >= 6.0;
-                t = std::fmin(6.0, std::fmax(-6.0, t));
-                const double win = std::cos(t * M_PI / 6.0 / 2.0);
-                t *= M_PI;
-                row[k] = (t == 0.0 ? 1.0 : std::sin(t) / t) * (win * win * scale);
-                if (!clamped) {
-                    if (k < f) f = k;
-                    l = k;
-                }
-            }
-            if (l < f) { f = 0; l = 0; }
-            if (pass == 0) {
-                if (l - f + 1 > max_taps) max_taps = l - f + 1;
-            } else {
-                if (f + max_taps > full) f = full - max_taps;           // keep the band inside the staged span
-                if (f < 0) f = 0;
-                (*first)[p] = f;
-                for (int k = 0; k < max_taps && f + k < full; ++k)
-                    (*w)[static_cast<size_t>(p) * max_taps + k] = static_cast<float>(row[f + k]);
-            }
-        }
-    }
-    plan->orig_f = orig;
-    plan->new_f = nw;
-    plan->width = width;
-    plan->taps_full = full;
-    plan->max_taps = max_taps;
-    return true;
-}
-
 size_t ingest_smem_bytes(const ResamplePlan& plan) {
     const long long m_span = (kBlock - 1) / plan.new_f + 1;             // m_hi - m_lo <= this
     return static_cast<size_t>(m_span * plan.orig_f + plan.taps_full) * sizeof(float);
