@@ -322,7 +322,7 @@ def run_native(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "kernel": "conv_umma_kernel<128,2> + conv_umma2_kernel<256> + block_rows_kernel + stem_fused_kernel "
+                     "kernel": "conv_umma_kernel<128,2,TR> + conv_umma2_kernel<256> + block_rows_kernel + stem_fused_kernel "
                                "(%d launches per chunk)" % n_conv_launches,
                      "algorithmic_bytes_per_launch": (H * args.max_batch * alg_mb * 1e6) / n_conv_launches,
                      "flops_model": "18.1278 GFLOP/head/segment (channel-folded stem, K=49)",
