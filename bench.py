@@ -3,17 +3,25 @@
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
     python bench.py --impl reference --gpus N --steps K --warmup W
+    python bench.py --impl torch_cuda                        (library bar: the reference's torch model on cuDNN)
+    python bench.py --frontend-only [--batch 4096]           (BASELINE.json configs[1]: the mel front end alone)
 
 Metric (BASELINE.json): 4-s 32 kHz segments/sec through (log-mel + merged ResNet-18 ensemble + decisions).
 A "step" = one pass of the hot path over one batch of synthetic segments:
-    workload = BASELINE.json configs[3]: bf16 tensor-core fused mel+ensemble, batch 2048, 6 heads, per GPU.
-`value`  : inputs already resident in HBM (2048 x 128000 fp32 = 1.05 GB > the 126 MB L2, so no L2 flush is needed).
+    workload = BASELINE.json configs[3]: bf16 tensor-core fused mel+ensemble, batch 2048, 6 heads, per GPU, driven
+    through sad_b200.sharded.run_sharded (whole clips per rank, rank-local clip reduction, ONE gather of clip results).
+`value`  : inputs already resident in HBM (2048 x 128000 fp32 = 1.05 GB > the 126 MB L2, so no L2 flush is needed),
+           timed WITHOUT per-kernel events.
+`roofline`: the dominant kernel class (tcgen05 implicit-GEMM convolutions): algorithmic FLOPs / CUDA-event time of
+           those launches, measured live in a SECOND pass of the same K steps with per-kernel events on
+           (`value_profiled` is that pass's throughput), against MEASURED_PEAKS.json.
 `e2e`    : the same batch through the C-ABI host entry (sad_forward_host): pinned host PCM -> H2D -> compute ->
            D2H of logits/probs/labels, every step.
-`roofline`: the dominant kernel (tcgen05 implicit-GEMM convolution, all 20 conv launches per chunk): algorithmic
-           FLOPs / CUDA-event time measured inside the timed region, against MEASURED_PEAKS.json.
-`cpu_baseline`: the CPU oracle (torch-fp32 restatement of the reference) timed on this box's host cores on a
-           bounded sample of the same workload.
+`cpu_baseline`: the reference's own functions (oracle/_ref, byte-compiled from /root/reference by oracle/build_ref.py)
+           run in the reference's own loop on this box's host cores, on a bounded sample of the same workload
+           (the oracle port when oracle/_ref is absent).
+`library_baseline`: the reference's torch model on cuDNN / cuBLAS on the same GPU (fp32 NCHW exactly as
+           inference_runner.py:240-241,284 and bf16 autocast + channels_last), bounded sample.
 """
 import argparse
 import json
@@ -31,6 +39,7 @@ if ROOT not in sys.path:
 METRIC = "segments_per_sec_mel_plus_ensemble"
 UNIT = "segments/s"
 SEGMENT_BYTES = 128000 * 4
+LOGMEL_BYTES = 128 * 251 * 4
 CLIP_SEGMENTS = 32            # clips of 32 segments; per-clip decisions are gathered
 
 
@@ -39,15 +48,21 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--batch", type=int, default=2048, help="segments per GPU per step")
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "torch_cuda"])
+    ap.add_argument("--batch", type=int, default=None, help="segments per GPU per step (2048; 4096 with --frontend-only)")
     ap.add_argument("--heads", type=int, default=6)
     ap.add_argument("--max-batch", type=int, default=128, help="segments per internal pass (workspace size)")
-    ap.add_argument("--cpu-sample", type=int, default=8, help="segments in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="segments per step of the CPU arms")
+    ap.add_argument("--lib-sample", type=int, default=256, help="segments per step of the cuDNN library bar")
+    ap.add_argument("--frontend-only", action="store_true", help="configs[1]: PCM -> log-mel dB only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--no-ingest", action="store_true", help="skip the ingest-stage measurement")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 4096 if a.frontend_only else 2048
+    return a
 
 
 def peaks():
@@ -105,72 +120,251 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_oracle_throughput(sd, n_heads, n_seg, threads):
-    """Oracle port (oracle/restatement.py == the reference's torch-CPU arithmetic) on `n_seg` segments."""
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arms: the reference's own loop (oracle/_ref) or, without it, the oracle port
+# ----------------------------------------------------------------------------------------------------------------
+def _cpu_stepper(heads, n_seg, threads):
+    """Returns (step(), kind, description): one pass of the reference CPU path over `n_seg` segments."""
     import torch
     from oracle import fixtures as FX
-    from oracle import restatement as R
-    torch.set_num_threads(threads)
-    x = FX.synth_segments(n_seg, first=0)
-
-    def once():
-        t0 = time.perf_counter()
-        img = R.waveform_to_image(x)                               # front end, per-segment semantics
-        logits = R.ensemble_forward(img.unsqueeze(1).repeat(1, 3, 1, 1), sd)
-        R.interpret(logits, 0.5)
-        return time.perf_counter() - t0
-
-    once()                                                         # warm-up
-    dt = min(once(), once())
-    return n_seg / dt
-
-
-def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path.  The reference is pure Python over
-    torch/torchaudio/torchvision; /root/reference does not exist on the GPU box, so the arm times the oracle port
-    (bit-identical to the reference functions in the build container, tests/test_oracle_golden.py)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    import torch
+    from oracle import reference_api as RA
     from sad_b200 import synthetic as S
-    threads = os.cpu_count() or 1
-    sd = S.random_merged_state_dict(args.heads, seed=0)
-    n_seg = args.cpu_sample
     torch.set_num_threads(threads)
-    times = []
-    from oracle import fixtures as FX
-    from oracle import restatement as R
+    sd = S.random_merged_state_dict(heads, seed=0)
     x = FX.synth_segments(n_seg, first=0)
+    names = FX.class_names(heads)
+    if RA.available() or RA.compiled_available():
+        from oracle import reference_loop as RL
+        IR, _ = RA.load(allow_compiled=True)
+        torch.backends.cudnn.deterministic = True                  # IR:240-241
+        torch.backends.cudnn.benchmark = False
+        model, _ = RL.build_model(IR, sd, names, torch.device("cpu"))
+        chunks = [x[i] for i in range(n_seg)]                      # what slice_waveform returns: views [128000]
+
+        def step():
+            RL.clip_pass(IR, model, chunks, torch.device("cpu"), names)
+        return step, "reference", (f"{n_seg} segments x {heads} heads per step through the reference's own functions "
+                                   f"(oracle/_ref: waveform_to_spectrogram per segment, load_merged_model's model in "
+                                   f"batches of 128, interpret_multihead_logits per row), torch fp32, {threads} threads")
+    from oracle import restatement as R
 
     def step():
         img = R.waveform_to_image(x)
         logits = R.ensemble_forward(img.unsqueeze(1).repeat(1, 3, 1, 1), sd)
         R.interpret(logits, 0.5)
+    return step, "port", f"{n_seg} segments x {heads} heads per step, oracle port (torch fp32), {threads} threads"
 
-    for _ in range(max(1, min(args.warmup, 2))):
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path on this box's host cores, `--steps` timed steps
+    after `--warmup` untimed ones, each step a bounded sample (`--cpu-sample` segments) of the native arm's workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_seg = args.cpu_sample
+    step, kind, sample = _cpu_stepper(args.heads, n_seg, threads)
+    for _ in range(args.warmup):
         step()
-    steps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    v = n_seg * steps / dt
-    sample = f"{n_seg} segments x {args.heads} heads per step, torch fp32, {threads} threads"
+    v = n_seg * args.steps / dt
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"fused mel+ensemble, {args.heads} heads, CPU sample of {n_seg} segments per step "
-                               f"(workload of the native arm: batch {args.batch} per GPU)", "heads": args.heads},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": f"BASELINE.json configs[3] (fused mel+ensemble, {args.heads} heads), CPU arm: bounded sample "
+                               f"of {n_seg} segments per step (native arm: batch 2048 per GPU)", "heads": args.heads,
+                   "weights": "random-init resnet18 x heads (seed 0)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# library bar: the reference's torch model on cuDNN / cuBLAS, same GPU
+# ----------------------------------------------------------------------------------------------------------------
+def library_bar(heads, n_seg, dev, reps=2):
+    """The reference model (IR.load_merged_model) on `dev`: (i) fp32 NCHW, cudnn.deterministic, batches of 128 exactly
+    as IR:240-241,284-288; (ii) bf16 autocast + channels_last.  Input images come from the reference's CPU front end
+    for 8 segments, tiled -- the model's speed does not depend on the pixel values.  Returns a dict."""
+    import torch
+    from oracle import fixtures as FX
+    from oracle import reference_api as RA
+    from oracle import reference_loop as RL
+    from sad_b200 import synthetic as S
+    if not (RA.available() or RA.compiled_available()):
+        return {"unavailable": "oracle/_ref is absent (run `python -m oracle.build_ref` in the build container)"}
+    IR, _ = RA.load(allow_compiled=True)
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    sd = S.random_merged_state_dict(heads, seed=0)
+    names = FX.class_names(heads)
+    model, _ = RL.build_model(IR, sd, names, dev)
+    spec_cfg = IR.SpectrogramConfig(2048, 512, 128, 20, 12000, 80, "slaney")
+    x = FX.synth_segments(8, first=0)
+    base = torch.cat([IR.waveform_to_spectrogram(x[i], 32000, spec_cfg) for i in range(8)]).to(dev)
+    imgs = base.repeat((n_seg + 7) // 8, 1, 1, 1)[:n_seg].contiguous()
+    gflop = S.conv_flops_total(folded_stem=False) * heads            # as the reference computes it (3-channel stem)
+    out = {"sample": f"{n_seg} segments x {heads} heads per pass, images resident on the GPU, batches of 128 (IR:284)",
+           "flops_model": "18.9499 GFLOP/head/segment (3-channel stem, what the library executes)"}
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    def fp32():
+        with torch.no_grad():
+            for s in range(0, n_seg, 128):
+                model(imgs[s:s + 128])
+    ms = timed(fp32)
+    out["fp32_cudnn"] = {"segments_per_s": n_seg / (ms / 1e3), "tflops": n_seg * gflop / ms / 1e6, "ms": ms,
+                         "how": "fp32 NCHW, cudnn.deterministic=True, benchmark=False, TF32 off (torch default)"}
+    model_cl = model.to(memory_format=torch.channels_last)
+    imgs_cl = imgs.to(memory_format=torch.channels_last)
+
+    def bf16():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            for s in range(0, n_seg, 128):
+                model_cl(imgs_cl[s:s + 128])
+    ms = timed(bf16)
+    out["bf16_autocast_channels_last"] = {"segments_per_s": n_seg / (ms / 1e3), "tflops": n_seg * gflop / ms / 1e6,
+                                          "ms": ms, "how": "torch.autocast(bfloat16) + channels_last, eval-mode BN unfolded"}
+    torch.backends.cudnn.benchmark = True
+
+    def bf16_tuned():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            for s in range(0, n_seg, 128):
+                model_cl(imgs_cl[s:s + 128])
+    ms = timed(bf16_tuned)
+    out["bf16_autocast_channels_last_cudnn_benchmark"] = {
+        "segments_per_s": n_seg / (ms / 1e3), "tflops": n_seg * gflop / ms / 1e6, "ms": ms,
+        "how": "as above with cudnn.benchmark=True (the reference sets it False; the library's best case)"}
+    torch.backends.cudnn.benchmark = False
+    del model, model_cl, imgs, imgs_cl
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_torch_cuda(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    n_seg = args.batch if args.batch != 2048 or args.lib_sample >= 2048 else args.lib_sample
+    r = library_bar(args.heads, n_seg, dev, reps=max(1, args.steps))
+    best = r.get("bf16_autocast_channels_last", {})
+    print(json.dumps({"impl": "torch_cuda", "metric": METRIC, "value": best.get("segments_per_s"), "unit": UNIT,
+                      "n_gpus": 1, "steps": args.steps, "warmup": 1, "higher_is_better": True, "dtype": "bf16",
+                      "data": "synthetic", "config": {"workload": "ensemble only (no front end): the reference's torch "
+                                                      "model on cuDNN", "heads": args.heads, "segments": n_seg},
+                      "library_baseline": r}))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# configs[1]: the front end alone
+# ----------------------------------------------------------------------------------------------------------------
+def run_frontend(args):
+    import torch
+    from sad_b200 import synthetic as S
+    from sad_b200.engine import Engine
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    eng = Engine(1, dev, max_batch=min(B, 512))
+    x = S.synth_pcm(B, 0, dev)
+    db = torch.empty(B, 128, 251, device=dev, dtype=torch.float32)
+    ms_ = torch.empty(B, 2, device=dev, dtype=torch.float32)
+    for _ in range(W):
+        eng.logmel_into(x, db, ms_)
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        eng.logmel_into(x, db, ms_)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = eng.launches - l0
+    v = B * K / (ms / 1e3)
+    # end to end: pinned host PCM -> H2D -> front end -> D2H of the log-mel
+    xh = torch.empty(B, 128000, dtype=torch.float32, pin_memory=True)
+    xh.copy_(x)
+    dbh = torch.empty(B, 128, 251, dtype=torch.float32, pin_memory=True)
+    xd = torch.empty_like(x)
+
+    def e2e_step():
+        xd.copy_(xh, non_blocking=True)
+        eng.logmel_into(xd, db, ms_)
+        dbh.copy_(db, non_blocking=True)
+    e2e_step()
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(K):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms2 = e0.elapsed_time(e1)
+    pk = peaks()
+    gbs = v * (SEGMENT_BYTES + LOGMEL_BYTES) / 1e9
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    tfl = v * 16.0e6 / 1e12
+    out = {"metric": "segments_per_sec_mel_frontend", "value": v, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": "BASELINE.json configs[1]: mel-spectrogram front end only, batch %d synthetic segments on "
+                                  "1xB200 (PCM fp32 in HBM -> log-mel dB fp32 [B,128,251] + per-segment mean/std)" % B,
+                      "batch": B, "l2": "inputs larger than L2 (%.2f GB PCM per step); no flush" % (B * SEGMENT_BYTES / 1e9)},
+           "clocks": clocks, "gpu_launches": int(launches),
+           "e2e": {"value": B * K / (ms2 / 1e3), "unit": UNIT, "h2d_bytes_per_step": B * SEGMENT_BYTES,
+                   "d2h_bytes_per_step": B * LOGMEL_BYTES},
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                        "traffic": None, "kernel": "logmel_kernel (one launch per chunk of <= 512 segments)",
+                        "algorithmic_bytes_per_segment": SEGMENT_BYTES + LOGMEL_BYTES,
+                        "peak_source": pk["source"] + " hbm_gbs",
+                        "compute": {"flops_model": "16 MFLOP fp32/segment (126 packed 2048-pt FFTs + window, power, mel, "
+                                                   "log): above the CUDA-core ridge, so the HBM fraction is bounded by "
+                                                   "fp32 throughput, not by bandwidth",
+                                    "achieved_tflops": tfl, "fp32_peak_tflops": fp32_peak, "frac": tfl / fp32_peak}}}
+    if not args.no_cpu_baseline:
+        import torch as T
+        from oracle import fixtures as FX
+        from oracle import restatement as R
+        threads = os.cpu_count() or 1
+        T.set_num_threads(threads)
+        xs = FX.synth_segments(64, first=0)
+        R.logmel_db(xs[:8])
+        t0 = time.perf_counter()
+        for i in range(0, 64, 8):
+            R.standardise(R.logmel_db(xs[i:i + 8]))
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 64 / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": "64 segments, oracle port of the torchaudio front end (torch fp32)"}
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------------------------------
 def run_native(args):
     import torch
     import torch.distributed as dist
+    from sad_b200 import sharded
     from sad_b200 import synthetic as S
     from sad_b200.engine import Engine
 
@@ -188,18 +382,14 @@ def run_native(args):
     sd = S.random_merged_state_dict(H, seed=0)
     eng.load_merged_state_dict(sd)
 
-    # this rank's shard of the step's segments: whole clips, contiguous
+    # the step's segments: world x B, whole clips per rank; global segment i is the same bytes at every N
+    n_clips = world * B // CLIP_SEGMENTS
+    lengths = [CLIP_SEGMENTS] * n_clips
     x = S.synth_pcm(B, first=rank * B, device=dev)
-    n_clips = B // CLIP_SEGMENTS
-    clip_id = (torch.arange(B, device=dev, dtype=torch.int32) // CLIP_SEGMENTS).contiguous()
-    gathered = [torch.empty(n_clips, H + 2, device=dev) for _ in range(world)] if world > 1 else None
 
     def step():
-        logits, probs, labels = eng.forward_pcm(x, 0.5)
-        cp, cl = eng.clip_reduce(probs, clip_id, n_clips, 0.5)
-        if world > 1:   # the path's only exchange: per-clip decisions to every rank
-            dist.all_gather(gathered, torch.cat([cp, cl.float().unsqueeze(1)], dim=1))
-        return labels, cl
+        return sharded.run_sharded(lengths, lambda lo, hi: x, lambda pcm: eng.forward_pcm(pcm, 0.5)[1:],
+                                   lambda p, cid, n: eng.clip_reduce(p, cid, n, 0.5))
 
     def barrier():
         torch.cuda.synchronize()
@@ -207,32 +397,36 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    eng.profile_enable(True)
+    def timed(k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(k):
+            step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    eng.profile_enable(False)
     for _ in range(W):
         step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    eng.profile_enable(True)                    # resets the per-kernel counters
     launches0 = eng.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(K):
-        step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = timed(K)                                   # pass 1: the headline, no per-kernel events
+    launches = eng.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
+    value = world * B * K / (ms / 1e3)
+
+    eng.profile_enable(True)                        # pass 2: same K steps with CUDA events around every kernel class
+    ms_prof = timed(K)
     prof_ms, prof_n = eng.profile_read()
     eng.profile_enable(False)
-    launches = eng.launches - launches0
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * B * K / (ms / 1e3)
 
     # ---- end to end through the host entry of the C ABI --------------------------------------------------
     e2e = None
@@ -241,6 +435,7 @@ def run_native(args):
         xh.copy_(x)
         for _ in range(2):
             eng.forward_host(xh, 0.5)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
         for _ in range(K):
@@ -262,6 +457,7 @@ def run_native(args):
         for _ in range(3):
             y = eng.ingest(pcm16, sr_in)
         torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
             y = eng.ingest(pcm16, sr_in)
@@ -293,12 +489,14 @@ def run_native(args):
     achieved = conv_tflop / (conv_ms / 1e3) if conv_ms > 0 else 0.0
     peak = pk["bf16_tflops_sustained"]
     traffic = None                              # DRAM bytes per conv launch from the committed ncu --set full capture
-    tp = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
-    if os.path.exists(tp):
-        with open(tp) as f:
-            tj = json.load(f)
-        if tj.get("chunk") == args.max_batch and tj.get("heads") == H:
-            traffic = tj["dram_bytes_per_launch_mean"]
+    for name in ("r02_roofline_traffic.json", "r01_roofline_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            if tj.get("chunk") == args.max_batch and tj.get("heads") == H:
+                traffic = tj["dram_bytes_per_launch_mean"]
+            break
     n_conv_launches = sum(1 for i in range(20) if prof_n[i] > 0)
     # activation bytes per (head, segment): 40 MB with one launch per conv; a fused layer1 block keeps its
     # intermediate and residual on chip: -3 x 2.1 MB per block
@@ -307,8 +505,6 @@ def run_native(args):
                  for i in range(20)}
     fe_ms = prof_ms[eng.PROF_FRONTEND]
     fe_gbs = (B * K * 512000 / 1e9) / (fe_ms / 1e3) if fe_ms > 0 else 0.0
-    fe_tflops = (B * K * 16.0e6 / 1e12) / (fe_ms / 1e3) if fe_ms > 0 else 0.0
-    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # SMs x FMA lanes x 2 x max SM clock
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -318,25 +514,25 @@ def run_native(args):
                    "batch_per_gpu": B, "heads": H, "outputs": H + 1, "internal_chunk": args.max_batch,
                    "l2": "inputs larger than L2 (1.05 GB PCM per step, activations ~%d MB per chunk); no flush"
                          % int(args.max_batch * H * 7),
-                   "weights": "random-init resnet18 x heads (seed 0)", "parallelism": f"segment-sharded x{world}"},
+                   "weights": "random-init resnet18 x heads (seed 0), BN statistics random (not calibrated)",
+                   "parallelism": f"segment-sharded x{world}"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "value_profiled": world * B * K / (ms_prof / 1e3),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
                      "kernel": "conv_umma_kernel<128,2,TR> + conv_umma2_kernel<256> + block_rows_kernel + stem_fused_kernel "
                                "(%d launches per chunk)" % n_conv_launches,
-                     "algorithmic_bytes_per_launch": (H * args.max_batch * alg_mb * 1e6) / n_conv_launches,
+                     "algorithmic_bytes_per_launch": (H * args.max_batch * alg_mb * 1e6) / max(n_conv_launches, 1),
                      "flops_model": "18.1278 GFLOP/head/segment (channel-folded stem, K=49)",
                      "peak_source": pk["source"] + " bf16_tflops_sustained",
+                     "measured_in": "second pass of the same K steps with per-kernel CUDA events (value_profiled)",
                      "kernel_ms_per_step": conv_ms / K, "kernel_launches": int(conv_launches),
-                     "share_of_step": conv_ms / ms if ms > 0 else None,
+                     "share_of_step": conv_ms / ms_prof if ms_prof > 0 else None,
                      "per_conv_tflops": per_layer},
         "roofline_frontend": {"bound": "hbm", "achieved": fe_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                              "frac": fe_gbs / pk["hbm_gbs"], "bytes_model": "512000 B/segment (PCM in; log-mel "
-                              "stays on the device for the fused path)", "kernel_ms_per_step": fe_ms / K,
-                              # the front end is above the CUDA-core ridge: compute-side view
-                              "compute": {"flops_model": "16 MFLOP fp32/segment (126 packed 2048-pt FFTs + window, "
-                                          "power, mel, log)", "achieved_tflops": fe_tflops,
-                                          "fp32_peak_tflops": fp32_peak, "frac": fe_tflops / fp32_peak}},
+                              "frac": fe_gbs / pk["hbm_gbs"], "bytes_model": "512000 B/segment (PCM in; the log-mel "
+                              "stays on the device for the fused path); stand-alone line: bench.py --frontend-only",
+                              "kernel_ms_per_step": fe_ms / K},
         "roofline_ingest": None if ingest is None else {
             "bound": "hbm", "achieved": ingest["bytes"] / 1e9 / (ingest["ms"] / 1e3), "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": ingest["bytes"] / 1e9 / (ingest["ms"] / 1e3) / pk["hbm_gbs"],
@@ -346,11 +542,21 @@ def run_native(args):
             "audio_seconds_per_second": ingest["seconds_of_audio"] / (ingest["ms"] / 1e3)},
         "other_ms_per_step": {"image": prof_ms[eng.PROF_IMAGE] / K, "head_merge": prof_ms[eng.PROF_HEAD] / K},
     }
+    eng.close()
+    if world == 1 and not args.no_library_baseline:
+        try:
+            out["library_baseline"] = library_bar(H, args.lib_sample, dev)
+        except Exception as e:                                     # the bar is a comparator, never a reason to fail
+            out["library_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v = cpu_oracle_throughput(sd, H, args.cpu_sample, threads)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"{args.cpu_sample} segments x {H} heads, oracle port (torch fp32), best of 2"}
+        stepf, kind, sample = _cpu_stepper(H, args.cpu_sample, threads)
+        stepf()                                                    # warm-up
+        t0 = time.perf_counter()
+        stepf()
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": args.cpu_sample / dt, "unit": UNIT, "cores": threads, "kind": kind,
+                               "sample": sample + ", 1 warm-up + 1 timed pass"}
     else:
         out["cpu_baseline"] = None
     print(json.dumps(out))
@@ -362,6 +568,10 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_cuda":
+        run_torch_cuda(args)
+    elif args.frontend_only:
+        run_frontend(args)
     else:
         run_native(args)
 

@@ -13,7 +13,12 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); calls are
  *     stream-ordered and do not synchronise unless stated;
  *   - the caller owns every buffer it passes; the library owns its context, weights and workspace;
- *   - there is no CPU fallback: without a CUDA device sad_create fails with SAD_ENODEVICE.
+ *   - there is no CPU fallback: without a CUDA device sad_create fails with SAD_ENODEVICE;
+ *   - a context owns ONE workspace: calls on a context may come from any stream (and sad_forward_host uses its own
+ *     internal streams), the library orders each call after the previous one on that context with an event, so
+ *     results never race -- but two calls on one context never overlap.  Use one context per concurrent stream.
+ *     Calls on one context must not be issued from two host threads at the same time;
+ *   - every entry point leaves the calling thread's current CUDA device as it found it.
  */
 #ifndef SAD_B200_H_
 #define SAD_B200_H_
@@ -47,9 +52,9 @@ typedef struct sad_ctx sad_ctx;
  * (ModularMultiHeadClassifier, inference_runner.py:53-73); `max_batch` = segments processed per
  * internal pass (workspace is sized for it; larger batches are chunked).                        */
 int sad_create(sad_ctx** out, int device, int n_heads, int max_batch);
-/* Same with the backbone named explicitly: "resnet18" (default) or "resnet34" -- the BasicBlock ResNets that
- * `--model-name` / `backbone_name` may select (model_merger.py:101, inference_runner.py:77).  Bottleneck variants
- * (resnet50+) return SAD_EINVAL.                                                                          */
+/* Same with the backbone named explicitly -- what `--model-name` / `backbone_name` may select (model_merger.py:101,
+ * inference_runner.py:77): "resnet18" (default), "resnet34" (BasicBlock) or "resnet50" / "resnet101" / "resnet152"
+ * (Bottleneck).  Any other name returns SAD_EINVAL.                                                          */
 int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const char* backbone);
 const char* sad_backbone(const sad_ctx* ctx);
 int sad_destroy(sad_ctx* ctx);
@@ -126,6 +131,13 @@ int sad_forward_host(sad_ctx* ctx, const float* pcm_host, int B, float threshold
  * segments of probs; clip_label = rule :207-213 applied to the clip mean (-1 for a clip with no segment). */
 int sad_clip_reduce(sad_ctx* ctx, const float* probs_dev, const int32_t* clip_id_dev, int B, int n_clips,
                     float threshold, float* clip_probs_dev, int32_t* clip_label_dev, void* stream);
+
+/* ---- synthetic corpus (bench.py, tools/run_corpus.py; no reference counterpart) ----------------- */
+/* out_dev [n,128000] fp32 = segments first .. first+n-1 of the seeded noise/tone corpus the benchmarks run on
+ * (a_n*N(0,1) + a_t*sin(2*pi*f*t+phi), clipped).  Counter based: a segment's bytes depend only on
+ * (seed, global segment index), never on chunking or on the number of GPUs sharing the corpus.  `ctx` may be NULL:
+ * the kernel then runs on the calling thread's current device.                                               */
+int sad_synth_segments(sad_ctx* ctx, float* out_dev, long long first, int n, unsigned long long seed, void* stream);
 
 /* ---- introspection (tests, bench) --------------------------------------------------------------- */
 int sad_n_heads(const sad_ctx* ctx);

@@ -63,6 +63,84 @@ def synth_segments(n: int, first: int = 0, seed: int = AUDIO_SEED) -> torch.Tens
     return out
 
 
+FAMILY_SEED = 4242
+N_FAMILIES = 7
+FAMILY_NAMES = ("white noise", "tone", "harmonic stack", "gated noise bursts", "low-pass noise", "high-pass noise",
+                "narrow-band noise")
+
+
+def _loguniform(u, lo: float, hi: float) -> float:
+    return math.exp(math.log(lo) + float(u) * (math.log(hi) - math.log(lo)))
+
+
+def family_segments(n: int, first: int = 0, n_classes: int = N_FAMILIES, seed: int = FAMILY_SEED):
+    """Class-structured noise/tone corpus for DECISION parity: ([n,128000] fp32 in [-1,1], class ids [n] int64).
+
+    A trained detector sees sources that form separate clusters (real audio, generator 1, generator 2, ...) and its
+    logits sit away from the threshold; pure random-init logits on a continuous corpus hug zero, where any rounding
+    flips the sign rule IR:207-213.  Segment i (global index first+i, generator seeded seed ^ i) is drawn from one of
+    ``n_classes`` signal families built from noise and tones, each with its own level / frequency / rate spread:
+
+      0 white noise ("real")      1 tone 700-1400 Hz          2 harmonic stack, f0 180-300 Hz, 12 partials
+      3 noise bursts gated 3-5 Hz 4 low-pass noise (two one-pole sections, 200-400 Hz)
+      5 high-pass noise (second difference)                   6 narrow-band noise (two biquad band-pass sections, 2.5-4 kHz)
+
+    Only sequential float64 recursions (torchaudio lfilter) and elementwise ops: no FFT, so the bytes do not depend on
+    the FFT library of the machine that regenerates them.
+    """
+    import torchaudio.functional as AF
+    T, sr = R.WINDOW_SAMPLES, R.SAMPLE_RATE
+    out = torch.empty(n, T, dtype=torch.float32)
+    cls = np.empty(n, np.int64)
+    t = torch.arange(T, dtype=torch.float64) / sr
+    for k in range(n):
+        g = torch.Generator().manual_seed(seed ^ (first + k))
+        u = torch.rand(8, generator=g, dtype=torch.float64)
+        c = min(int(float(u[0]) * n_classes), n_classes - 1)
+        cls[k] = c
+        noise = torch.randn(T, generator=g, dtype=torch.float64)
+        a_t = 0.1 + 0.4 * float(u[2])
+        phi = 2 * math.pi * float(u[4])
+        a_n = _loguniform(u[1], 1e-3, 0.02)
+        if c == 0:
+            sig = torch.zeros(T, dtype=torch.float64)
+            a_n = _loguniform(u[1], 0.01, 0.2)
+        elif c == 1:
+            sig = a_t * torch.sin(2 * math.pi * _loguniform(u[3], 700, 1400) * t + phi)
+        elif c == 2:
+            f0 = _loguniform(u[3], 180, 300)
+            sig = torch.zeros(T, dtype=torch.float64)
+            for h in range(1, 13):
+                sig = sig + torch.sin(2 * math.pi * f0 * h * t + phi * h)
+            sig = 0.5 * a_t * sig / math.sqrt(12.0)
+        elif c == 3:
+            r = 3 + 2 * float(u[5])
+            gate = (torch.sin(2 * math.pi * r * t + 2 * math.pi * float(u[6])) > 0).double()
+            a_n = _loguniform(u[1], 1e-3, 0.005)
+            sig = (0.05 + 0.25 * float(u[2])) * gate * torch.randn(T, generator=g, dtype=torch.float64)
+        elif c == 4:
+            a = 1 - math.exp(-2 * math.pi * _loguniform(u[3], 200, 400) / sr)
+            den = torch.tensor([1.0, a - 1.0], dtype=torch.float64)
+            num = torch.tensor([a, 0.0], dtype=torch.float64)
+            y = torch.randn(T, generator=g, dtype=torch.float64)
+            y = AF.lfilter(AF.lfilter(y, den, num, clamp=False), den, num, clamp=False)
+            sig = (0.05 + 0.3 * float(u[2])) * y / y.std()
+            a_n = _loguniform(u[1], 1e-4, 5e-4)
+        elif c == 5:
+            w = torch.randn(T + 2, generator=g, dtype=torch.float64)
+            y = w[2:] - 2 * w[1:-1] + w[:-2]
+            sig = (0.05 + 0.3 * float(u[2])) * y / y.std()
+            a_n = _loguniform(u[1], 1e-4, 5e-4)
+        else:
+            fc = _loguniform(u[3], 2500, 4000)
+            y = torch.randn(T, generator=g, dtype=torch.float64)
+            y = AF.bandpass_biquad(AF.bandpass_biquad(y, sr, fc, 3.0), sr, fc, 3.0)
+            sig = (0.05 + 0.25 * float(u[2])) * y / y.std()
+            a_n = _loguniform(u[1], 1e-4, 1e-3)
+        out[k] = torch.clamp(a_n * noise + sig, -1.0, 1.0).float()
+    return out, cls
+
+
 def synth_clip(n_samples: int, seed: int, silent_spans=()) -> torch.Tensor:
     """A longer clip for slicing tests; ``silent_spans`` are (start, stop) sample ranges zeroed."""
     g = torch.Generator().manual_seed(seed)
@@ -163,17 +241,16 @@ def random_head_state(g: torch.Generator, backbone: str = "resnet18") -> "Ordere
     return sd
 
 
-def _calibrate(sd: Dict[str, torch.Tensor], images: torch.Tensor, head_index: int = 0) -> None:
-    """Set every BN's running stats to the statistics its input has on ``images``.
+def _stat(sd, x, key, dims):
+    sd[key + ".running_mean"] = x.mean(dim=dims).clone()
+    sd[key + ".running_var"] = x.var(dim=dims, unbiased=False).clone() + 1e-3
 
-    Done layer by layer in forward order (so later layers see calibrated inputs).  The
-    final Linear(256,2) is then ridge-fitted on the calibration corpus (see below) so the
-    logits are bimodal with a margin on in-distribution inputs, like a trained detector's,
-    instead of hugging zero where any rounding flips the decision (hard part 1).
-    """
+
+def _calibrate_trunk(sd: Dict[str, torch.Tensor], images: torch.Tensor) -> torch.Tensor:
+    """Set every trunk BN's running stats to the statistics its input has on ``images`` (layer by layer in forward
+    order, so later layers see calibrated inputs); returns the pooled features [n, C]."""
     def stat(x, key, dims):
-        sd[key + ".running_mean"] = x.mean(dim=dims).clone()
-        sd[key + ".running_var"] = x.var(dim=dims, unbiased=False).clone() + 1e-3
+        _stat(sd, x, key, dims)
 
     with torch.no_grad():
         p = "base."
@@ -218,29 +295,111 @@ def _calibrate(sd: Dict[str, torch.Tensor], images: torch.Tensor, head_index: in
                 else:
                     idn = x
                 x = F.relu(o + idn)
-        v = x.mean(dim=(2, 3))
-        v = F.linear(v, sd["head.2.weight"], sd["head.2.bias"])
-        stat(v, "head.3", (0,))
+        return x.mean(dim=(2, 3))
+
+
+def _fit_head(sd: Dict[str, torch.Tensor], pooled: torch.Tensor, y_real: torch.Tensor, y_syn: torch.Tensor,
+              ridge: float) -> None:
+    """Calibrate the head's two BN1d layers on ``pooled`` and ridge-fit the last Linear(256,2) to the targets
+    (column 0 = Real logit, column 1 = Synthetic logit, IR:31)."""
+    with torch.no_grad():
+        v = F.linear(pooled, sd["head.2.weight"], sd["head.2.bias"])
+        _stat(sd, v, "head.3", (0,))
         v = F.relu(R._bn(v, sd, "head.3"))
         v = F.linear(v, sd["head.6.weight"], sd["head.6.bias"])
-        stat(v, "head.7", (0,))
+        _stat(sd, v, "head.7", (0,))
         v = F.relu(R._bn(v, sd, "head.7"))
-        # "Trained-like" read-out: ridge-fit the last Linear so that on the calibration corpus
-        # the Synthetic logit is +-TARGET according to an input attribute this head "detects"
-        # (mean level of one 64-row strip of the image = 16 mel bands); the Real logit follows an
-        # attribute common to all heads (strip 7).
-        def strip_sign(k):
-            a = images[:, 0, 64 * k:64 * k + 64, :].mean(dim=(1, 2))
-            return torch.where(a > a.median(), TARGET, -TARGET)
-        y_syn = strip_sign(head_index % 7)       # what THIS head detects
-        y_real = strip_sign(7)                   # shared by all heads, so mean_i(real_i) keeps its margin
         Y = torch.stack([y_real, y_syn], dim=1).double()
         X = torch.cat([v, torch.ones(v.shape[0], 1)], dim=1).double()
-        A = X.T @ X + RIDGE * torch.eye(X.shape[1], dtype=torch.float64)
-        A[-1, -1] -= RIDGE
+        A = X.T @ X + ridge * torch.eye(X.shape[1], dtype=torch.float64)
+        A[-1, -1] -= ridge
         Wb = torch.linalg.solve(A, X.T @ Y).float()
         sd["head.10.weight"] = Wb[:-1].T.contiguous()
         sd["head.10.bias"] = Wb[-1].contiguous()
+
+
+def _calibrate(sd: Dict[str, torch.Tensor], images: torch.Tensor, head_index: int = 0) -> None:
+    """v1 fixture (goldens ensemble_n2 / n5 / r34 / r50): trunk BN statistics from ``images``, then a "trained-like"
+    read-out: the last Linear is ridge-fitted so that on the calibration corpus the Synthetic logit is +-TARGET
+    according to an input attribute this head "detects" (mean level of one 64-row strip of the image = 16 mel bands);
+    the Real logit follows an attribute common to all heads (strip 7).  32 segments only: it gives margin to the
+    calibration segments, not to held-out ones -- decision parity uses the v2 fixture below."""
+    pooled = _calibrate_trunk(sd, images)
+
+    def strip_sign(k):
+        a = images[:, 0, 64 * k:64 * k + 64, :].mean(dim=(1, 2))
+        return torch.where(a > a.median(), TARGET, -TARGET)
+    y_syn = strip_sign(head_index % 7)       # what THIS head detects
+    y_real = strip_sign(7)                   # shared by all heads, so mean_i(real_i) keeps its margin
+    _fit_head(sd, pooled, y_real, y_syn, RIDGE)
+
+
+# --------------------------------------------------------------------------------------
+# v2 "decision" fixture: frozen random-init trunks (BN calibrated) + read-outs fitted on 2048 segments of the
+# class-structured corpus, the regime the reference trains in (submodel_trainer.py:609-633 freezes the backbone and
+# trains the attached head).  The fitted numbers are committed (tests/golden/decision_fixture.npz, written by
+# oracle/make_decision_fixture.py) so loading the fixture costs no trunk forward.
+# --------------------------------------------------------------------------------------
+DEC_CAL_FIRST = 5_000_000      # 64 segments: trunk BN statistics
+DEC_N_CAL = 64
+DEC_FIT_FIRST = 6_000_000      # 2048 segments: head BN statistics + read-out
+DEC_N_FIT = 2048
+DEC_HELD_FIRST = 7_000_000     # held-out segments of the decision goldens start here
+DEC_RIDGE = 10.0
+DEC_MAX_HEADS = 6
+_DEC_FILE = "decision_fixture.npz"
+
+
+def decision_fixture_path() -> str:
+    import os
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", _DEC_FILE)
+
+
+def fit_decision_head(i: int, seed: int = WEIGHT_SEED, batch: int = 32, log=None) -> Dict[str, np.ndarray]:
+    """Calibrate + fit head i (detects family i+1; its Real logit detects family 0).  Returns the arrays that differ
+    from random_head_state: every BN running_mean / running_var and head.10.*."""
+    g = torch.Generator().manual_seed(seed * 1000 + i)
+    sd = random_head_state(g)
+    xc, _ = family_segments(DEC_N_CAL, DEC_CAL_FIRST)
+    _calibrate_trunk(sd, R.waveform_to_image(xc).unsqueeze(1).repeat(1, 3, 1, 1))
+    pooled, classes = [], []
+    with torch.no_grad():
+        for b0 in range(0, DEC_N_FIT, batch):
+            x, c = family_segments(min(batch, DEC_N_FIT - b0), DEC_FIT_FIRST + b0)
+            img = R.waveform_to_image(x).unsqueeze(1).repeat(1, 3, 1, 1)
+            pooled.append(R.backbone_features(img, sd, "base.").mean(dim=(2, 3)))
+            classes.append(c)
+            if log and (b0 // batch) % 8 == 0:
+                log(f"head {i}: {b0}/{DEC_N_FIT}")
+    pooled = torch.cat(pooled)
+    cls = torch.from_numpy(np.concatenate(classes))
+    y_real = torch.where(cls == 0, TARGET, -TARGET)
+    y_syn = torch.where(cls == i + 1, TARGET, -TARGET)
+    _fit_head(sd, pooled, y_real, y_syn, DEC_RIDGE)
+    return {k: v.numpy() for k, v in sd.items()
+            if k.endswith("running_mean") or k.endswith("running_var") or k.startswith("head.10.")}
+
+
+_DEC_CACHE = {}
+
+
+def decision_state_dict(n_heads: int, seed: int = WEIGHT_SEED) -> "OrderedDict[str, torch.Tensor]":
+    """Merged state_dict of the v2 fixture: random_head_state(seed) per head with the committed calibration on top."""
+    if n_heads > DEC_MAX_HEADS or seed != WEIGHT_SEED:
+        raise ValueError("the committed decision fixture holds heads 0..%d of seed %d" % (DEC_MAX_HEADS - 1, WEIGHT_SEED))
+    if "npz" not in _DEC_CACHE:
+        _DEC_CACHE["npz"] = np.load(decision_fixture_path(), allow_pickle=False)
+    z = _DEC_CACHE["npz"]
+    merged: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for i in range(n_heads):
+        g = torch.Generator().manual_seed(seed * 1000 + i)
+        sd = random_head_state(g)
+        for k in z.files:
+            if k.startswith(f"h{i}."):
+                sd[k[len(f"h{i}."):]] = torch.from_numpy(z[k].copy())
+        for k, v in sd.items():
+            merged[f"sub_models.{i}.{k}"] = v.contiguous()
+    return merged
 
 
 def calibration_images(n: int = N_CAL) -> torch.Tensor:

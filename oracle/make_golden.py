@@ -92,6 +92,33 @@ def golden_frontend(IR, seg_ids):
     return x
 
 
+def golden_frontend_256(IR, n_seg=256, first=20000):
+    """BASELINE.json configs[1] asks for a >= 256-segment parity subset of the front end.  Full log-mel tensors would be
+    33 MB, so per segment the golden keeps (mean, unbiased std), the max, the float64 sum and a strided sample of the
+    log-mel dB (every 7th mel band x every 5th frame + the last frame), all from the reference's own transforms
+    (IR:158-170) -- plus a strided sample of the 512x512 image from IR.waveform_to_spectrogram (IR:157-174)."""
+    cfg = IR.SpectrogramConfig(2048, 512, 128, 20, 12000, 80, "slaney")
+    mel = torchaudio.transforms.MelSpectrogram(sample_rate=32000, n_fft=2048, hop_length=512, n_mels=128,
+                                               f_min=20, f_max=12000, norm="slaney")
+    a2d = torchaudio.transforms.AmplitudeToDB(top_db=80)
+    frames = np.r_[np.arange(0, 251, 5), 250]
+    db_s, mu, sd, mx, sm, img_s = [], [], [], [], [], []
+    for i in range(n_seg):
+        x = FX.synth_segments(1, first=first + i)[0]
+        spec = a2d(mel(x.unsqueeze(0)))[0]
+        db_s.append(spec[::7][:, frames].numpy().copy())
+        mu.append(float(spec.mean())); sd.append(float(spec.std())); mx.append(float(spec.max()))
+        sm.append(float(spec.double().sum()))
+        img = IR.waveform_to_spectrogram(x, 32000, cfg)[0, 0]
+        img_s.append(img[::37, ::41].numpy().copy())
+    np.savez_compressed(os.path.join(OUT, "frontend_256.npz"), first=np.array(first, dtype=np.int64),
+                        mel_stride=np.array(7), frames=frames.astype(np.int64),
+                        logmel_sample=np.stack(db_s).astype(np.float32), mu=np.array(mu, np.float32),
+                        sigma=np.array(sd, np.float32), db_max=np.array(mx, np.float32), db_sum=np.array(sm, np.float64),
+                        image_sample=np.stack(img_s).astype(np.float32))
+    print("frontend_256:", np.stack(db_s).shape, np.stack(img_s).shape)
+
+
 def golden_ensemble(IR, MM, n_heads, seg_ids, tag, backbone="resnet18"):
     """load_merged_model + ModularMultiHeadClassifier.forward + interpret_multihead_logits."""
     x = torch.cat([FX.synth_segments(1, first=i) for i in seg_ids])
@@ -120,6 +147,46 @@ def golden_ensemble(IR, MM, n_heads, seg_ids, tag, backbone="resnet18"):
         percentages=pct.astype(np.float64),
     )
     print(f"ensemble_{tag}: logits\n", merged.numpy(), "\nlabels", labels)
+
+
+def golden_decisions(IR, n_heads, n_seg, tag, batch=32):
+    """Decision parity at scale (north star: identical Real/Synthetic decision on >= 99.9% of segments): the LIVE
+    reference -- load_merged_model (IR:77-123), waveform_to_spectrogram per segment (IR:157-174), the merged model in
+    mini-batches (IR:284-288), interpret_multihead_logits per row (IR:194-214) -- on `n_seg` HELD-OUT segments of the
+    class-structured corpus with the v2 fixture (oracle/fixtures.py: read-outs fitted on other segments)."""
+    import time
+    cfg = IR.SpectrogramConfig(2048, 512, 128, 20, 12000, 80, "slaney")
+    sd = FX.decision_state_dict(n_heads)
+    names = FX.class_names(n_heads)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "merged.pth")
+        torch.save({"state_dict": sd, "metadata": {"class_names": names}}, path)
+        model, meta = IR.load_merged_model(path, torch.device("cpu"))
+    names = meta["class_names"]
+    logits, labels, classes = [], [], []
+    t0 = time.time()
+    for b0 in range(0, n_seg, batch):
+        x, cls = FX.family_segments(min(batch, n_seg - b0), FX.DEC_HELD_FIRST + b0, n_classes=n_heads + 1)
+        imgs = torch.cat([IR.waveform_to_spectrogram(x[i], 32000, cfg) for i in range(x.shape[0])])
+        with torch.no_grad():
+            merged = model(imgs)
+        for row in merged:
+            lab, _ = IR.interpret_multihead_logits(row, 0.5, names[:-1], names[-1])
+            labels.append(names.index(lab))
+        logits.append(merged.numpy().copy())
+        classes.append(cls)
+        if (b0 // batch) % 8 == 0:
+            print(f"decisions_{tag}: {b0}/{n_seg}  {time.time() - t0:.0f} s", flush=True)
+    logits = np.concatenate(logits)
+    labels = np.array(labels, dtype=np.int16)            # index into class_names: n_heads == Real
+    classes = np.concatenate(classes).astype(np.int16)
+    np.savez_compressed(os.path.join(OUT, f"decisions_{tag}.npz"), first=np.array(FX.DEC_HELD_FIRST, dtype=np.int64),
+                        n_heads=np.array(n_heads), merged_logits=logits.astype(np.float32), labels=labels,
+                        classes=classes, class_names=np.array(names))
+    m = np.abs(logits).min(axis=1)
+    want = np.where(classes == 0, n_heads, classes - 1)
+    print(f"decisions_{tag}: {n_seg} segments; label == source family on {(labels == want).mean():.4f}; "
+          f"min |logit| p0.1 {np.percentile(m, 0.1):.4f} p1 {np.percentile(m, 1):.4f} median {np.median(m):.4f}")
 
 
 def golden_ingest(IR):
@@ -160,10 +227,20 @@ def main():
     torch.manual_seed(0)
     IR, MM = reference_api.load()
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "frontend256":
+        golden_frontend_256(IR)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "decisions":           # ~40 min of CPU: made separately
+        for n_heads, n_seg in ((2, 4096), (5, 2048), (6, 2048)):
+            if len(sys.argv) > 2 and str(n_heads) not in sys.argv[2:]:
+                continue
+            golden_decisions(IR, n_heads, n_seg, f"n{n_heads}")
+        return
     golden_slicing(IR)
     golden_ingest(IR)
     # segments 0..5 (mixed), plus the first "pure tone" and "pure noise" draws of the stream
     golden_frontend(IR, [0, 1, 2, 3, 4, 5, 6, 13])
+    golden_frontend_256(IR)
     golden_ensemble(IR, MM, 2, [0, 1, 2, 3, 4, 5, FX.CAL_FIRST, FX.CAL_FIRST + 1], "n2")
     golden_ensemble(IR, MM, 5, [0, 1, FX.CAL_FIRST, FX.CAL_FIRST + 1], "n5")
     golden_ensemble(IR, MM, 2, [0, 1, FX.CAL_FIRST], "r34_n2", backbone="resnet34")

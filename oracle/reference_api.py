@@ -1,38 +1,46 @@
-"""Import the UNMODIFIED reference modules (build container only).
+"""Import the UNMODIFIED reference modules (TEST INFRASTRUCTURE).
 
-``/root/reference`` is read-only, exists only in the build container and never on
-the GPU box.  Nothing in ``-m gpu`` tests, ``smoke()`` or ``bench.py`` may call
-this at run time; it is used by ``make_golden.py`` and by the CPU tests that
-re-check the restatement against the live reference when it is present.
+Two places can hold them:
+  * ``/root/reference/modular/source`` -- the read-only sources, present only in the build container
+    (``make_golden.py``, CPU tests that re-check the restatement against the live reference);
+  * ``oracle/_ref/*.pyc`` -- the same modules byte-compiled by ``oracle/build_ref.py`` (git-ignored binaries that
+    travel to the GPU box), used by ``bench.py``'s reference arm / ``cpu_baseline`` leg there.
+Nothing in the product path imports this.
 """
 import importlib
 import os
 import sys
 
 REFERENCE_SRC = "/root/reference/modular/source"
+REFERENCE_BIN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 def available() -> bool:
+    """The reference SOURCES are present (build container)."""
     return os.path.isfile(os.path.join(REFERENCE_SRC, "inference_runner.py"))
 
 
-def load():
-    """Return ``(inference_runner, model_merger)`` reference modules.
+def compiled_available() -> bool:
+    return all(os.path.isfile(os.path.join(REFERENCE_BIN, m + ".pyc")) for m in ("inference_runner", "model_merger"))
 
-    They are imported under their own names from ``REFERENCE_SRC`` with the
-    ``timm`` shim in place; the product's same-named modules live inside the
-    package directory and are never on ``sys.path`` as top-level names, so there
-    is no clash.
-    """
-    if not available():
-        raise RuntimeError("reference sources are not present on this machine")
+
+def load(allow_compiled: bool = False):
+    """Return ``(inference_runner, model_merger)`` reference modules, imported under their own names with the ``timm``
+    shim in place; the product's same-named modules live inside the package directory and are never on ``sys.path`` as
+    top-level names, so there is no clash.  ``allow_compiled``: fall back to ``oracle/_ref/*.pyc``."""
+    if available():
+        where = REFERENCE_SRC
+    elif allow_compiled and compiled_available():
+        where = REFERENCE_BIN
+    else:
+        raise RuntimeError("the reference is not present on this machine")
     from . import timm_shim
     timm_shim.install()
-    if REFERENCE_SRC not in sys.path:
-        sys.path.insert(0, REFERENCE_SRC)
+    if where not in sys.path:
+        sys.path.insert(0, where)
     ir = importlib.import_module("inference_runner")
     mm = importlib.import_module("model_merger")
     for mod in (ir, mm):
-        if not os.path.abspath(mod.__file__).startswith(REFERENCE_SRC):
+        if not os.path.abspath(mod.__file__).startswith(where):
             raise RuntimeError(f"{mod.__name__} resolved to {mod.__file__}, not the reference")
     return ir, mm

@@ -42,6 +42,7 @@ SIGNATURES = {
     "sad_launch_count": (_ll, [_vp]),
     "sad_profile_enable": (_i, [_vp, _i]),
     "sad_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_ll)]),
+    "sad_synth_segments": (_i, [_vp, _vp, _ll, _i, C.c_ulonglong, _vp]),
     "sad_ingest_length": (_ll, [_ll, _i]),
     "sad_ingest": (_i, [_vp, _vp, _i, _ll, _i, _i, _vp, _vp]),
     "sad_debug_conv": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),

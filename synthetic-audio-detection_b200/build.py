@@ -1,15 +1,24 @@
-"""Build libsad_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so must travel with the repo)."""
+"""Build libsad_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so must travel with the repo).
+
+Each .cu is compiled to its own object (in parallel, re-done only when the file or a header changed) and linked."""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libsad_b200.so")
-SOURCES = ["api.cu", "conv_umma.cu", "conv_umma2.cu", "conv_rows.cu", "block_rows.cu", "stem_fused.cu", "frontend.cu", "ingest.cu", "head.cu"]
-HEADERS = ["conv_umma.h", "frontend.h", "ingest.h", "ingest_taps.h", "head.h", "stem_fused.h", "ptx.cuh", "fft2048.cuh", os.path.join("..", "..", "include", "sad_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+SOURCES = ["api.cu", "conv_umma.cu", "conv_umma2.cu", "conv_rows.cu", "block_rows.cu", "stem_fused.cu", "frontend.cu",
+           "ingest.cu", "head.cu", "synth.cu"]
+HEADERS = ["conv_umma.h", "frontend.h", "ingest.h", "ingest_taps.h", "head.h", "stem_fused.h", "ptx.cuh", "fft2048.cuh",
+           "synth.h", os.path.join("..", "..", "include", "sad_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC"]
+
+
+def _newest_header() -> float:
+    return max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
 
 
 def _stale() -> bool:
@@ -21,14 +30,28 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile if sources are newer than the library; returns the library path."""
+    """Compile what is newer than its object, link if anything changed; returns the library path."""
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True)
+    os.makedirs(OBJ, exist_ok=True)
+    hdr_t = _newest_header()
+    jobs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(OBJ, s[:-3] + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append([nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj])
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        list(ex.map(run, jobs))
+    run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", LIB] +
+        [os.path.join(OBJ, s[:-3] + ".o") for s in SOURCES])
     return LIB
 
 

@@ -22,6 +22,7 @@
 #include "frontend.h"
 #include "head.h"
 #include "stem_fused.h"
+#include "synth.h"
 
 namespace {
 
@@ -257,6 +258,9 @@ struct sad_ctx {
     float* d_bias_fused[kMaxConvs] = {nullptr}; // [H][Cout] = bias(conv2) + bias(downsample) for the conv2 that absorbs it
     int rows_mode = 1;                  // layer1 row-stationary kernel (conv_rows.cu): 0 = use the generic kernel instead
 
+    // one workspace per context: every call waits for the previous call's last kernel, whatever stream it ran on
+    cudaEvent_t ev_last = nullptr;
+
     // end-to-end path
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr};
@@ -295,6 +299,39 @@ int fail(sad_ctx* c, int code, const char* fmt, ...) {
             return fail(ctx, SAD_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
                         __LINE__);                                                                        \
     } while (0)
+
+// Entry points run on the context's device and leave the caller's current device untouched (PyTorch reads the
+// runtime's current device; a GC-time sad_destroy of an engine on another GPU must not flip it).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1;   // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ON_DEVICE(ctx)                 \
+    DeviceGuard dev_guard__((ctx)->device); \
+    CU_OK(ctx, dev_guard__.err)
+
+// Orders a call that touches the context's workspace after the previous such call (any stream) and publishes its
+// own completion for the next one.
+struct WorkspaceOrder {
+    sad_ctx* c;
+    cudaStream_t st;
+    WorkspaceOrder(sad_ctx* c_, cudaStream_t st_) : c(c_), st(st_) {
+        if (c->ev_last) cudaStreamWaitEvent(st, c->ev_last, 0);
+    }
+    ~WorkspaceOrder() {
+        if (c->ev_last) cudaEventRecord(c->ev_last, st);
+    }
+};
 
 template <typename T>
 cudaError_t dalloc(T** p, size_t n) {
@@ -743,7 +780,7 @@ int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const c
     if (const char* e = getenv("SAD_TR128")) c->tr128 = atoi(e);
     if (const char* e = getenv("SAD_2CTA")) c->two_cta = atoi(e);
     *out = c;   // returned even on failure so the caller can read sad_last_error, then sad_destroy
-    CU_OK(c, cudaSetDevice(device));
+    ON_DEVICE(c);
 
     const long long H = n_heads, Bc = max_batch, HB = H * Bc;
     const int n_convs = static_cast<int>(net->convs.size());
@@ -819,6 +856,7 @@ int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const c
             return SAD_ECUDA;
     }
 
+    CU_OK(c, cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming));
     CU_OK(c, cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     CU_OK(c, cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
@@ -830,7 +868,7 @@ int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const c
 
 int sad_destroy(sad_ctx* c) {
     if (!c) return SAD_OK;
-    cudaSetDevice(c->device);
+    DeviceGuard dev_guard__(c->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < kMaxConvs; ++i) {
         cudaFree(c->d_w[i]);
@@ -849,6 +887,7 @@ int sad_destroy(sad_ctx* c) {
     }
     prof_collect(c);
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
+    if (c->ev_last) cudaEventDestroy(c->ev_last);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     cudaGetLastError();
@@ -858,7 +897,7 @@ int sad_destroy(sad_ctx* c) {
 
 int sad_set_frontend_constants(sad_ctx* c, const float* host_window, const float* host_mel_fb) {
     if (!c) return SAD_EINVAL;
-    CU_OK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     if (host_window) CU_OK(c, cudaMemcpy(c->d_window, host_window, 2048 * sizeof(float), cudaMemcpyHostToDevice));
     if (host_mel_fb) return upload_mel(c, host_mel_fb);
     return SAD_OK;
@@ -874,7 +913,7 @@ int sad_load_weights(sad_ctx* c, int head, const float* const* T, int n_tensors)
                     n_tensors);
     for (int i = 0; i < n_tensors; ++i)
         if (!T[i]) return fail(c, SAD_EINVAL, "tensor %d (%s) is null", i, net.tensors[i].name.c_str());
-    CU_OK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     std::vector<double> s, t;
     std::vector<std::vector<float>> host_bias(n_convs);
     int ti = 0;
@@ -974,8 +1013,9 @@ int sad_frontend_logmel(sad_ctx* c, const float* pcm, int B, float* logmel_db, f
     if (!c) return SAD_EINVAL;
     if (B == 0) return SAD_OK;   // an empty batch is a no-op (its buffers may be null)
     if (!pcm || B < 0) return fail(c, SAD_EINVAL, "null pcm or negative batch");
-    CU_OK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    WorkspaceOrder ws_order__(c, st);
     for (int b0 = 0; b0 < B; b0 += c->Bc) {
         const int nb = B - b0 < c->Bc ? B - b0 : c->Bc;
         CU_OK(c, sad::frontend_logmel_launch(pcm + static_cast<size_t>(b0) * SAD_SEGMENT_SAMPLES, nb, c->d_window, c->d_mel,
@@ -993,8 +1033,9 @@ int sad_frontend_image(sad_ctx* c, const float* pcm, int B, float* image, void* 
     if (!c) return SAD_EINVAL;
     if (B == 0) return SAD_OK;
     if (!pcm || !image || B < 0) return fail(c, SAD_EINVAL, "null buffer or negative batch");
-    CU_OK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    WorkspaceOrder ws_order__(c, st);
     for (int b0 = 0; b0 < B; b0 += c->Bc) {
         const int nb = B - b0 < c->Bc ? B - b0 : c->Bc;
         CU_OK(c, sad::frontend_logmel_launch(pcm + static_cast<size_t>(b0) * SAD_SEGMENT_SAMPLES, nb, c->d_window, c->d_mel,
@@ -1014,8 +1055,9 @@ int sad_ingest(sad_ctx* c, const void* pcm, int sample_format, long long n_frame
         (sample_format != SAD_PCM_S16 && sample_format != SAD_PCM_F32))
         return fail(c, SAD_EINVAL, "bad ingest arguments (frames %lld, channels %d, rate %d, format %d)", n_frames, n_channels,
                     sr_in, sample_format);
-    CU_OK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    WorkspaceOrder ws_order__(c, st);
     long long n_real = 0;
     const long long out_len = sad::ingest_length(n_frames, sr_in, &n_real);
     if (sr_in == sad::kIngestRate) {
@@ -1030,7 +1072,7 @@ int sad_ingest(sad_ctx* c, const void* pcm, int sample_format, long long n_frame
         if (!sad::build_resample_taps(sr_in, &plan, &first, &w) || sad::ingest_smem_bytes(plan) > 48 * 1024)
             return fail(c, SAD_EINVAL, "sample rate %d: ratio to 32000 not supported (reduced rates %d:%d)", sr_in,
                         plan.orig_f, plan.new_f);
-        CU_OK(c, cudaStreamSynchronize(st));                     // a previous ingest may still read the old tables
+        CU_OK(c, cudaEventSynchronize(c->ev_last));              // a previous ingest (on any stream) may still read the old tables
         cudaFree(c->d_tap_first);
         cudaFree(c->d_tap_w);
         c->d_tap_first = nullptr;
@@ -1054,7 +1096,7 @@ int sad_slice_gate(sad_ctx* c, const float* wf, long long n_samples, long long w
     if (!c || !wf || !keep) return SAD_EINVAL;
     const long long n = sad_slice_count(n_samples, window, hop);
     if (n < 0) return fail(c, SAD_EINVAL, "bad window/hop");
-    CU_OK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     CU_OK(c, sad::slice_gate_launch(wf, n, window, hop, thr, keep, static_cast<cudaStream_t>(stream), &c->launches));
     return SAD_OK;
 }
@@ -1062,7 +1104,7 @@ int sad_slice_gate(sad_ctx* c, const float* wf, long long n_samples, long long w
 int sad_gather_windows(sad_ctx* c, const float* wf, const long long* starts, int n_kept, long long window, float* dst,
                        void* stream) {
     if (!c || !wf || !starts || !dst || n_kept < 0) return SAD_EINVAL;
-    CU_OK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     CU_OK(c, sad::gather_windows_launch(wf, starts, n_kept, window, dst, static_cast<cudaStream_t>(stream), &c->launches));
     return SAD_OK;
 }
@@ -1072,8 +1114,9 @@ int sad_forward(sad_ctx* c, const float* pcm, int B, float thr, float* logits, f
     if (!c) return SAD_EINVAL;
     if (B == 0) return SAD_OK;
     if (!pcm || B < 0) return fail(c, SAD_EINVAL, "null pcm or negative batch");
-    CU_OK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    WorkspaceOrder ws_order__(c, st);
     const int n1 = c->H + 1;
     for (int b0 = 0; b0 < B; b0 += c->Bc) {
         const int nb = B - b0 < c->Bc ? B - b0 : c->Bc;
@@ -1090,7 +1133,7 @@ int sad_forward_images(sad_ctx* c, const float* x, int B, float thr, float* logi
     if (!c) return SAD_EINVAL;
     if (B == 0) return SAD_OK;
     if (!x || B < 0) return fail(c, SAD_EINVAL, "null images or negative batch");
-    CU_OK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     if (!c->stem3_ready) {
         CU_OK(c, dalloc(&c->d_A3, static_cast<size_t>(c->Bc) * 65536 * 192));
         CU_OK(c, dalloc(&c->d_stem, static_cast<size_t>(c->H) * c->Bc * 65536 * 64));
@@ -1098,6 +1141,7 @@ int sad_forward_images(sad_ctx* c, const float* x, int B, float thr, float* logi
         c->stem3_ready = true;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    WorkspaceOrder ws_order__(c, st);
     const int n1 = c->H + 1;
     for (int b0 = 0; b0 < B; b0 += c->Bc) {
         const int nb = B - b0 < c->Bc ? B - b0 : c->Bc;
@@ -1114,7 +1158,7 @@ int sad_forward_host(sad_ctx* c, const float* pcm_host, int B, float thr, float*
     if (!c) return SAD_EINVAL;
     if (B == 0) return SAD_OK;
     if (!pcm_host || B < 0) return fail(c, SAD_EINVAL, "null pcm or negative batch");
-    CU_OK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     const size_t seg = SAD_SEGMENT_SAMPLES;
     const int n1 = c->H + 1;
     if (!c->d_pcm[0]) {
@@ -1135,6 +1179,7 @@ int sad_forward_host(sad_ctx* c, const float* pcm_host, int B, float thr, float*
         CU_OK(c, dalloc(&c->d_res_labels, static_cast<size_t>(B)));
         c->res_capacity = B;
     }
+    WorkspaceOrder ws_order__(c, c->s_comp);
     // is the caller's buffer page-locked?  then DMA straight from it, otherwise stage through pinned memory
     cudaPointerAttributes attr;
     bool pinned = cudaPointerGetAttributes(&attr, pcm_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
@@ -1179,7 +1224,7 @@ int sad_clip_reduce(sad_ctx* c, const float* probs, const int32_t* clip_id, int 
     if (n_clips == 0) return SAD_OK;
     if (!clip_probs || !clip_label || B < 0 || n_clips < 0 || (B > 0 && (!probs || !clip_id)))
         return fail(c, SAD_EINVAL, "null buffer or negative count");
-    CU_OK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     CU_OK(c, sad::clip_reduce_launch(probs, clip_id, B, n_clips, c->H, thr, clip_probs, clip_label,
                                      static_cast<cudaStream_t>(stream), &c->launches));
     return SAD_OK;
@@ -1192,7 +1237,7 @@ int sad_debug_conv(sad_ctx* c, int head, int layer, const void* in, const void* 
         return fail(c, SAD_EINVAL, "layer %d out of range [1,%d)", layer, static_cast<int>(c->net->convs.size()));
     if (head < 0 || head >= c->H) return fail(c, SAD_EINVAL, "head out of range");
     if (!c->loaded[head]) return fail(c, SAD_ESTATE, "weights of head %d not loaded", head);
-    CU_OK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     sad::ConvLaunch L;
     if (!make_launch(c, &L, layer, static_cast<const bf16*>(in), static_cast<const bf16*>(residual), static_cast<bf16*>(out),
                      B, relu))
@@ -1220,7 +1265,7 @@ int sad_debug_block(sad_ctx* c, int head, int layer, const void* in, void* out, 
         return fail(c, SAD_EINVAL, "convs %d,%d are not a 64-channel 128x128 block", layer, layer + 1);
     if (head < 0 || head >= c->H) return fail(c, SAD_EINVAL, "head out of range");
     if (!c->loaded[head]) return fail(c, SAD_ESTATE, "weights of head %d not loaded", head);
-    CU_OK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     sad::ConvLaunch L;
     if (!make_launch(c, &L, layer, static_cast<const bf16*>(in), static_cast<const bf16*>(in), static_cast<bf16*>(out), B, 1, -1,
                      nullptr, layer + 1))
@@ -1238,9 +1283,20 @@ int sad_debug_block(sad_ctx* c, int head, int layer, const void* in, void* out, 
     return SAD_OK;
 }
 
+int sad_synth_segments(sad_ctx* c, float* out, long long first, int n, unsigned long long seed, void* stream) {
+    if (n == 0) return SAD_OK;
+    if (!out || n < 0 || first < 0) return c ? fail(c, SAD_EINVAL, "null buffer or negative count") : SAD_EINVAL;
+    if (!c)   // no context: the calling thread's current device
+        return sad::synth_segments_launch(out, first, n, seed, static_cast<cudaStream_t>(stream), nullptr) == cudaSuccess
+                   ? SAD_OK : SAD_ECUDA;
+    ON_DEVICE(c);
+    CU_OK(c, sad::synth_segments_launch(out, first, n, seed, static_cast<cudaStream_t>(stream), &c->launches));
+    return SAD_OK;
+}
+
 int sad_profile_enable(sad_ctx* c, int on) {
     if (!c) return SAD_EINVAL;
-    cudaSetDevice(c->device);
+    ON_DEVICE(c);
     prof_collect(c);
     c->prof_on = on != 0;
     if (on) {
@@ -1254,7 +1310,7 @@ int sad_profile_enable(sad_ctx* c, int on) {
 
 int sad_profile_read(sad_ctx* c, double* ms_by_kind, long long* launches_by_kind) {
     if (!c) return SAD_EINVAL;
-    cudaSetDevice(c->device);
+    ON_DEVICE(c);
     prof_collect(c);   // synchronises on the recorded events
     for (int i = 0; i < SAD_PROF_KINDS; ++i) {
         if (ms_by_kind) ms_by_kind[i] = c->prof_ms[i];
@@ -1267,8 +1323,9 @@ int sad_debug_stem(sad_ctx* c, const float* pcm, int B, void* out, void* stream)
     if (!c || !pcm || !out || B < 1 || B > c->Bc) return SAD_EINVAL;
     for (int h = 0; h < c->H; ++h)
         if (!c->loaded[h]) return fail(c, SAD_ESTATE, "weights of head %d not loaded", h);
-    CU_OK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    WorkspaceOrder ws_order__(c, st);
     CU_OK(c, sad::frontend_logmel_launch(pcm, B, c->d_window, c->d_mel, c->d_db, c->d_segmax, nullptr, c->d_musig, st,
                                          &c->launches));
     CU_OK(c, sad::image_launch_bf16(c->d_db, c->d_musig, c->d_resize, c->d_img, B, st, &c->launches));
@@ -1283,6 +1340,8 @@ int sad_debug_stem(sad_ctx* c, const float* pcm, int B, void* out, void* stream)
 
 long long sad_debug_read(sad_ctx* c, int which, void* dst, long long capacity, void* stream) {
     if (!c || !dst) return SAD_EINVAL;
+    ON_DEVICE(c);
+    WorkspaceOrder ws_order__(c, static_cast<cudaStream_t>(stream));
     const long long B = c->last_B, H = c->H;
     const void* src = nullptr;
     long long bytes = 0;

@@ -1,5 +1,6 @@
 // Host-visible launch description of the tcgen05 implicit-GEMM convolution (conv_umma.cu).
 #pragma once
+#include <atomic>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -38,14 +39,15 @@ struct alignas(64) ConvLaunch {
 // non-type template parameter so every kernel gets its own flags (kernels with the same signature share one TYPE).
 template <auto Kernel>
 inline cudaError_t ensure_dynamic_smem(int bytes) {
-    static bool done[64] = {false};
+    // per-device flag; atomics because two contexts may launch from two host threads (setting the attribute twice is harmless)
+    static std::atomic<bool> done[64];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64 || !done[dev]) {
+    if (dev < 0 || dev >= 64 || !done[dev].load(std::memory_order_acquire)) {
         e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) done[dev] = true;
+        if (dev >= 0 && dev < 64) done[dev].store(true, std::memory_order_release);
     }
     return cudaSuccess;
 }

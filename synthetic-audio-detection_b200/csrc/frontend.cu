@@ -9,6 +9,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "fft2048.cuh"
 #include "frontend.h"
 
@@ -311,26 +313,41 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __res
 __global__ void __launch_bounds__(256) slice_gate_kernel(const float* __restrict__ wf, long long window, long long hop,
                                                          float thr, uint8_t* __restrict__ keep) {
     const float* x = wf + static_cast<long long>(blockIdx.x) * hop;
+    // torch's max propagates NaN and `NaN < thr` is False (IR:186): a window holding a NaN is KEPT.  fmaxf drops NaNs,
+    // so they are tracked separately.
     float m = 0.f;
-    for (long long i = threadIdx.x; i < window; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+    int nan = 0;
+    for (long long i = threadIdx.x; i < window; i += blockDim.x) {
+        const float v = fabsf(x[i]);
+        nan |= (v != v);
+        m = fmaxf(m, v);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    nan = __any_sync(0xffffffffu, nan);
     __shared__ float red[8];
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __shared__ int red_nan[8];
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5] = m;
+        red_nan[threadIdx.x >> 5] = nan;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
-        keep[blockIdx.x] = (m < thr) ? 0 : 1;
+        for (int i = 1; i < 8; ++i) {
+            m = fmaxf(m, red[i]);
+            nan |= red_nan[i];
+        }
+        keep[blockIdx.x] = (!nan && m < thr) ? 0 : 1;
     }
 }
 
 __global__ void __launch_bounds__(256) gather_windows_kernel(const float* __restrict__ wf, const long long* __restrict__ starts,
                                                              long long window, float* __restrict__ dst) {
-    const float* x = wf + starts[blockIdx.y];
-    float* d = dst + static_cast<long long>(blockIdx.y) * window;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < window;
-         i += static_cast<long long>(gridDim.x) * blockDim.x)
-        d[i] = x[i];
+    // window index on gridDim.x (2^31-1 blocks): a long clip at a small hop has more than 65535 kept windows
+    const long long w = blockIdx.x / 32, part = blockIdx.x % 32;
+    const float* x = wf + starts[w];
+    float* d = dst + w * window;
+    for (long long i = part * blockDim.x + threadIdx.x; i < window; i += 32LL * blockDim.x) d[i] = x[i];
 }
 
 __global__ void fill_u32_kernel(unsigned* p, unsigned v, int n) {
@@ -345,15 +362,15 @@ size_t stft_smem_bytes() { return sizeof(StftSmem); }
 cudaError_t frontend_logmel_launch(const float* pcm, int B, const float* window, const MelTable* mel, float* db_work,
                                    unsigned* segmax, float* out_db, float* mu_sigma, cudaStream_t stream, long long* launches) {
     {
-        static bool done[64] = {false};
+        static std::atomic<bool> done[64];   // per device; two contexts may launch from two host threads
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        if (dev < 0 || dev >= 64 || !done[dev]) {
+        if (dev < 0 || dev >= 64 || !done[dev].load(std::memory_order_acquire)) {
             e = cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(sizeof(StftSmem)));
             if (e != cudaSuccess) return e;
-            if (dev >= 0 && dev < 64) done[dev] = true;
+            if (dev >= 0 && dev < 64) done[dev].store(true, std::memory_order_release);
         }
     }
     fill_u32_kernel<<<(B + 255) / 256, 256, 0, stream>>>(segmax, 0u, B);   // 0 orders below every float
@@ -398,7 +415,7 @@ cudaError_t slice_gate_launch(const float* wf, long long n_windows, long long wi
 cudaError_t gather_windows_launch(const float* wf, const long long* starts, int n_kept, long long window, float* dst,
                                   cudaStream_t stream, long long* launches) {
     if (n_kept <= 0) return cudaSuccess;
-    gather_windows_kernel<<<dim3(32, n_kept), 256, 0, stream>>>(wf, starts, window, dst);
+    gather_windows_kernel<<<static_cast<unsigned>(n_kept) * 32u, 256, 0, stream>>>(wf, starts, window, dst);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

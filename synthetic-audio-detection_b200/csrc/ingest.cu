@@ -44,7 +44,9 @@ __device__ __forceinline__ float pcm_to_float<float>(float v) { return v; }
 // mean over channels in channel order, as ATen's sum-then-divide on a [C, T] tensor
 template <typename T>
 __device__ __forceinline__ float mono_mix(const T* __restrict__ pcm, long long frame, int channels) {
-    if (channels == 2) {                                   // one aligned load per stereo frame; x/2 == x*0.5 exactly
+    // one load per stereo frame when the stream's base allows it (a view that starts at an odd element is only
+    // element aligned: the C ABI states no alignment requirement); x/2 == x*0.5 exactly
+    if (channels == 2 && (reinterpret_cast<uintptr_t>(pcm) & (2 * sizeof(T) - 1)) == 0) {
         if constexpr (sizeof(T) == 2) {
             const short2 v = reinterpret_cast<const short2*>(pcm)[frame];
             return (static_cast<float>(v.x) * (1.0f / 32768.0f) + static_cast<float>(v.y) * (1.0f / 32768.0f)) * 0.5f;

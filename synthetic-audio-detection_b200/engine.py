@@ -134,6 +134,13 @@ class Engine:
                    "sad_frontend_logmel")
         return db, ms
 
+    def logmel_into(self, pcm: torch.Tensor, db: torch.Tensor, mu_sigma: Optional[torch.Tensor] = None):
+        """As logmel(), into caller-provided CUDA buffers (db [B,128,251] fp32, mu_sigma [B,2] fp32 or None)."""
+        self._check(pcm, (SEGMENT,))
+        self._check(db, (128, 251))
+        _lib.check(self.ctx, self.lib.sad_frontend_logmel(self.ctx, _ptr(pcm), pcm.shape[0], _ptr(db), _ptr(mu_sigma),
+                                                          _stream(self.device)), "sad_frontend_logmel")
+
     def image(self, pcm: torch.Tensor) -> torch.Tensor:
         self._check(pcm, (SEGMENT,))
         B = pcm.shape[0]

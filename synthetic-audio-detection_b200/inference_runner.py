@@ -44,8 +44,11 @@ def _cuda_device(device) -> torch.device:
     return torch.device("cuda", d.index if d.index is not None else torch.cuda.current_device())
 
 
-def _state_version(module: nn.Module) -> int:
-    return sum(int(t._version) + id(t) % 1009 for t in list(module.parameters()) + list(module.buffers()))
+def _state_version(module: nn.Module):
+    """Engine-cache key: identity, storage and in-place version of every parameter / buffer.  `p.data = ...` swaps the
+    storage (data_ptr changes), in-place ops bump `_version`; writes through `.data` (`p.data.copy_()`) change neither --
+    call `invalidate()` after those (load_state_dict does it through a hook)."""
+    return tuple((id(t), t.data_ptr(), int(t._version)) for t in list(module.parameters()) + list(module.buffers()))
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -66,6 +69,12 @@ class BinaryClassifier(nn.Module):
         self._engine: Optional[Engine] = None
         self._engine_key = None
         self.base._features_fn = self._features
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
+
+    def invalidate(self) -> None:
+        """Drop the folded weights held on the device; the next forward re-reads the live parameters (needed after
+        writes the cache key cannot see, e.g. `p.data.copy_(...)`)."""
+        self._engine_key = None
 
     def _own_engine(self, device) -> Engine:
         key = (str(device), _state_version(self))
@@ -107,6 +116,14 @@ class ModularMultiHeadClassifier(nn.Module):
         self._engine: Optional[Engine] = None
         self._engine_key = None
         self.max_batch = 64
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
+
+    def invalidate(self) -> None:
+        """Drop the folded weights held on the device; the next forward re-reads the live parameters."""
+        self._engine_key = None
+        for m in self.sub_models:
+            if hasattr(m, "invalidate"):
+                m.invalidate()
 
     def engine(self, device) -> Engine:
         """The sad_ctx holding this ensemble's folded weights (rebuilt when parameters change)."""

@@ -96,3 +96,64 @@ def test_profile_counters():
     assert e.launches - n0 == 3 + 1 + 1 + 14 + 2
     assert sum(1 for v in n[:40] if v) == 15 and n[e.PROF_FRONTEND] == 1 and n[e.PROF_HEAD] == 1
     assert all(v >= 0 for v in ms) and sum(ms) > 0
+
+
+def test_mixed_streams_on_one_context_do_not_race():
+    """One context = one workspace: a call on the caller's stream followed, without a sync, by the host entry (which runs
+    on the context's internal streams) and by a call on another torch stream must all see their own inputs
+    (the library orders each call after the previous one on that context with an event)."""
+    e = G.engine(2)
+    xa = FX.synth_segments(8, first=940).cuda()
+    xb = FX.synth_segments(8, first=948)
+    ref_a = e.forward_pcm(xa, 0.5)[0].clone()
+    ref_b = e.forward_host(xb, 0.5)[0].clone()
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    for _ in range(3):
+        a = e.forward_pcm(xa, 0.5)[0]                     # current stream, not synchronised ...
+        b = e.forward_host(xb, 0.5)[0]                    # ... internal streams
+        with torch.cuda.stream(s):
+            c = e.forward_pcm(xa, 0.5)[0]                 # ... a third stream
+        d = e.forward_pcm(xb.cuda(), 0.5)[0]
+        torch.cuda.synchronize()
+        assert torch.equal(a, ref_a) and torch.equal(b, ref_b) and torch.equal(c, ref_a) and torch.equal(d.cpu(), ref_b)
+
+
+def test_current_device_is_left_alone():
+    """Every entry point restores the caller's current CUDA device (matters with several GPUs in one process; on a
+    one-GPU box this only checks that nothing changes)."""
+    before = torch.cuda.current_device()
+    e = Engine(1, torch.device("cuda", torch.cuda.device_count() - 1), max_batch=2)
+    x = torch.zeros(1, 128000, device=e.device)
+    e.logmel(x)
+    e.close()
+    assert torch.cuda.current_device() == before
+
+
+def test_nan_window_is_kept_and_many_windows_gather():
+    """slice gate: `piece.abs().max() < thr` is False for a window holding a NaN (IR:186), so it is kept; gather: more
+    kept windows than gridDim.y allows (65535) -- the reference has no such limit."""
+    e = G.engine(2)
+    wf = torch.zeros(3 * 1000, device="cuda")
+    wf[1500] = float("nan")
+    keep = e.slice_gate(wf, 1000, 1000, 1e-3)
+    assert keep.cpu().tolist() == [0, 1, 0]
+    n, window = 70000, 64
+    src = torch.arange(n + window, device="cuda", dtype=torch.float32)
+    starts = torch.arange(n, device="cuda", dtype=torch.int64)
+    out = e.gather_windows(src, starts, window)
+    want = src.unfold(0, window, 1)[:n]
+    assert torch.equal(out, want)
+
+
+def test_ingest_accepts_element_aligned_stereo_views():
+    """A stereo stream that starts at an odd element is only element aligned (not frame aligned); the C ABI states no
+    alignment requirement."""
+    e = G.engine(2)
+    for dtype in (torch.float32, torch.int16):
+        base = (torch.randn(2 * 5000 + 1, device="cuda") * 8000).to(dtype) if dtype == torch.int16 else \
+            torch.randn(2 * 5000 + 1, device="cuda") * 0.2
+        view = base[1:].view(5000, 2)                              # storage offset 1 element
+        got = e.ingest(view, 32000)
+        want = e.ingest(view.clone(), 32000)                       # the clone is allocation aligned
+        assert torch.equal(got, want)

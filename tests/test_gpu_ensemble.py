@@ -95,8 +95,11 @@ def test_decisions_and_logits_on_corpus():
           f"(cal {agree[:FX.N_CAL].mean():.4f}, held-out {agree[FX.N_CAL:].mean():.4f}); "
           f"min margin {margin.min():.4f}; disagreements' margins {margin[~agree]}")
     assert d.max() <= LOGIT_TOL
+    # v1 fixture: only the 32 calibration segments carry margin; held-out logits hug the threshold, so here a flip is
+    # only required to sit inside the logit tolerance band.  The >= 99.9% decision criterion is asserted (strictly) on
+    # 4096 / 2048 / 2048 held-out segments of the class-structured corpus in tests/test_gpu_decisions.py.
     assert np.all(margin[~agree] <= LOGIT_TOL), "a decision flipped outside the logit tolerance band"
-    assert agree.mean() >= 0.999 or np.all(margin[~agree] <= LOGIT_TOL)
+    assert agree[:FX.N_CAL].mean() == 1.0
     # device vs the CPU emulation of the device data path (localises kernel bugs, not a parity claim)
     emu = E.ensemble_bf16(img3[:8, :1], sd)
     print("device vs bf16 emulation: max |diff|", (lo[:8] - emu).abs().max().item())

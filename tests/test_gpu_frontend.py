@@ -90,3 +90,27 @@ def test_slicing_gate_bit_exact():
                 got = e.gather_windows(wf.cuda(), st, window).cpu()
                 assert torch.equal(got[0], wf[starts[keep][0]:starts[keep][0] + window])
                 assert torch.equal(got[-1], wf[starts[keep][-1]:starts[keep][-1] + window])
+
+
+def test_logmel_and_image_vs_reference_golden_256_segments():
+    """BASELINE.json configs[1]: a >= 256-segment parity subset of the front end against the LIVE reference's transforms
+    (tests/golden/frontend_256.npz: strided log-mel samples, mean / std / max / sum per segment, strided image samples)."""
+    g = G.golden("frontend_256.npz")
+    n, first, ms_ = g["mu"].shape[0], int(g["first"]), int(g["mel_stride"])
+    assert n >= 256
+    x = FX.synth_segments(n, first=first).cuda()
+    e = G.engine(2, max_batch=64)
+    db, ms = e.logmel(x)
+    img = e.image(x)
+    db = db.cpu().numpy()
+    got = db[:, ::ms_][:, :, g["frames"]]
+    err = G.rel_db_err(got, g["logmel_sample"])
+    print(f"{n} segments vs the reference: log-mel max tol-units {err.max():.3f} p99.99 {np.quantile(err, 0.9999):.3f}; "
+          f"|mu diff| {np.abs(ms[:, 0].cpu().numpy() - g['mu']).max():.2e} |sigma diff| "
+          f"{np.abs(ms[:, 1].cpu().numpy() - g['sigma']).max():.2e}")
+    assert err.max() <= 1.0
+    np.testing.assert_allclose(ms[:, 0].cpu().numpy(), g["mu"], rtol=0, atol=3e-5)
+    np.testing.assert_allclose(ms[:, 1].cpu().numpy(), g["sigma"], rtol=0, atol=3e-5)
+    np.testing.assert_allclose(db.max(axis=(1, 2)), g["db_max"], rtol=0, atol=1e-4 * np.maximum(np.abs(g["db_max"]), 1))
+    np.testing.assert_allclose(db.astype(np.float64).sum(axis=(1, 2)), g["db_sum"], rtol=0, atol=32128 * 2e-4)
+    np.testing.assert_allclose(img.cpu().numpy()[:, ::37, ::41], g["image_sample"], rtol=0, atol=5e-4)

@@ -29,7 +29,7 @@ def _fake_probs(s_lo, s_hi, n1):
     return allp[s_lo:s_hi]
 
 
-def _worker(rank, world, port, clip_lengths, n1, out_dir):
+def _worker(rank, world, port, clip_lengths, n1, out_dir, chunk=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -47,18 +47,23 @@ def _worker(rank, world, port, clip_lengths, n1, out_dir):
         cp, cl = R.clip_aggregate(probs.numpy(), cid.numpy(), n, 0.5)
         return torch.from_numpy(cp), torch.from_numpy(cl)
 
-    allp, alll, seg = S.run_sharded(clip_lengths, fetch, forward, clip_reduce)
+    allp, alll, seg = S.run_sharded(clip_lengths, fetch, forward, clip_reduce, chunk=chunk)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), p=allp.numpy(), l=alll.numpy(), nseg=len(seg))
     dist.destroy_process_group()
 
 
-def test_world2_gloo_gathers_all_clips(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("chunk", [None, 2])
+def test_world2_gloo_gathers_all_clips(tmp_path, chunk):
+    """chunk=2: the shard is streamed in pieces that cut across clip boundaries (the corpus driver's mode)."""
     clip_lengths = [3, 1, 4, 1, 5, 9, 2]           # 7 clips -> rank 0 owns 4, rank 1 owns 3 (ragged)
     n1 = 4
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(2, port, clip_lengths, n1, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, clip_lengths, n1, str(tmp_path), chunk), nprocs=2, join=True)
     total = sum(clip_lengths)
     probs = _fake_probs(0, total, n1).numpy()
     cid = np.repeat(np.arange(len(clip_lengths)), clip_lengths)

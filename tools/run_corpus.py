@@ -1,0 +1,72 @@
+#!/usr/bin/env python3
+"""BASELINE.json configs[4]: the 3.8 M-segment synthetic corpus (118 750 ragged clips) sharded over N GPUs with one
+per-clip gather.
+
+    python tools/run_corpus.py --clips 118750                      (1 GPU)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \\
+        tools/run_corpus.py --clips 118750 --out gpurun_out/corpus_n8.json
+
+Prints (rank 0) one JSON line: segments/s over all ranks (device time, max over ranks), the gather time, and the sha256
+of the per-clip probabilities + labels -- equal digests across N prove bit-identical per-clip decisions."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--clips", type=int, default=118750)
+    ap.add_argument("--mean-segments", type=int, default=32)
+    ap.add_argument("--heads", type=int, default=6)
+    ap.add_argument("--chunk", type=int, default=2048, help="segments generated + processed per pass")
+    ap.add_argument("--max-batch", type=int, default=128)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sad_b200 import corpus as CO
+    from sad_b200 import synthetic as S
+    from sad_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Engine(args.heads, dev, max_batch=args.max_batch)
+    eng.load_merged_state_dict(S.random_merged_state_dict(args.heads, seed=0))
+    lengths = CO.clip_lengths(args.clips, args.mean_segments)
+    warm = CO.clip_lengths(8 * world, args.mean_segments)          # warm-up: kernels, NCCL communicator
+    CO.run_corpus(eng, warm, chunk=args.chunk)
+    r = CO.run_corpus(eng, lengths, chunk=args.chunk)
+    total = int(lengths.sum())
+    labels = r["clip_labels"].cpu().numpy()
+    out = {"config": "BASELINE.json configs[4]: synthetic corpus, %d clips (%d..%d segments, ragged), %d segments, %d heads"
+                     % (args.clips, int(lengths.min()), int(lengths.max()), total, args.heads),
+           "n_gpus": world, "segments": total, "clips": int(args.clips), "ms": r["ms"],
+           "segments_per_s": total / (r["ms"] / 1e3), "gather_ms": r["gather_ms"],
+           "digest": CO.digest(r["clip_probs"], r["clip_labels"]),
+           "label_histogram": np.bincount(labels[labels >= 0], minlength=args.heads + 1).tolist(),
+           "rank_segments": int(r["segment_labels"].shape[0])}
+    if rank == 0:
+        print(json.dumps(out))
+        if args.out:
+            os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+            with open(args.out, "w") as f:
+                json.dump(out, f)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
