@@ -60,6 +60,10 @@ const char* sad_backbone(const sad_ctx* ctx);
 int sad_destroy(sad_ctx* ctx);
 const char* sad_last_error(const sad_ctx* ctx);
 const char* sad_version(void);
+/* "bf16" (libsad_b200.so, the default build) or "fp16" (libsad_b200_f16.so, built with -DSAD_ACT_F16): the element type of
+ * activations and conv weights -- the layout every `bf16` in this header refers to.  Same tensor-core rate; fp16 keeps 3
+ * more mantissa bits and is what the 50+-conv Bottleneck backbones need to meet the 2e-2 logit bound.              */
+const char* sad_act_dtype(void);
 
 /* ---- weights: replaces load_merged_model's per-head rebuild (inference_runner.py:101-114) ----- */
 /* The library describes the fp32 tensors it needs for ONE BinaryClassifier (inference_runner.py:28-51),

@@ -3,11 +3,12 @@
 Two places can hold them:
   * ``/root/reference/modular/source`` -- the read-only sources, present only in the build container
     (``make_golden.py``, CPU tests that re-check the restatement against the live reference);
-  * ``oracle/_ref/*.pyc`` -- the same modules byte-compiled by ``oracle/build_ref.py`` (git-ignored binaries that
+  * ``oracle/_ref/*.pyc.bin`` -- the same modules byte-compiled by ``oracle/build_ref.py`` (git-ignored binaries that
     travel to the GPU box), used by ``bench.py``'s reference arm / ``cpu_baseline`` leg there.
 Nothing in the product path imports this.
 """
 import importlib
+import importlib.util
 import os
 import sys
 
@@ -21,13 +22,29 @@ def available() -> bool:
 
 
 def compiled_available() -> bool:
-    return all(os.path.isfile(os.path.join(REFERENCE_BIN, m + ".pyc")) for m in ("inference_runner", "model_merger"))
+    return all(os.path.isfile(os.path.join(REFERENCE_BIN, m + ".pyc.bin")) for m in ("inference_runner", "model_merger"))
+
+
+def _load_compiled(name: str):
+    """Execute a byte-compiled module (a .pyc: 16-byte header + marshalled code object) under its own name."""
+    import marshal
+    import types
+    path = os.path.join(REFERENCE_BIN, name + ".pyc.bin")
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:4] != importlib.util.MAGIC_NUMBER:
+        raise RuntimeError(f"{path} was compiled by another Python version; re-run `python -m oracle.build_ref`")
+    mod = types.ModuleType(name)
+    mod.__file__ = path
+    sys.modules[name] = mod
+    exec(marshal.loads(data[16:]), mod.__dict__)
+    return mod
 
 
 def load(allow_compiled: bool = False):
     """Return ``(inference_runner, model_merger)`` reference modules, imported under their own names with the ``timm``
     shim in place; the product's same-named modules live inside the package directory and are never on ``sys.path`` as
-    top-level names, so there is no clash.  ``allow_compiled``: fall back to ``oracle/_ref/*.pyc``."""
+    top-level names, so there is no clash.  ``allow_compiled``: fall back to ``oracle/_ref/*.pyc.bin``."""
     if available():
         where = REFERENCE_SRC
     elif allow_compiled and compiled_available():
@@ -36,6 +53,8 @@ def load(allow_compiled: bool = False):
         raise RuntimeError("the reference is not present on this machine")
     from . import timm_shim
     timm_shim.install()
+    if where == REFERENCE_BIN:
+        return _load_compiled("inference_runner"), _load_compiled("model_merger")
     if where not in sys.path:
         sys.path.insert(0, where)
     ir = importlib.import_module("inference_runner")

@@ -6,6 +6,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SAD_LIB") or os.path.join(_HERE, "libsad_b200.so")   # SAD_LIB: A/B a differently built library
+LIB_PATHS = {"bf16": LIB_PATH, "fp16": os.path.join(_HERE, "libsad_b200_f16.so")}   # one build per activation dtype
 
 SAD_OK, SAD_EINVAL, SAD_ENODEVICE, SAD_ECUDA, SAD_ESTATE = 0, -1, -2, -3, -4
 _CODES = {SAD_EINVAL: "SAD_EINVAL", SAD_ENODEVICE: "SAD_ENODEVICE", SAD_ECUDA: "SAD_ECUDA", SAD_ESTATE: "SAD_ESTATE"}
@@ -20,6 +21,7 @@ SIGNATURES = {
     "sad_destroy": (_i, [_vp]),
     "sad_last_error": (C.c_char_p, [_vp]),
     "sad_version": (C.c_char_p, []),
+    "sad_act_dtype": (C.c_char_p, []),
     "sad_weight_count": (_i, []),
     "sad_weight_name": (C.c_char_p, [_i]),
     "sad_weight_numel": (_ll, [_i]),
@@ -51,33 +53,38 @@ SIGNATURES = {
     "sad_debug_read": (_ll, [_vp, _i, _vp, _ll, _vp]),
 }
 
-_lib = None
+_libs = {}
 
 
 class SadError(RuntimeError):
     pass
 
 
-def load() -> C.CDLL:
-    """dlopen the library (no GPU needed for this) and declare the prototypes."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def load(dtype: str = "bf16") -> C.CDLL:
+    """dlopen the library built for activation dtype `dtype` ("bf16" default, "fp16") -- no GPU needed for this -- and
+    declare the prototypes."""
+    if dtype in _libs:
+        return _libs[dtype]
+    if dtype not in LIB_PATHS:
+        raise ValueError(f"activation dtype {dtype!r}: choose 'bf16' or 'fp16'")
+    path = LIB_PATHS[dtype]
+    if not os.path.exists(path):
         raise SadError(
-            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` (nvcc, sm_100a). "
+            f"{path} is missing: build it with `python __graft_entry__.py build` (nvcc, sm_100a). "
             "There is no CPU or PyTorch fallback for this path.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    if lib.sad_act_dtype().decode() != dtype and not os.environ.get("SAD_LIB"):
+        raise SadError(f"{path} was built for {lib.sad_act_dtype().decode()} activations, expected {dtype}")
+    _libs[dtype] = lib
     return lib
 
 
 def check(ctx, code: int, what: str):
     if code >= 0:
         return code
-    msg = load().sad_last_error(ctx)
+    msg = next(iter(_libs.values())).sad_last_error(ctx) if _libs else b""   # ctx-only accessor: any loaded build serves
     raise SadError(f"{what}: {_CODES.get(code, code)}: {msg.decode() if msg else ''}")

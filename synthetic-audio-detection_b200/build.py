@@ -10,10 +10,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libsad_b200.so")
+LIB_F16 = os.path.join(HERE, "libsad_b200_f16.so")   # same sources with -DSAD_ACT_F16 (csrc/act.cuh)
 SOURCES = ["api.cu", "conv_umma.cu", "conv_umma2.cu", "conv_rows.cu", "block_rows.cu", "stem_fused.cu", "frontend.cu",
            "ingest.cu", "head.cu", "synth.cu"]
 HEADERS = ["conv_umma.h", "frontend.h", "ingest.h", "ingest_taps.h", "head.h", "stem_fused.h", "ptx.cuh", "fft2048.cuh",
-           "synth.h", os.path.join("..", "..", "include", "sad_b200.h")]
+           "synth.h", "act.cuh", os.path.join("..", "..", "include", "sad_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 
@@ -21,27 +22,33 @@ def _newest_header() -> float:
     return max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB):
+def _stale(lib: str) -> bool:
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Both builds: bf16 activations (libsad_b200.so, returned) and fp16 (libsad_b200_f16.so)."""
+    _build_one(LIB_F16, os.path.join(HERE, "build_f16"), ["-DSAD_ACT_F16"], force, verbose)
+    return _build_one(LIB, OBJ, [], force, verbose)
+
+
+def _build_one(lib: str, obj_dir: str, defines, force: bool, verbose: bool) -> str:
     """Compile what is newer than its object, link if anything changed; returns the library path."""
-    if not force and not _stale():
-        return LIB
+    if not force and not _stale(lib):
+        return lib
     nvcc = os.environ.get("NVCC", "nvcc")
-    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
     hdr_t = _newest_header()
     jobs = []
     for s in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(OBJ, s[:-3] + ".o")
+        obj = os.path.join(obj_dir, s[:-3] + ".o")
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
-            jobs.append([nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj])
+            jobs.append([nvcc] + NVCC_FLAGS + defines + ["-c", src, "-o", obj])
 
     def run(cmd):
         if verbose:
@@ -50,9 +57,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         list(ex.map(run, jobs))
-    run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", LIB] +
-        [os.path.join(OBJ, s[:-3] + ".o") for s in SOURCES])
-    return LIB
+    run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", lib] +
+        [os.path.join(obj_dir, s[:-3] + ".o") for s in SOURCES])
+    return lib
 
 
 def build_fft_host_check() -> str:

@@ -5,7 +5,6 @@
 // side, waveform_to_spectrogram (:157-174) + ModularMultiHeadClassifier.forward (:62-73) +
 // interpret_multihead_logits (:194-214) for the per-segment path, :328-334 for the clip mean.
 #include <cuda.h>
-#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -26,7 +25,7 @@
 
 namespace {
 
-using bf16 = __nv_bfloat16;
+using bf16 = sad::act_t;   // activation / conv-weight element: bf16, or fp16 in the -DSAD_ACT_F16 build (act.cuh)
 
 // ------------------------------------------------------------------------------------------------
 // network description (ResNet-18 trunk as timm builds it: conv1/bn1/act1/maxpool/layer1..4)
@@ -135,6 +134,11 @@ const NetSpec* get_net(const char* name) {
     return nullptr;
 }
 
+#if defined(SAD_ACT_F16)
+constexpr CUtensorMapDataType kMapType = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#else
+constexpr CUtensorMapDataType kMapType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#endif
 constexpr int kMaxConvs = 160;   // resnet152: 155
 // profile slots 0..SAD_PROF_CONV_SLOTS-1 are per conv; deeper convs (Bottleneck nets) share the last slot
 inline int prof_slot(int conv) { return conv < SAD_PROF_CONV_SLOTS ? conv : SAD_PROF_CONV_SLOTS - 1; }
@@ -410,7 +414,7 @@ bool encode_act_map(CUtensorMap* m, const void* base, int C, int W, int H, long 
                              static_cast<cuuint64_t>(sn) * 2};
     cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+    CUresult r = fn(m, kMapType, 4, const_cast<void*>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -432,7 +436,7 @@ bool encode_pix_map32(CUtensorMap* m, const void* base, int C, long long pixels,
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(C) * 2};
     cuuint32_t box[2] = {32, 32};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+    CUresult r = fn(m, kMapType, 2, const_cast<void*>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -450,7 +454,7 @@ bool encode_weight_map(CUtensorMap* m, const void* base, long long K, long long 
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+    CUresult r = fn(m, kMapType, 2, const_cast<void*>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -693,7 +697,7 @@ void resize_axis(int in, int* idx, float* w) {
 }
 
 // ---- weight folding ---------------------------------------------------------------------------------
-inline bf16 to_bf16(double v) { return __float2bfloat16_rn(static_cast<float>(v)); }
+inline bf16 to_bf16(double v) { return sad::act_from_float(static_cast<float>(v)); }
 
 void bn_scale_shift(const float* g, const float* b, const float* m, const float* v, int n, std::vector<double>& s,
                     std::vector<double>& t) {
@@ -715,7 +719,8 @@ int run_chunk(sad_ctx* c, const float* pcm, const float* x_nchw, int B, float th
 // ================================================================================================
 extern "C" {
 
-const char* sad_version(void) { return "sad_b200 0.1 (sm_100a)"; }
+const char* sad_version(void) { return "sad_b200 0.2 (sm_100a, " SAD_ACT_NAME " activations)"; }
+const char* sad_act_dtype(void) { return SAD_ACT_NAME; }
 
 int sad_backbone_weight_count(const char* backbone) {
     const NetSpec* n = get_net(backbone);
@@ -944,10 +949,10 @@ int sad_load_weights(sad_ctx* c, int head, const float* const* T, int n_tensors)
                 }
                 // folded BN shift as three bf16 terms against the constant {1,1,1} slots of the A tile (k = 56..58)
                 const float b = static_cast<float>(t[o]);
-                const bf16 hi = __float2bfloat16_rn(b);
-                const float r1 = b - __bfloat162float(hi);
-                const bf16 mid = __float2bfloat16_rn(r1);
-                const bf16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+                const bf16 hi = sad::act_from_float(b);
+                const float r1 = b - sad::act_as_float(hi);
+                const bf16 mid = sad::act_from_float(r1);
+                const bf16 lo = sad::act_from_float(r1 - sad::act_as_float(mid));
                 p1[o * 64 + 56] = hi;
                 p1[o * 64 + 57] = mid;
                 p1[o * 64 + 58] = lo;

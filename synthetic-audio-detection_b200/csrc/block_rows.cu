@@ -146,6 +146,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     __syncthreads();
     cluster_sync_all();                           // both CTAs' barriers are initialised before any remote arrive / store
     tc_fence_after();
+    pdl_launch_dependents();                        // the next kernel in the stream may start its prologue on SMs we leave
+    pdl_wait();                                     // our inputs (and buffers we overwrite) belong to the previous kernel until here
     const uint32_t tmem_base = *tmem_base_slot;
 
     const int units_per_head = p.imgs_per_head * kStripsPerImg;
@@ -313,12 +315,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                         uint32_t pk[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(fmaxf(f[2 * q], 0.f), fmaxf(f[2 * q + 1], 0.f));
-                            pk[q] = inside ? *reinterpret_cast<uint32_t*>(&b2) : 0u;
+                            pk[q] = inside ? act_pack_relu(f[2 * q], f[2 * q + 1]) : 0u;
                         }
                         // pixel p goes to peer slot row p+1: same bytes within the row, swizzle phase (p+1) & 7
-                        *reinterpret_cast<uint4*>(stg + prow * 128 + ((ch ^ ((prow + 1) & 7)) << 4)) =
-                            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        st_shared_v4(smem_u32(stg) + prow * 128 + ((ch ^ ((prow + 1) & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -366,20 +366,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                                       __uint_as_float(v[o + 2]) + b0.z, __uint_as_float(v[o + 3]) + b0.w,
                                       __uint_as_float(v[o + 4]) + b1.x, __uint_as_float(v[o + 5]) + b1.y,
                                       __uint_as_float(v[o + 6]) + b1.z, __uint_as_float(v[o + 7]) + b1.w};
-                        const uint4 rr = *reinterpret_cast<const uint4*>(res_row + sw128_offset(prow, ch));
+                        const uint4 rr = ld_shared_v4(smem_u32(res_row) + sw128_offset(prow, ch));
                         const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            f[2 * q] += __uint_as_float(rw[q] << 16);
-                            f[2 * q + 1] += __uint_as_float(rw[q] & 0xFFFF0000u);
+                            f[2 * q] += act_lo(rw[q]);
+                            f[2 * q + 1] += act_hi(rw[q]);
                         }
                         uint32_t pk[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(fmaxf(f[2 * q], 0.f), fmaxf(f[2 * q + 1], 0.f));
-                            pk[q] = *reinterpret_cast<uint32_t*>(&b2);
+                            pk[q] = act_pack_relu(f[2 * q], f[2 * q + 1]);
                         }
-                        *reinterpret_cast<uint4*>(stage + sw128_offset(lane, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        st_shared_v4(smem_u32(stage) + sw128_offset(lane, ch), pk[0], pk[1], pk[2], pk[3]);
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -412,8 +411,7 @@ cudaError_t block_rows_launch(const ConvLaunch& p_in, int heads, int num_sms, cu
     int clusters = num_sms / 2;
     if (p.total_tiles < clusters) clusters = p.total_tiles;
     if (clusters < 1) return cudaSuccess;
-    block_rows_kernel<<<2 * clusters, kThreads, kSmemBytes, stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(block_rows_kernel, dim3(2 * clusters), dim3(kThreads), kSmemBytes, stream, p);
 }
 
 }  // namespace sad

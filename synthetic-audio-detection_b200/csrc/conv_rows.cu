@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_rows_kernel(const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_launch_dependents();                        // the next kernel in the stream may start its prologue on SMs we leave
+    pdl_wait();                                     // our inputs (and buffers we overwrite) belong to the previous kernel until here
     const uint32_t tmem_base = *tmem_base_slot;
 
     const int units_per_head = p.imgs_per_head * kStripsPerImg;
@@ -264,26 +266,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_rows_kernel(const __grid_con
                                   __uint_as_float(v[o + 4]) + b1.x, __uint_as_float(v[o + 5]) + b1.y,
                                   __uint_as_float(v[o + 6]) + b1.z, __uint_as_float(v[o + 7]) + b1.w};
                     if (has_res) {
-                        const uint4 rr = *reinterpret_cast<const uint4*>(res_row + sw128_offset(prow, ch));
+                        const uint4 rr = ld_shared_v4(smem_u32(res_row) + sw128_offset(prow, ch));
                         const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            f[2 * q] += __uint_as_float(rw[q] << 16);
-                            f[2 * q + 1] += __uint_as_float(rw[q] & 0xFFFF0000u);
+                            f[2 * q] += act_lo(rw[q]);
+                            f[2 * q + 1] += act_hi(rw[q]);
                         }
                     }
                     uint32_t pk[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float a0 = f[2 * q], a1 = f[2 * q + 1];
-                        if (p.relu) {
-                            a0 = fmaxf(a0, 0.f);
-                            a1 = fmaxf(a1, 0.f);
-                        }
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(a0, a1);
-                        pk[q] = *reinterpret_cast<uint32_t*>(&b2);
+                        pk[q] = p.relu ? act_pack_relu(f[2 * q], f[2 * q + 1]) : act_pack(f[2 * q], f[2 * q + 1]);
                     }
-                    *reinterpret_cast<uint4*>(stage + sw128_offset(lane, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    st_shared_v4(smem_u32(stage) + sw128_offset(lane, ch), pk[0], pk[1], pk[2], pk[3]);
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -312,8 +308,7 @@ cudaError_t conv_rows_launch(const ConvLaunch& p_in, int heads, int num_sms, cud
     ConvLaunch p = p_in;
     p.total_tiles = heads * p.imgs_per_head * kStripsPerImg;
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-    conv_rows_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(conv_rows_kernel, dim3(grid), dim3(kThreads), kSmemBytes, stream, p);
 }
 
 }  // namespace sad

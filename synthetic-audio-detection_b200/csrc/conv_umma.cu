@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_launch_dependents();                        // the next kernel in the stream may start its prologue on SMs we leave
+    pdl_wait();                                     // our inputs (and buffers we overwrite) belong to the previous kernel until here
     const uint32_t tmem_base = *tmem_base_slot;
 
     const int taps = p.ksize * p.ksize;
@@ -253,11 +255,13 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
                     if (lane == 0) tma_store_wait_read<C::kOutBufs - 1>();
                     __syncwarp();
                     uint8_t* stage = my_out + (nstore % C::kOutBufs) * 4096;
+                    const uint32_t st_addr = smem_u32(stage) + lane * 2;          // [px][32 ch]: this thread's channel column
 #pragma unroll
-                    for (int px = 0; px < 32; ++px) {
-                        float f = __uint_as_float(v[px]) + bias;
-                        if (p.relu) f = fmaxf(f, 0.f);
-                        *reinterpret_cast<uint16_t*>(stage + px * 64 + lane * 2) = __bfloat16_as_ushort(__float2bfloat16_rn(f));
+                    for (int px = 0; px < 32; px += 2) {
+                        const float f0 = __uint_as_float(v[px]) + bias, f1 = __uint_as_float(v[px + 1]) + bias;
+                        const uint32_t w = p.relu ? act_pack_relu(f0, f1) : act_pack(f0, f1);
+                        st_shared_u16(st_addr + px * 64, w & 0xFFFFu);
+                        st_shared_u16(st_addr + (px + 1) * 64, w >> 16);
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
             for (int m = m_lo; m < m_hi; ++m) {
             const long long pix0 = (static_cast<long long>(head) * p.imgs_per_head + img) * (p.m_tiles_per_img * kBlockM) +
                                    (m_t + m) * kBlockM;
-            const __nv_bfloat16* res = p.residual ? p.residual + (pix0 + row) * p.Cout + co0 : nullptr;
+            const act_t* res = p.residual ? p.residual + (pix0 + row) * p.Cout + co0 : nullptr;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::kAccCols + m * N_TILE;
 #pragma unroll 1
             for (int c0 = 0; c0 < N_TILE; c0 += 64, ++nstore) {
@@ -328,22 +332,16 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
                         const uint32_t rw[4] = {rv[ch].x, rv[ch].y, rv[ch].z, rv[ch].w};
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            f[2 * q] += __uint_as_float(rw[q] << 16);
-                            f[2 * q + 1] += __uint_as_float(rw[q] & 0xFFFF0000u);
+                            f[2 * q] += act_lo(rw[q]);
+                            f[2 * q + 1] += act_hi(rw[q]);
                         }
                     }
                     uint32_t pk[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float a0 = f[2 * q], a1 = f[2 * q + 1];
-                        if (p.relu) {
-                            a0 = fmaxf(a0, 0.f);
-                            a1 = fmaxf(a1, 0.f);
-                        }
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(a0, a1);
-                        pk[q] = *reinterpret_cast<uint32_t*>(&b2);
+                        pk[q] = p.relu ? act_pack_relu(f[2 * q], f[2 * q + 1]) : act_pack(f[2 * q], f[2 * q + 1]);
                     }
-                    *reinterpret_cast<uint4*>(stage + sw128_offset(lane, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    st_shared_v4(smem_u32(stage) + sw128_offset(lane, ch), pk[0], pk[1], pk[2], pk[3]);
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -370,8 +368,7 @@ cudaError_t launch_t(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     const int groups = p.total_tiles / MT;
     int grid = groups < num_sms ? groups : num_sms;
-    conv_umma_kernel<N_TILE, MT, TR><<<grid, C::kThreadsCfg, C::kSmemBytes, stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(conv_umma_kernel<N_TILE, MT, TR>, dim3(grid), dim3(C::kThreadsCfg), C::kSmemBytes, stream, p);
 }
 
 }  // namespace

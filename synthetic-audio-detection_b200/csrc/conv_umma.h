@@ -1,8 +1,9 @@
 // Host-visible launch description of the tcgen05 implicit-GEMM convolution (conv_umma.cu).
 #pragma once
 #include <atomic>
+#include <cstdlib>
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include "act.cuh"
 #include <cuda_runtime.h>
 
 namespace sad {
@@ -19,8 +20,8 @@ struct alignas(64) ConvLaunch {
     CUtensorMap b2h_map;
     const float* bias;      // [heads*Cout] fp32 (folded BN shift)
     const float* bias2;     // fused BasicBlock (block_rows.cu): bias of conv2 (its weights are b2_map)
-    const __nv_bfloat16* residual;   // NHWC [heads*imgs][Ho*Wo][Cout] or nullptr
-    __nv_bfloat16* out;     // NHWC [heads*imgs][Ho*Wo][Cout]
+    const act_t* residual;   // NHWC [heads*imgs][Ho*Wo][Cout] or nullptr
+    act_t* out;     // NHWC [heads*imgs][Ho*Wo][Cout]
     int Cin, Cout;
     int ksize, stride, pad;
     int imgs_per_head;      // B
@@ -50,6 +51,33 @@ inline cudaError_t ensure_dynamic_smem(int bytes) {
         if (dev >= 0 && dev < 64) done[dev].store(true, std::memory_order_release);
     }
     return cudaSuccess;
+}
+
+// Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may begin while its predecessor
+// in the stream drains; every kernel launched this way calls pdl_wait() (ptx.cuh) before its first dependent access.
+// SAD_PDL=0 turns the attribute off (A/B switch).
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("SAD_PDL");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+template <typename Kernel, typename... Args>
+inline cudaError_t launch_pdl(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (pdl_enabled()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 int conv_n_tile(int Cout);

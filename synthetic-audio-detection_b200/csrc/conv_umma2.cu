@@ -87,6 +87,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
     __syncthreads();
     cluster_sync_all();                             // barriers of both CTAs are initialised before any remote signal
     tc_fence_after();
+    pdl_launch_dependents();                        // the next kernel in the stream may start its prologue on SMs we leave
+    pdl_wait();                                     // our inputs (and buffers we overwrite) belong to the previous kernel until here
     const uint32_t tmem_base = *tmem_base_slot;
 
     const int taps = p.ksize * p.ksize;
@@ -199,7 +201,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
             for (int m = 0; m < MT; ++m) {
             const long long pix0 = (static_cast<long long>(head) * p.imgs_per_head + img) * (p.m_tiles_per_img * kBlockM) +
                                    (m_t + m) * kBlockM;
-            const __nv_bfloat16* res = p.residual ? p.residual + (pix0 + row) * p.Cout + co0 : nullptr;
+            const act_t* res = p.residual ? p.residual + (pix0 + row) * p.Cout + co0 : nullptr;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::kAccCols + m * N_TILE;
 #pragma unroll 1
             for (int c0 = 0; c0 < N_TILE; c0 += 64, ++nstore) {
@@ -233,22 +235,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
                         const uint32_t rw[4] = {rv[ch].x, rv[ch].y, rv[ch].z, rv[ch].w};
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            f[2 * q] += __uint_as_float(rw[q] << 16);
-                            f[2 * q + 1] += __uint_as_float(rw[q] & 0xFFFF0000u);
+                            f[2 * q] += act_lo(rw[q]);
+                            f[2 * q + 1] += act_hi(rw[q]);
                         }
                     }
                     uint32_t pk[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float a0 = f[2 * q], a1 = f[2 * q + 1];
-                        if (p.relu) {
-                            a0 = fmaxf(a0, 0.f);
-                            a1 = fmaxf(a1, 0.f);
-                        }
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(a0, a1);
-                        pk[q] = *reinterpret_cast<uint32_t*>(&b2);
+                        pk[q] = p.relu ? act_pack_relu(f[2 * q], f[2 * q + 1]) : act_pack(f[2 * q], f[2 * q + 1]);
                     }
-                    *reinterpret_cast<uint4*>(stage + sw128_offset(lane, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    st_shared_v4(smem_u32(stage) + sw128_offset(lane, ch), pk[0], pk[1], pk[2], pk[3]);
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -279,12 +275,7 @@ cudaError_t launch2_t(const ConvLaunch& p, int num_sms, cudaStream_t stream) {
     const int groups = p.total_tiles / (2 * MT);
     int pairs = num_sms / 2;
     if (groups < pairs) pairs = groups;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(kThreads2);
-    cfg.dynamicSmemBytes = C::kSmemBytes;
-    cfg.stream = stream;
-    e = cudaLaunchKernelEx(&cfg, conv_umma2_kernel<N_TILE, MT>, p);
+    e = launch_pdl(conv_umma2_kernel<N_TILE, MT>, dim3(2 * pairs), dim3(kThreads2), C::kSmemBytes, stream, p);
     if (e != cudaSuccess)
         fprintf(stderr, "conv_umma2<%d>: launch grid %d smem %d -> %s\n", N_TILE, 2 * pairs, C::kSmemBytes, cudaGetErrorString(e));
     return e;

@@ -6,7 +6,6 @@
 //   10*log10(clamp(x,1e-10)); max(x, segment max - 80)                           -> stft_mel_kernel + db_clamp_stats_kernel
 //   (x - mean) / (unbiased std + 1e-6)                                          -> db_clamp_stats_kernel + image_kernel
 //   bilinear resize 128x251 -> 512x512 (anti-aliased taps), 3 identical channels -> image_kernel
-#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -207,7 +206,7 @@ __device__ __forceinline__ T to_out(float v);
 template <>
 __device__ __forceinline__ float to_out<float>(float v) { return v; }
 template <>
-__device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ act_t to_out<act_t>(float v) { return act_from_float(v); }
 
 // Standardise + separable 2-tap resize (horizontal first, taps accumulated with one fma each, as ATen does).
 // grid (512 rows, B), 256 threads.  The two source rows of an output row are standardised ONCE into shared memory
@@ -240,7 +239,7 @@ __global__ void __launch_bounds__(256) image_kernel(const float* __restrict__ db
 }
 
 // Stem im2col for a generic 3-channel NCHW fp32 image: k = (ky*7+kx)*3 + c (147 real taps, zero to 192).
-__global__ void __launch_bounds__(256) im2col_stem3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ A,
+__global__ void __launch_bounds__(256) im2col_stem3_kernel(const float* __restrict__ x, act_t* __restrict__ A,
                                                            long long n_chunks) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n_chunks) return;
@@ -260,7 +259,10 @@ __global__ void __launch_bounds__(256) im2col_stem3_kernel(const float* __restri
             const int iy = 2 * oy + tap / 7 - 3, ix = 2 * ox + tap % 7 - 3;
             if (iy >= 0 && iy < 512 && ix >= 0 && ix < 512) val = __ldg(src + (c * 512 + iy) * 512 + ix);
         }
-        v[j] = __bfloat16_as_ushort(__float2bfloat16_rn(val));
+        {
+            const act_t a = act_from_float(val);
+            v[j] = *reinterpret_cast<const unsigned short*>(&a);
+        }
     }
     uint4 o;
     o.x = v[0] | (static_cast<unsigned>(v[1]) << 16);
@@ -272,16 +274,15 @@ __global__ void __launch_bounds__(256) im2col_stem3_kernel(const float* __restri
 
 __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
     uint4 r;
-    __nv_bfloat162* ra = reinterpret_cast<__nv_bfloat162*>(&a);
-    __nv_bfloat162* rb = reinterpret_cast<__nv_bfloat162*>(&b);
-    __nv_bfloat162* rr = reinterpret_cast<__nv_bfloat162*>(&r);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) rr[i] = __hmax2(ra[i], rb[i]);
+    r.x = act_max2(a.x, b.x);
+    r.y = act_max2(a.y, b.y);
+    r.z = act_max2(a.z, b.z);
+    r.w = act_max2(a.w, b.w);
     return r;
 }
 
 // maxpool 3x3 / stride 2 / pad 1 on NHWC bf16 [n,256,256,64] -> [n,128,128,64]; one thread per 8 channels.
-__global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256) maxpool_kernel(const act_t* __restrict__ in, act_t* __restrict__ out,
                                                       long long n_chunks) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n_chunks) return;
@@ -386,19 +387,19 @@ cudaError_t image_launch_f32(const float* db, const float* mu_sigma, const Resiz
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
-cudaError_t image_launch_bf16(const float* db, const float* mu_sigma, const ResizeTable* rt, __nv_bfloat16* img, int B,
+cudaError_t image_launch_bf16(const float* db, const float* mu_sigma, const ResizeTable* rt, act_t* img, int B,
                               cudaStream_t stream, long long* launches) {
-    image_kernel<__nv_bfloat16><<<dim3(512, B), 256, 0, stream>>>(db, mu_sigma, rt, img);
+    image_kernel<act_t><<<dim3(512, B), 256, 0, stream>>>(db, mu_sigma, rt, img);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
-cudaError_t im2col_stem3_launch(const float* x, __nv_bfloat16* A, int B, cudaStream_t stream, long long* launches) {
+cudaError_t im2col_stem3_launch(const float* x, act_t* A, int B, cudaStream_t stream, long long* launches) {
     const long long n = static_cast<long long>(B) * 65536 * 24;
     im2col_stem3_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(x, A, n);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
-cudaError_t maxpool_launch(const __nv_bfloat16* in, __nv_bfloat16* out, long long n_img, cudaStream_t stream,
+cudaError_t maxpool_launch(const act_t* in, act_t* out, long long n_img, cudaStream_t stream,
                            long long* launches) {
     const long long n = n_img * 128 * 128 * 8;
     maxpool_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, out, n);

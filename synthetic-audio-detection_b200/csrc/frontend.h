@@ -2,7 +2,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
-#include <cuda_bf16.h>
+#include "act.cuh"
 #include <cuda_runtime.h>
 
 namespace sad {
@@ -32,10 +32,10 @@ cudaError_t frontend_logmel_launch(const float* pcm, int B, const float* window,
                                    long long* launches);
 cudaError_t image_launch_f32(const float* db, const float* mu_sigma, const ResizeTable* rt, float* img, int B,
                              cudaStream_t stream, long long* launches);
-cudaError_t image_launch_bf16(const float* db, const float* mu_sigma, const ResizeTable* rt, __nv_bfloat16* img, int B,
+cudaError_t image_launch_bf16(const float* db, const float* mu_sigma, const ResizeTable* rt, act_t* img, int B,
                               cudaStream_t stream, long long* launches);
-cudaError_t im2col_stem3_launch(const float* x, __nv_bfloat16* A, int B, cudaStream_t stream, long long* launches);
-cudaError_t maxpool_launch(const __nv_bfloat16* in, __nv_bfloat16* out, long long n_img, cudaStream_t stream,
+cudaError_t im2col_stem3_launch(const float* x, act_t* A, int B, cudaStream_t stream, long long* launches);
+cudaError_t maxpool_launch(const act_t* in, act_t* out, long long n_img, cudaStream_t stream,
                            long long* launches);
 cudaError_t slice_gate_launch(const float* wf, long long n_windows, long long window, long long hop, float thr,
                               uint8_t* keep, cudaStream_t stream, long long* launches);

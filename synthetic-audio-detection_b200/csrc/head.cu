@@ -3,7 +3,6 @@
 // Replaces BinaryClassifier.head (reference modular/source/inference_runner.py:36-48, eval mode),
 // ModularMultiHeadClassifier.forward's merge (:62-73), interpret_multihead_logits (:194-214) and the clip
 // mean (:328-334).
-#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -20,7 +19,7 @@ namespace {
 // one 16-byte load; the K dimension is split over thread groups and reduced through shared memory.
 // F = trunk feature width: 512 (resnet18/34) or 2048 (Bottleneck nets).
 template <int F>
-__global__ void __launch_bounds__(256) head_mlp_kernel(const __nv_bfloat16* __restrict__ feats, HeadWeights hw, int B,
+__global__ void __launch_bounds__(256) head_mlp_kernel(const act_t* __restrict__ feats, HeadWeights hw, int B,
                                                        float* __restrict__ head_logits) {
     constexpr int kC8 = F / 8;            // 16-byte channel groups per pixel
     constexpr int kG = 256 / kC8;         // pixel groups in the pooling phase (4 for F=512, 1 for F=2048)
@@ -45,8 +44,8 @@ __global__ void __launch_bounds__(256) head_mlp_kernel(const __nv_bfloat16* __re
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                acc[2 * j] += __uint_as_float(w[j] << 16);
-                acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+                acc[2 * j] += act_lo(w[j]);
+                acc[2 * j + 1] += act_hi(w[j]);
             }
         }
 #pragma unroll
@@ -199,7 +198,7 @@ __global__ void __launch_bounds__(256) clip_reduce_kernel(const float* __restric
 
 }  // namespace
 
-cudaError_t head_mlp_launch(const __nv_bfloat16* feats, const HeadWeights& hw, int B, int H, int features, float* head_logits,
+cudaError_t head_mlp_launch(const act_t* feats, const HeadWeights& hw, int B, int H, int features, float* head_logits,
                             cudaStream_t stream, long long* launches) {
     if (features == 512) head_mlp_kernel<512><<<dim3(B, H), 256, 0, stream>>>(feats, hw, B, head_logits);
     else if (features == 2048) head_mlp_kernel<2048><<<dim3(B, H), 256, 0, stream>>>(feats, hw, B, head_logits);

@@ -1,6 +1,6 @@
 // Launch wrappers of the head / merge / clip kernels (head.cu).
 #pragma once
-#include <cuda_bf16.h>
+#include "act.cuh"
 #include <cuda_runtime.h>
 
 namespace sad {
@@ -18,7 +18,7 @@ struct HeadWeights {
     const float* b3;
 };
 
-cudaError_t head_mlp_launch(const __nv_bfloat16* feats, const HeadWeights& hw, int B, int H, int features, float* head_logits,
+cudaError_t head_mlp_launch(const act_t* feats, const HeadWeights& hw, int B, int H, int features, float* head_logits,
                             cudaStream_t stream, long long* launches);
 cudaError_t merge_decide_launch(const float* head_logits, int B, int N, float thr, float* logits, float* probs, int* labels,
                                 cudaStream_t stream, long long* launches);

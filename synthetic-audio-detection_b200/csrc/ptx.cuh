@@ -2,6 +2,7 @@
 // Written for this project; encodings follow the PTX ISA and were cross-read against the
 // CuTe sm100 headers (cute/arch/mma_sm100_desc.hpp) for the descriptor bit layouts.
 #pragma once
+#include "act.cuh"
 #include <cstdint>
 #include <cuda.h>
 
@@ -113,10 +114,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major:
-//   [4,6) D fmt = 1 (f32)  [7,10) A fmt = 1 (bf16)  [10,13) B fmt = 1 (bf16)
+//   [4,6) D fmt = 1 (f32)  [7,10) A fmt, [10,13) B fmt: 1 = bf16, 0 = f16 (act.cuh)
 //   [15] A major = 0 (K)  [16] B major = 0 (K)  [17,23) N>>3  [24,29) M>>4
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {   // "bf16" = the build's operand type (act.cuh)
+    return (1u << 4) | (kUmmaOperandFormat << 7) | (kUmmaOperandFormat << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
@@ -247,6 +248,29 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   /
 
 // Byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a SWIZZLE_128B tile whose rows are 128 B
 // (what TMA writes and what the UMMA descriptor above reads): chunk index is XORed with (row mod 8).
+// Programmatic dependent launch (the launch carries cudaLaunchAttributeProgrammaticStreamSerialization): a kernel lets
+// its successor in the stream start early with pdl_launch_dependents(); the successor runs its prologue (barrier init,
+// TMEM allocation, tensor-map prefetch) on SMs the predecessor's CTAs have already left and must call pdl_wait() --
+// which returns when the predecessor grid has COMPLETED and its writes are visible -- before it touches any global
+// memory the predecessor reads or writes.  Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
+// Shared-space accesses by 32-bit address.  Pointers carved out of the aligned dynamic-smem base lose their address
+// space, and the compiler then emits GENERIC ld/st (ST.E with a 64-bit address and no immediate folding): the epilogues'
+// staging stores were 4-6 instructions each that way.
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<uint16_t>(v)) : "memory");
+}
+
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
     return row * 128u + ((chunk ^ (row & 7u)) << 4);
 }

@@ -23,7 +23,6 @@
 //                       pooled row is transposed through swizzled smem and written with TMA stores
 //                       ([128 px][64 ch] per head).
 // Work unit = (image, head pair, strip of 32 pooled rows); persistent CTAs, round-robin.
-#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "conv_umma.h"
@@ -57,13 +56,10 @@ constexpr int kTmemCols = 512;                 // 2 buffers x 256 pixel columns
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(n) : "memory");
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
-    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-    return *reinterpret_cast<uint32_t*>(&r);
+__device__ __forceinline__ float fmax3(float a, float b, float c) {   // FMNMX3: one instruction on sm_100
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_constant__ StemLaunch p) {
@@ -101,7 +97,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
     if (warp >= 1 && warp <= 4) {
         // chunk 7 of every pixel row is constant: {1, 1, 1, 0, 0, 0, 0, 0} (bias terms), written once
         const int i = (warp - 1) * 32 + lane;
-        const uint4 ones = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);
+        const uint4 ones = make_uint4(kActOne | (kActOne << 16), kActOne, 0u, 0u);
         for (int b = 0; b < 2; ++b) {
             *reinterpret_cast<uint4*>(p_sm + b * kPixTile + sw128_offset(2 * i, 7)) = ones;
             *reinterpret_cast<uint4*>(p_sm + b * kPixTile + sw128_offset(2 * i + 1, 7)) = ones;
@@ -111,6 +107,8 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_launch_dependents();                        // the next kernel in the stream may start its prologue on SMs we leave
+    pdl_wait();                                     // our inputs (and buffers we overwrite) belong to the previous kernel until here
     const uint32_t tmem_base = *tmem_base_slot;
 
     const int units_per_group = p.B * kStrips;
@@ -156,6 +154,12 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
         // ------------------------------------------------------------------ builders: image -> pixel tile
         const int i = (warp - 1) * 32 + lane;          // builds conv pixels x = 2i and 2i+1
         uint32_t arow = 0;
+        uint32_t off_e[7], off_o[7];                    // swizzled chunk offsets of this thread's two pixel rows
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+            off_e[ky] = smem_u32(p_sm) + sw128_offset(2 * i, ky);
+            off_o[ky] = smem_u32(p_sm) + sw128_offset(2 * i + 1, ky);
+        }
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
             const int r0 = u % units_per_group;
             const int img = r0 / kStrips;
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                     w[ky][0] = q0.x; w[ky][1] = q0.y; w[ky][2] = q1.x; w[ky][3] = q1.y; w[ky][4] = q2.x; w[ky][5] = q2.y;
                 }
                 mbar_wait(&p_empty[b], ((arow >> 1) & 1) ^ 1);
-                uint8_t* tile = p_sm + b * kPixTile;
+                const uint32_t tile = b * kPixTile;
 #pragma unroll
                 for (int ky = 0; ky < 7; ++ky) {
                     // even pixel x = 2i: image pixels [4i-3, 4i+4] = halves starting at the high half of word 0
@@ -189,8 +193,8 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                     // odd pixel x = 2i+1: image pixels [4i-1, 4i+6]
                     const uint4 co = make_uint4(__funnelshift_r(w[ky][1], w[ky][2], 16), __funnelshift_r(w[ky][2], w[ky][3], 16),
                                                 __funnelshift_r(w[ky][3], w[ky][4], 16), __funnelshift_r(w[ky][4], w[ky][5], 16));
-                    *reinterpret_cast<uint4*>(tile + sw128_offset(2 * i, ky)) = ce;
-                    *reinterpret_cast<uint4*>(tile + sw128_offset(2 * i + 1, ky)) = co;
+                    st_shared_v4(off_e[ky] + tile, ce.x, ce.y, ce.z, ce.w);
+                    st_shared_v4(off_o[ky] + tile, co.x, co.y, co.z, co.w);
                 }
                 fence_proxy_async();
                 mbar_arrive(&p_full[b]);
@@ -223,7 +227,12 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                 mbar_wait(&tmem_full[b], (arow >> 1) & 1);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * 256 + half * kGroupCols;
-                uint8_t* stage = out_sm + (eb * 2 + hh) * kHeadTile + (cc & 7) * 2;   // + swizzled (px, chunk cc/8)
+                // staging tile of this thread's head: shared-space addresses, one base per value of (px & 7) so that
+                // every store below is [base + immediate] (a generic-pointer version compiled to ST + 4 address ops each)
+                const uint32_t stage = smem_u32(out_sm) + (eb * 2 + hh) * kHeadTile + (cc & 7) * 2 + half * (kGroupCols / 2) * 128;
+                uint32_t sbase[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sbase[k] = stage + ((((cc >> 3) ^ k) & 7) << 4);
                 uint32_t va[32], vb[32];
                 float prev = -INFINITY;                            // conv pixel 2p-1 of the first pooled px
                 if (half) {
@@ -249,27 +258,27 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                     for (int j = 0; j < 8; ++j) {
                         const float a0 = __uint_as_float(v[4 * j]), a1 = __uint_as_float(v[4 * j + 1]);
                         const float a2 = __uint_as_float(v[4 * j + 2]), a3 = __uint_as_float(v[4 * j + 3]);
-                        const float h0 = fmaxf(fmaxf(prev, a0), a1);      // pooled px 2j   : conv 2p-1, 2p, 2p+1
-                        const float h1 = fmaxf(fmaxf(a1, a2), a3);        // pooled px 2j+1
+                        const float h0 = fmax3(prev, a0, a1);             // pooled px 2j   : conv 2p-1, 2p, 2p+1
+                        const float h1 = fmax3(a1, a2, a3);               // pooled px 2j+1
                         prev = a3;
-                        hb[j] = pack_bf16(h0, h1);
+                        hb[j] = act_pack_relu(h0, h1);
                     }
                     if (t == 0) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) carry[cb * 8 + j] = r < 0 ? 0xFF80FF80u /* -inf, -inf */ : hb[j];
+                        for (int j = 0; j < 8; ++j) carry[cb * 8 + j] = r < 0 ? 0u /* max identity after ReLU */ : hb[j];
                     } else if (!emit) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) carry[cb * 8 + j] = bf16x2_max(carry[cb * 8 + j], hb[j]);
+                        for (int j = 0; j < 8; ++j) carry[cb * 8 + j] = act_max2(carry[cb * 8 + j], hb[j]);
                     } else {
-                        // pooled row done: relu(max(carry, h)); this conv row also starts the next pooled row.
+                        // pooled row done: max(carry, h) (ReLU already applied); this conv row also starts the next pooled row.
                         // Transpose through smem: this thread owns channel cc, pooled px half*64 + 16cb .. +15.
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const uint32_t o = bf16x2_max(bf16x2_max(carry[cb * 8 + j], hb[j]), 0u);
+                            const uint32_t o = act_max2(carry[cb * 8 + j], hb[j]);
                             carry[cb * 8 + j] = hb[j];
-                            const int px = half * (kGroupCols / 2) + cb * 16 + 2 * j;
-                            *reinterpret_cast<uint16_t*>(stage + sw128_offset(px, cc >> 3)) = static_cast<uint16_t>(o & 0xFFFFu);
-                            *reinterpret_cast<uint16_t*>(stage + sw128_offset(px + 1, cc >> 3)) = static_cast<uint16_t>(o >> 16);
+                            const int px = cb * 16 + 2 * j;                 // within this group's 64 pooled px (a multiple of 8 apart)
+                            st_shared_u16(sbase[px & 7] + px * 128, o & 0xFFFFu);
+                            st_shared_u16(sbase[(px + 1) & 7] + (px + 1) * 128, o >> 16);
                         }
                     }
                     if (cb < kChunks - 1) {
@@ -318,8 +327,7 @@ cudaError_t stem_fused_launch(const StemLaunch& p_in, int num_sms, cudaStream_t 
     p.G = (p.H + 1) / 2;
     p.total_units = p.G * p.B * kStrips;
     const int grid = p.total_units < num_sms ? p.total_units : num_sms;
-    stem_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(stem_fused_kernel, dim3(grid), dim3(kThreads), kSmemBytes, stream, p);
 }
 
 }  // namespace sad

@@ -37,12 +37,25 @@ def _frontend_constants() -> Tuple[torch.Tensor, torch.Tensor]:
     return window.contiguous(), fb.contiguous()
 
 
+def default_dtype(backbone: str) -> str:
+    return "fp16" if backbone in ("resnet50", "resnet101", "resnet152") else "bf16"
+
+
 class Engine:
     """Owns a sad_ctx.  Tensors passed in must be CUDA fp32 contiguous on this engine's device."""
 
     def __init__(self, n_heads: int, device: Optional[torch.device] = None, max_batch: int = 64,
-                 backbone: str = "resnet18"):
-        self.lib = _lib.load()
+                 backbone: str = "resnet18", dtype: Optional[str] = None):
+        """dtype: element type of activations / conv weights, "bf16" or "fp16" (two builds of the same kernels,
+        csrc/act.cuh).  Default: bf16 -- the dtype BASELINE.json names -- for the BasicBlock nets (resnet18/34), fp16 for
+        the Bottleneck nets (resnet50/101/152), whose 53+ convolutions do not meet the 2e-2 logit bound with bf16
+        storage.  SAD_DTYPE in the environment overrides the default."""
+        import os
+        if dtype is None:
+            dtype = os.environ.get("SAD_DTYPE") or default_dtype(backbone)
+        self.dtype = dtype
+        self.act_dtype = torch.float16 if dtype == "fp16" else torch.bfloat16
+        self.lib = _lib.load(dtype)
         if not torch.cuda.is_available():
             raise _lib.SadError("no CUDA device: the sm_100a kernels cannot run and there is no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda")
@@ -228,7 +241,7 @@ class Engine:
         return out
 
     def debug_conv(self, head: int, layer: int, x: torch.Tensor, residual: Optional[torch.Tensor], out_shape, relu: bool):
-        out = torch.empty(out_shape, device=self.device, dtype=torch.bfloat16)
+        out = torch.empty(out_shape, device=self.device, dtype=self.act_dtype)
         _lib.check(self.ctx, self.lib.sad_debug_conv(self.ctx, head, layer, _ptr(x), _ptr(residual), _ptr(out), x.shape[0],
                                                      int(relu), _stream(self.device)), "sad_debug_conv")
         return out
@@ -244,7 +257,7 @@ class Engine:
         """Pooled stem output [H*B,128,128,64] bf16 for pcm [B,128000] (B <= max_batch)."""
         self._check(pcm, (SEGMENT,))
         B = pcm.shape[0]
-        out = torch.empty(self.n_heads * B, 128, 128, 64, device=self.device, dtype=torch.bfloat16)
+        out = torch.empty(self.n_heads * B, 128, 128, 64, device=self.device, dtype=self.act_dtype)
         _lib.check(self.ctx, self.lib.sad_debug_stem(self.ctx, _ptr(pcm), B, _ptr(out), _stream(self.device)),
                    "sad_debug_stem")
         return out

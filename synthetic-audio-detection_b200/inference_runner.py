@@ -95,7 +95,7 @@ class BinaryClassifier(nn.Module):
             xb = x[i:i + eng.max_batch]
             eng.forward_images(xb)
             outs.append(eng.debug_read(3, (xb.shape[0], 2), torch.float32))
-            feats.append(eng.debug_read(2, (xb.shape[0], 16, 16, self.base.num_features), torch.bfloat16))
+            feats.append(eng.debug_read(2, (xb.shape[0], 16, 16, self.base.num_features), eng.act_dtype))
         return torch.cat(outs), torch.cat(feats)
 
     def _features(self, x: torch.Tensor) -> torch.Tensor:          # timm forward_features: [B,512,16,16]

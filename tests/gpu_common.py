@@ -22,12 +22,13 @@ def merged_sd(n_heads, backbone="resnet18"):
 _ENGINES = {}
 
 
-def engine(n_heads, max_batch=8, backbone="resnet18"):
-    """One engine per (heads, batch, backbone) per process, weights of the seeded fixture loaded through the C ABI."""
+def engine(n_heads, max_batch=8, backbone="resnet18", dtype=None):
+    """One engine per (heads, batch, backbone, dtype) per process, weights of the seeded fixture loaded through the C ABI.
+    dtype None = the engine's default (bf16 for resnet18/34, fp16 for the Bottleneck nets)."""
     from sad_b200.engine import Engine
-    key = (n_heads, max_batch, backbone)
+    key = (n_heads, max_batch, backbone, dtype)
     if key not in _ENGINES:
-        e = Engine(n_heads, torch.device("cuda", 0), max_batch=max_batch, backbone=backbone)
+        e = Engine(n_heads, torch.device("cuda", 0), max_batch=max_batch, backbone=backbone, dtype=dtype)
         e.load_merged_state_dict(merged_sd(n_heads, backbone))
         _ENGINES[key] = e
     return _ENGINES[key]

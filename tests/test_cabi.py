@@ -16,15 +16,18 @@ def _declared():
     return sorted(set(re.findall(r"\b(sad_[a-z0-9_]+)\s*\(", text)))
 
 
-def test_header_symbols_are_exported_and_bound():
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_header_symbols_are_exported_and_bound(dtype):
+    """Both builds of the library (bf16 activations = libsad_b200.so, fp16 = libsad_b200_f16.so, csrc/act.cuh)."""
     from sad_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load(dtype)
     names = _declared()
     assert len(names) >= 20
     for n in names:
-        assert hasattr(lib, n), f"{n} declared in include/sad_b200.h but not exported by libsad_b200.so"
+        assert hasattr(lib, n), f"{n} declared in include/sad_b200.h but not exported by {_lib.LIB_PATHS[dtype]}"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes prototype in _lib.SIGNATURES"
     assert sorted(_lib.SIGNATURES) == names
+    assert lib.sad_act_dtype().decode() == dtype and dtype in lib.sad_version().decode()
 
 
 def test_weight_manifest_matches_checkpoint_layout():

@@ -160,19 +160,20 @@ def test_bottleneck_conv_layer(idx):
     sd = G.merged_sd(2, "resnet50")
     p = f"sub_models.{head}.base."
     w, b = E.fold_bn(sd[p + name + ".weight"], sd, p + R50_BNS[idx][1])
-    wq = w.to(torch.bfloat16).float()
+    e = G.engine(2, backbone="resnet50")                    # Bottleneck nets default to the fp16 build (csrc/act.cuh)
+    qt = e.act_dtype
+    wq = w.to(qt).float()
     B = 2
     g = torch.Generator().manual_seed(700 + idx)
-    x = torch.randn(B, cin, hin, hin, generator=g).to(torch.bfloat16)
+    x = torch.randn(B, cin, hin, hin, generator=g).to(qt)
     use_res = name.endswith("conv3") and name.split(".")[1] != "0"
-    res = torch.randn(B, cout, hout, hout, generator=g).to(torch.bfloat16) if use_res else None
+    res = torch.randn(B, cout, hout, hout, generator=g).to(qt) if use_res else None
     relu = "downsample" not in name
     want = F.conv2d(x.float(), wq, b, stride=stride, padding=k // 2)
     if use_res:
         want = want + res.float()
     if relu:
         want = F.relu(want)
-    e = G.engine(2, backbone="resnet50")
     x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
     r_nhwc = res.permute(0, 2, 3, 1).contiguous().cuda() if use_res else None
     got = e.debug_conv(head, idx, x_nhwc, r_nhwc, (B, hout, hout, cout), relu)

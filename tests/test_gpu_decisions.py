@@ -21,18 +21,19 @@ MIN_AGREEMENT = 0.999
 def _histogram(margin):
     edges = [0, 0.005, 0.01, 0.02, 0.04, 0.08, 0.16, 1e9]
     h, _ = np.histogram(margin, bins=edges)
-    return ", ".join(f"<{e:g}: {c}" for e, c in zip(edges[1:-1] + ["inf"], h))
+    return ", ".join(f"<{e}: {c}" for e, c in zip([f"{v:g}" for v in edges[1:-1]] + ["inf"], h))
 
 
-@pytest.mark.parametrize("n_heads", [2, 5, 6])
-def test_decisions_match_the_reference_on_held_out_segments(n_heads):
+@pytest.mark.parametrize("n_heads,dtype", [(2, "bf16"), (5, "bf16"), (6, "bf16"), (2, "fp16")])
+def test_decisions_match_the_reference_on_held_out_segments(n_heads, dtype):
+    """bf16 is the named dtype; (2, fp16) is the A/B of the activation format on the same segments."""
     g = G.golden(f"decisions_n{n_heads}.npz")
     want_logits = g["merged_logits"]
     want_labels = g["labels"].astype(np.int64)
     n = want_logits.shape[0]
     assert int(g["n_heads"]) == n_heads and n >= 2048
     from sad_b200.engine import Engine
-    e = Engine(n_heads, torch.device("cuda", 0), max_batch=64)
+    e = Engine(n_heads, torch.device("cuda", 0), max_batch=64, dtype=dtype)
     e.load_merged_state_dict(FX.decision_state_dict(n_heads))
     logits, labels = [], []
     first = int(g["first"])
@@ -49,7 +50,7 @@ def test_decisions_match_the_reference_on_held_out_segments(n_heads):
     agree = labels == want_labels
     margin = G.decision_margin(want_logits)
     binary = (labels == n_heads) == (want_labels == n_heads)                       # Real vs any synthetic
-    print(f"N={n_heads}: {n} held-out segments; max |logit diff| {d.max():.4f} (p99 {np.percentile(d, 99):.4f}, mean "
+    print(f"N={n_heads} ({dtype}): {n} held-out segments; max |logit diff| {d.max():.4f} (p99 {np.percentile(d, 99):.4f}, mean "
           f"{d.mean():.4f}); decision agreement {agree.mean():.5f} ({int((~agree).sum())} differ), Real-vs-synthetic "
           f"agreement {binary.mean():.5f}; reference decision-margin histogram: {_histogram(margin)}; "
           f"margins of differing segments {np.round(margin[~agree], 4).tolist()}")

@@ -20,7 +20,8 @@ LOGIT_TOL = 2e-2
 @pytest.mark.parametrize("tag", ["n2", "n5", "r34_n2", "r50_n2"])
 def test_fused_forward_vs_reference_golden(tag):
     """r34_n2: the resnet34 backbone through the same kernels (depths 3-4-6-3); r50_n2: resnet50, the
-    Bottleneck member (1x1 - 3x3 - 1x1, 2048 features, projection folded into conv3)."""
+    Bottleneck member (1x1 - 3x3 - 1x1, 2048 features, projection folded into conv3), on the fp16 build the Bottleneck
+    nets default to -- every backbone is held to the same 2e-2 logit bound, no waiver."""
     g = G.golden(f"ensemble_{tag}.npz")
     n = int(g["n_heads"])
     e = G.engine(n, backbone={"r34": "resnet34", "r50": "resnet50"}.get(tag[:3], "resnet18"))
@@ -28,19 +29,8 @@ def test_fused_forward_vs_reference_golden(tag):
     logits, probs, labels = e.forward_pcm(x, 0.5)
     torch.cuda.synchronize()
     d = np.abs(logits.cpu().numpy() - g["merged_logits"])
-    print(f"{tag}: max |logit diff| vs reference golden {d.max():.4f}")
+    print(f"{tag} ({e.dtype}): max |logit diff| vs reference golden {d.max():.4f}")
     tol = LOGIT_TOL
-    if tag.startswith("r50"):
-        # 53 convolutions with bf16 activations: the CPU emulation of the SAME data path (bf16 weights / activations, fp32
-        # accumulation) sits 0.047 from the fp32 reference on these segments, so the 2e-2 bound of the resnet18 ensemble
-        # does not transfer; the implementation is held to the emulation instead (1e-2) and to 6e-2 against fp32.
-        from oracle import bf16_emulation as E
-        with torch.no_grad():
-            emu = E.ensemble_bf16(R.waveform_to_image(x.cpu()).unsqueeze(1), G.merged_sd(n, "resnet50")).numpy()
-        de = np.abs(logits.cpu().numpy() - emu)
-        print(f"{tag}: max |logit diff| vs bf16 emulation {de.max():.4f}; emulation vs fp32 {np.abs(emu - g['merged_logits']).max():.4f}")
-        assert de.max() <= 1e-2
-        tol = 6e-2
     assert d.max() <= tol
     np.testing.assert_allclose(probs.cpu().numpy(), g["probs"], rtol=0, atol=tol / 4 + 1e-6)
     names = [str(s) for s in g["class_names"]]
@@ -49,6 +39,37 @@ def test_fused_forward_vs_reference_golden(tag):
     margin = G.decision_margin(g["merged_logits"])
     for a, b, m in zip(mine, want, margin):
         assert a == b or m <= tol, (a, b, m)
+
+
+def test_resnet50_bf16_build_is_bounded_by_its_storage_format():
+    """The same resnet50 golden on the bf16 build: 53 convolutions with bf16 activations sit ~0.045 from fp32 with ANY
+    implementation (the CPU emulation of the same data path does too), which is why Bottleneck nets default to fp16.
+    The bf16 build is held to the emulation of its own data path (1e-2) and to 6e-2 against the reference."""
+    g = G.golden("ensemble_r50_n2.npz")
+    e = G.engine(2, backbone="resnet50", dtype="bf16")
+    x = G.segs(g["seg_ids"]).cuda()
+    logits, _, _ = e.forward_pcm(x, 0.5)
+    with torch.no_grad():
+        emu = E.ensemble_bf16(R.waveform_to_image(x.cpu()).unsqueeze(1), G.merged_sd(2, "resnet50")).numpy()
+    de = np.abs(logits.cpu().numpy() - emu)
+    d = np.abs(logits.cpu().numpy() - g["merged_logits"])
+    print(f"resnet50 bf16 build: vs reference {d.max():.4f}, vs bf16 emulation {de.max():.4f}; emulation vs fp32 "
+          f"{np.abs(emu - g['merged_logits']).max():.4f}")
+    assert de.max() <= 1e-2 and d.max() <= 6e-2
+
+
+def test_resnet18_fp16_build_ab():
+    """A/B of the activation format on the headline network: the fp16 build of the same kernels against the same
+    reference golden (N=5).  bf16 stays the named dtype; fp16 is reported beside it."""
+    g = G.golden("ensemble_n5.npz")
+    x = G.segs(g["seg_ids"]).cuda()
+    out = {}
+    for dt in ("bf16", "fp16"):
+        e = G.engine(5, dtype=dt)
+        out[dt] = np.abs(e.forward_pcm(x, 0.5)[0].cpu().numpy() - g["merged_logits"]).max()
+    print(f"resnet18 x5 max |logit diff| vs reference: bf16 {out['bf16']:.4f}, fp16 {out['fp16']:.4f}")
+    assert out["bf16"] <= LOGIT_TOL and out["fp16"] <= LOGIT_TOL
+    assert out["fp16"] <= out["bf16"] + 1e-3
 
 
 def test_images_entry_matches_fused_entry():
