@@ -205,8 +205,6 @@ def test_decision_goldens_pin_the_v2_fixture(golden_dir, n_heads):
     """tests/golden/decisions_n*.npz were written by the LIVE reference from the committed v2 fixture: the corpus
     regenerates to the same classes, the restatement reproduces the reference logits / labels on a sample, and the
     held-out reference logits keep the margin the 99.9% decision criterion needs (p1 of min |logit| > 2e-2)."""
-    if not os.path.exists(os.path.join(golden_dir, f"decisions_n{n_heads}.npz")):
-        pytest.skip("golden still being generated (oracle.make_golden decisions)")
     g = _load(golden_dir, f"decisions_n{n_heads}.npz")
     z = g["merged_logits"]
     assert z.shape[0] >= 2048 and z.shape[1] == n_heads + 1 and int(g["n_heads"]) == n_heads
