@@ -165,36 +165,64 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
             const int img = r0 / kStrips;
             const int py0 = (r0 % kStrips) * kStripRows;
             const uint2* image = reinterpret_cast<const uint2*>(p.img + static_cast<size_t>(img) * 512 * 512);
+            // Consecutive conv rows share 5 of their 7 image rows (stride 2): chunk ky of row r+1 is chunk ky+2 of row r.
+            // The shifted 16-byte chunks stay in registers and roll down by two per row; only the two new image rows are
+            // loaded -- one conv row AHEAD, so their L2 latency hides behind this row's buffer wait and stores
+            // (ncu, round 2: the UMMA thread spent its time waiting for the builders, and the builders 45% of theirs
+            // on the first use of freshly loaded pixels).
+            uint4 ce[7], co[7];                           // even pixel x = 2i / odd pixel x = 2i+1, per ky
+            uint32_t nw[2][6];                            // raw words of the next row's two new image rows
+            auto load_row = [&](int iy, uint32_t (&w)[6]) {
+                uint2 q0 = make_uint2(0u, 0u), q1 = q0, q2 = q0;
+                if (iy >= 0 && iy < 512) {
+                    const uint2* rp = image + iy * 128;   // 128 uint2 (4 pixels each) per image row
+                    if (i > 0) q0 = __ldg(rp + i - 1);    // pixels [4i-4, 4i+7] = uint2 index i-1, i, i+1
+                    q1 = __ldg(rp + i);
+                    if (i < 127) q2 = __ldg(rp + i + 1);
+                }
+                w[0] = q0.x; w[1] = q0.y; w[2] = q1.x; w[3] = q1.y; w[4] = q2.x; w[5] = q2.y;
+            };
+            auto shift_row = [&](const uint32_t (&w)[6], uint4& e, uint4& o) {
+                // even pixel x = 2i: image pixels [4i-3, 4i+4] = halves starting at the high half of word 0
+                e = make_uint4(__funnelshift_r(w[0], w[1], 16), __funnelshift_r(w[1], w[2], 16),
+                               __funnelshift_r(w[2], w[3], 16), __funnelshift_r(w[3], w[4], 16));
+                // odd pixel x = 2i+1: image pixels [4i-1, 4i+6]
+                o = make_uint4(__funnelshift_r(w[1], w[2], 16), __funnelshift_r(w[2], w[3], 16),
+                               __funnelshift_r(w[3], w[4], 16), __funnelshift_r(w[4], w[5], 16));
+            };
+            {   // first conv row of the unit: all seven image rows
+                const int r = 2 * py0 - 1;
+#pragma unroll
+                for (int ky = 0; ky < 7; ++ky) {
+                    uint32_t w[6];
+                    load_row(2 * r + ky - 3, w);
+                    shift_row(w, ce[ky], co[ky]);
+                }
+                load_row(2 * (r + 1) + 2, nw[0]);
+                load_row(2 * (r + 1) + 3, nw[1]);
+            }
             for (int t = 0; t < kConvRowsPerUnit; ++t, ++arow) {
                 const int b = arow & 1;
                 const int r = 2 * py0 - 1 + t;            // conv output row (may be -1: result is ignored)
-                uint32_t w[7][6];
+                if (t > 0) {
 #pragma unroll
-                for (int ky = 0; ky < 7; ++ky) {
-                    const int iy = 2 * r + ky - 3;
-                    const bool rowok = iy >= 0 && iy < 512;
-                    const uint2* rp = image + iy * 128;   // 128 uint2 (4 pixels each) per image row
-                    // pixels [4i-4, 4i+7] = uint2 index i-1, i, i+1
-                    uint2 q0 = make_uint2(0u, 0u), q1 = q0, q2 = q0;
-                    if (rowok) {
-                        if (i > 0) q0 = __ldg(rp + i - 1);
-                        q1 = __ldg(rp + i);
-                        if (i < 127) q2 = __ldg(rp + i + 1);
+                    for (int ky = 0; ky < 5; ++ky) {
+                        ce[ky] = ce[ky + 2];
+                        co[ky] = co[ky + 2];
                     }
-                    w[ky][0] = q0.x; w[ky][1] = q0.y; w[ky][2] = q1.x; w[ky][3] = q1.y; w[ky][4] = q2.x; w[ky][5] = q2.y;
+                    shift_row(nw[0], ce[5], co[5]);
+                    shift_row(nw[1], ce[6], co[6]);
+                    if (t + 1 < kConvRowsPerUnit) {       // prefetch for row r+1: image rows 2(r+1)+2, 2(r+1)+3
+                        load_row(2 * (r + 1) + 2, nw[0]);
+                        load_row(2 * (r + 1) + 3, nw[1]);
+                    }
                 }
                 mbar_wait(&p_empty[b], ((arow >> 1) & 1) ^ 1);
                 const uint32_t tile = b * kPixTile;
 #pragma unroll
                 for (int ky = 0; ky < 7; ++ky) {
-                    // even pixel x = 2i: image pixels [4i-3, 4i+4] = halves starting at the high half of word 0
-                    const uint4 ce = make_uint4(__funnelshift_r(w[ky][0], w[ky][1], 16), __funnelshift_r(w[ky][1], w[ky][2], 16),
-                                                __funnelshift_r(w[ky][2], w[ky][3], 16), __funnelshift_r(w[ky][3], w[ky][4], 16));
-                    // odd pixel x = 2i+1: image pixels [4i-1, 4i+6]
-                    const uint4 co = make_uint4(__funnelshift_r(w[ky][1], w[ky][2], 16), __funnelshift_r(w[ky][2], w[ky][3], 16),
-                                                __funnelshift_r(w[ky][3], w[ky][4], 16), __funnelshift_r(w[ky][4], w[ky][5], 16));
-                    st_shared_v4(off_e[ky] + tile, ce.x, ce.y, ce.z, ce.w);
-                    st_shared_v4(off_o[ky] + tile, co.x, co.y, co.z, co.w);
+                    st_shared_v4(off_e[ky] + tile, ce[ky].x, ce[ky].y, ce[ky].z, ce[ky].w);
+                    st_shared_v4(off_o[ky] + tile, co[ky].x, co[ky].y, co[ky].z, co[ky].w);
                 }
                 fence_proxy_async();
                 mbar_arrive(&p_full[b]);

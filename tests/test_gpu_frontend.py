@@ -111,6 +111,6 @@ def test_logmel_and_image_vs_reference_golden_256_segments():
     assert err.max() <= 1.0
     np.testing.assert_allclose(ms[:, 0].cpu().numpy(), g["mu"], rtol=0, atol=3e-5)
     np.testing.assert_allclose(ms[:, 1].cpu().numpy(), g["sigma"], rtol=0, atol=3e-5)
-    np.testing.assert_allclose(db.max(axis=(1, 2)), g["db_max"], rtol=0, atol=1e-4 * np.maximum(np.abs(g["db_max"]), 1))
+    assert np.all(np.abs(db.max(axis=(1, 2)) - g["db_max"]) <= 1e-4 * np.maximum(np.abs(g["db_max"]), 1))
     np.testing.assert_allclose(db.astype(np.float64).sum(axis=(1, 2)), g["db_sum"], rtol=0, atol=32128 * 2e-4)
     np.testing.assert_allclose(img.cpu().numpy()[:, ::37, ::41], g["image_sample"], rtol=0, atol=5e-4)
