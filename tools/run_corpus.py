@@ -18,6 +18,35 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def compare(paths):
+    """Bit-identity of per-clip probabilities and labels across runs (different GPU counts, subset vs full corpus)."""
+    import numpy as np
+    runs = []
+    for p in paths:
+        with open(p) as f:
+            j = json.load(f)
+        z = np.load(os.path.splitext(p)[0] + ".npz")
+        runs.append((p, j, z["clip_probs"], z["clip_labels"]))
+    runs.sort(key=lambda r: (r[1]["clips"], r[1]["n_gpus"]))
+    base = runs[0]
+    ok = True
+    rows = []
+    for p, j, probs, labels in runs:
+        n = base[2].shape[0]
+        same = bool(np.array_equal(probs[:n].view(np.uint32), base[2].view(np.uint32)) and np.array_equal(labels[:n], base[3]))
+        ok &= same
+        rows.append({"run": os.path.basename(p), "n_gpus": j["n_gpus"], "clips": j["clips"], "segments": j["segments"],
+                     "segments_per_s": round(j["segments_per_s"], 1), "gather_ms": round(j["gather_ms"], 3),
+                     "first_%d_clips_bit_identical_to_%s" % (n, os.path.basename(base[0])): same})
+    one = [r for r in rows if r["clips"] == rows[0]["clips"]]
+    t1 = next((r["segments_per_s"] for r in one if r["n_gpus"] == 1), None)
+    for r in one:
+        if t1:
+            r["strong_scaling_efficiency"] = round(r["segments_per_s"] / (t1 * r["n_gpus"]), 4)
+    print(json.dumps({"bit_identical_across_runs": ok, "runs": rows}, indent=1))
+    return 0 if ok else 1
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--clips", type=int, default=118750)
@@ -25,8 +54,12 @@ def main():
     ap.add_argument("--heads", type=int, default=6)
     ap.add_argument("--chunk", type=int, default=2048, help="segments generated + processed per pass")
     ap.add_argument("--max-batch", type=int, default=128)
-    ap.add_argument("--out", default=None)
+    ap.add_argument("--out", default=None, help="JSON summary; per-clip results go to the same path with .npz")
+    ap.add_argument("--compare", nargs="+", default=None, help="JSON summaries of finished runs: check that per-clip "
+                    "results are bit-identical (shorter runs against the prefix of longer ones)")
     args = ap.parse_args()
+    if args.compare:
+        return compare(args.compare)
 
     import numpy as np
     import torch
@@ -64,9 +97,11 @@ def main():
             os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
             with open(args.out, "w") as f:
                 json.dump(out, f)
+            np.savez_compressed(os.path.splitext(args.out)[0] + ".npz", clip_probs=r["clip_probs"].cpu().numpy(),
+                                clip_labels=labels)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())
