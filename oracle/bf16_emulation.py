@@ -28,8 +28,15 @@ def fold_bn(w: torch.Tensor, sd: Dict[str, torch.Tensor], bn: str):
     return wf, bf
 
 
+_QT = [torch.bfloat16]          # storage type being emulated: bfloat16 (default build) or float16 (the fp16 build)
+
+
+def set_storage_dtype(dt: torch.dtype) -> None:
+    _QT[0] = dt
+
+
 def _q(x: torch.Tensor) -> torch.Tensor:
-    return x.to(torch.bfloat16).to(torch.float32)
+    return x.to(_QT[0]).to(torch.float32)
 
 
 def backbone_bf16(img1: torch.Tensor, sd: Dict[str, torch.Tensor], p: str, taps: List = None):

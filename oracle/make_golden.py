@@ -227,6 +227,10 @@ def main():
     torch.manual_seed(0)
     IR, MM = reference_api.load()
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "deep":                # the two deepest Bottleneck backbones
+        golden_ensemble(IR, MM, 2, [0, FX.CAL_FIRST], "r101_n2", backbone="resnet101")
+        golden_ensemble(IR, MM, 2, [0, FX.CAL_FIRST], "r152_n2", backbone="resnet152")
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "frontend256":
         golden_frontend_256(IR)
         return

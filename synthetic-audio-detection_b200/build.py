@@ -14,7 +14,7 @@ LIB_F16 = os.path.join(HERE, "libsad_b200_f16.so")   # same sources with -DSAD_A
 SOURCES = ["api.cu", "conv_umma.cu", "conv_umma2.cu", "conv_rows.cu", "block_rows.cu", "stem_fused.cu", "frontend.cu",
            "ingest.cu", "head.cu", "synth.cu"]
 HEADERS = ["conv_umma.h", "frontend.h", "ingest.h", "ingest_taps.h", "head.h", "stem_fused.h", "ptx.cuh", "fft2048.cuh",
-           "synth.h", "act.cuh", os.path.join("..", "..", "include", "sad_b200.h")]
+           "synth.h", "act.cuh", "fft2048r16.cuh", os.path.join("..", "..", "include", "sad_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 
@@ -69,6 +69,15 @@ def build_fft_host_check() -> str:
     if not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out) or \
             os.path.getmtime(os.path.join(CSRC, "fft2048.cuh")) > os.path.getmtime(out):
         subprocess.run(["g++", "-O2", "-std=c++17", "-o", out, src], check=True)
+    return out
+
+
+def build_fft16_host_check() -> str:
+    """CPU test helper for the radix 16-16-8 FFT of the one-launch front end (see csrc/fft16_host_check.cpp)."""
+    out = os.path.join(HERE, "fft16_host_check.bin")
+    srcs = [os.path.join(CSRC, f) for f in ("fft16_host_check.cpp", "fft2048r16.cuh", "fft2048.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(f) > os.path.getmtime(out) for f in srcs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-o", out, srcs[0]], check=True)
     return out
 
 

@@ -239,6 +239,7 @@ struct sad_ctx {
 
     // workspace (per chunk)
     float* d_db = nullptr;              // [Bc][128][251]
+    float* d_scratch = nullptr;         // [Bc][251][128] unclamped dB, frame-major (logmel_kernel phase 1 -> phase 2)
     unsigned* d_segmax = nullptr;       // [Bc]
     float* d_musig = nullptr;           // [Bc][2]
     bf16* d_img = nullptr;              // [Bc][512][512]
@@ -671,6 +672,21 @@ int upload_mel(sad_ctx* c, const float* fb) {
         off += cnt;
     }
     t.n_weights = off;
+    int off4 = 0;
+    for (int m = 0; m < 128; ++m) {
+        const int first4 = t.start[m] & ~3;
+        const int last4 = t.count[m] > 0 ? ((t.start[m] + t.count[m] - 1) | 3) : first4 - 1;
+        const int cnt4 = last4 - first4 + 1;
+        if (off4 + cnt4 > 2816) return fail(c, SAD_EINVAL, "mel filterbank too wide for the 16-byte tap table");
+        t.start4[m] = first4;
+        t.count4[m] = cnt4;
+        t.off4[m] = off4;
+        for (int k = 0; k < cnt4; ++k) {
+            const int bin = first4 + k;
+            t.w4[off4 + k] = (bin >= t.start[m] && bin < t.start[m] + t.count[m]) ? t.w[t.off[m] + bin - t.start[m]] : 0.f;
+        }
+        off4 += cnt4;
+    }
     CU_OK(c, cudaMemcpy(c->d_mel, &t, sizeof(t), cudaMemcpyHostToDevice));
     return SAD_OK;
 }
@@ -823,6 +839,7 @@ int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const c
     }
 
     CU_OK(c, dalloc(&c->d_db, Bc * 128 * 251));
+    CU_OK(c, dalloc(&c->d_scratch, Bc * 128 * 251));
     CU_OK(c, dalloc(&c->d_segmax, Bc));
     CU_OK(c, dalloc(&c->d_musig, Bc * 2));
     CU_OK(c, dalloc(&c->d_img, Bc * 512 * 512));
@@ -881,7 +898,7 @@ int sad_destroy(sad_ctx* c) {
     }
     for (int i = 0; i < kMaxConvs; ++i) cudaFree(c->d_bias_fused[i]);
     void* ptrs[] = {c->d_w_stem1, c->d_w_stem3, c->d_w1t, c->d_b1, c->d_w2t, c->d_b2, c->d_w3, c->d_b3, c->d_window,
-                    c->d_mel, c->d_resize, c->d_db, c->d_segmax, c->d_musig, c->d_img, c->d_A3, c->d_stem,
+                    c->d_mel, c->d_resize, c->d_db, c->d_scratch, c->d_segmax, c->d_musig, c->d_img, c->d_A3, c->d_stem,
                     c->d_buf[0], c->d_buf[1], c->d_buf[2], c->d_buf[3], c->d_head_logits, c->d_pcm[0], c->d_pcm[1],
                     c->d_res_logits, c->d_res_probs, c->d_res_labels, c->d_tap_first, c->d_tap_w, c->d_ident128};
     for (void* p : ptrs) cudaFree(p);
@@ -1026,7 +1043,7 @@ int sad_frontend_logmel(sad_ctx* c, const float* pcm, int B, float* logmel_db, f
         CU_OK(c, sad::frontend_logmel_launch(pcm + static_cast<size_t>(b0) * SAD_SEGMENT_SAMPLES, nb, c->d_window, c->d_mel,
                                              c->d_db, c->d_segmax,
                                              logmel_db ? logmel_db + static_cast<size_t>(b0) * 128 * 251 : nullptr,
-                                             c->d_musig, st, &c->launches));
+                                             c->d_musig, c->d_scratch, st, &c->launches));
         if (mu_sigma)
             CU_OK(c, cudaMemcpyAsync(mu_sigma + 2 * static_cast<size_t>(b0), c->d_musig, 2 * nb * sizeof(float),
                                      cudaMemcpyDeviceToDevice, st));
@@ -1044,7 +1061,7 @@ int sad_frontend_image(sad_ctx* c, const float* pcm, int B, float* image, void* 
     for (int b0 = 0; b0 < B; b0 += c->Bc) {
         const int nb = B - b0 < c->Bc ? B - b0 : c->Bc;
         CU_OK(c, sad::frontend_logmel_launch(pcm + static_cast<size_t>(b0) * SAD_SEGMENT_SAMPLES, nb, c->d_window, c->d_mel,
-                                             c->d_db, c->d_segmax, nullptr, c->d_musig, st, &c->launches));
+                                             c->d_db, c->d_segmax, nullptr, c->d_musig, c->d_scratch, st, &c->launches));
         CU_OK(c, sad::image_launch_f32(c->d_db, c->d_musig, c->d_resize, image + static_cast<size_t>(b0) * 512 * 512, nb, st,
                                        &c->launches));
     }
@@ -1331,7 +1348,7 @@ int sad_debug_stem(sad_ctx* c, const float* pcm, int B, void* out, void* stream)
     ON_DEVICE(c);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     WorkspaceOrder ws_order__(c, st);
-    CU_OK(c, sad::frontend_logmel_launch(pcm, B, c->d_window, c->d_mel, c->d_db, c->d_segmax, nullptr, c->d_musig, st,
+    CU_OK(c, sad::frontend_logmel_launch(pcm, B, c->d_window, c->d_mel, c->d_db, c->d_segmax, nullptr, c->d_musig, c->d_scratch, st,
                                          &c->launches));
     CU_OK(c, sad::image_launch_bf16(c->d_db, c->d_musig, c->d_resize, c->d_img, B, st, &c->launches));
     sad::StemLaunch sl = c->stem1;
@@ -1380,7 +1397,7 @@ int run_chunk(sad_ctx* c, const float* pcm, const float* x_nchw, int B, float th
     if (pcm) {
         {
             ProfScope ps(c, SAD_PROF_FRONTEND, st);
-            CU_OK(c, sad::frontend_logmel_launch(pcm, B, c->d_window, c->d_mel, c->d_db, c->d_segmax, nullptr, c->d_musig, st,
+            CU_OK(c, sad::frontend_logmel_launch(pcm, B, c->d_window, c->d_mel, c->d_db, c->d_segmax, nullptr, c->d_musig, c->d_scratch, st,
                                                  &c->launches));
         }
         {

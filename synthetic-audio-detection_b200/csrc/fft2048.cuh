@@ -34,7 +34,7 @@ constexpr int kFftN = 2048;
 constexpr int kFftThreads = 256;
 constexpr int kFftBuf = 2304;   // floats per component: max padded index is pad2(2047) = 2295
 
-struct cpx {
+struct alignas(8) cpx {   // 8-byte aligned: one LDS.64 / STS.64 per element
     float x, y;
 };
 

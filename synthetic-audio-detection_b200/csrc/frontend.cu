@@ -9,8 +9,10 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 
 #include "fft2048.cuh"
+#include "fft2048r16.cuh"
 #include "frontend.h"
 
 namespace sad {
@@ -201,6 +203,224 @@ __global__ void __launch_bounds__(512) db_clamp_stats_kernel(float* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// logmel_kernel (round 2): the whole front end of a segment in ONE launch -- framing, Hann, 126 packed 2048-point FFTs
+// (radix 16-16-8, fft2048r16.cuh), |X|^2, banded mel projection, 10*log10, the per-segment max for the top_db clamp,
+// the clamp, mean / unbiased std, and the final [mel][frame] layout.  Replaces fill_u32 + stft_mel_kernel +
+// db_clamp_stats_kernel (three launches, the unclamped dB written, re-read, re-written and read again by the image
+// kernel, a global atomic max per CTA).
+//   CTA = 384 threads = 3 groups of 128; a group transforms one frame PAIR at a time (126 pairs = 42 rounds x 3 groups,
+//   no idle round) and synchronises on its own named barrier, so the three groups hide each other's barrier and
+//   shared-memory latency.  Persistent: CTA c handles segments c, c + gridDim.x, ...
+//   Phase 1 writes unclamped dB FRAME-major to a scratch buffer (thread = mel band: coalesced 512-byte rows; the
+//   segment's 128 KB stay in L2); phase 2 (same CTA, after a block-wide max) clamps, accumulates the statistics in
+//   fp64 and transposes 32x32 tiles through shared memory into the [mel][frame] layout the reference produces.
+constexpr int kFeGroups = 3;
+constexpr int kFeThreads = kFft16Threads * kFeGroups;   // 384
+constexpr int kPairs = (kFrames + 1) / 2;               // 126
+static_assert(kPairs % kFeGroups == 0, "frame pairs must divide evenly over the groups");
+
+struct __align__(16) FeSmem {
+    cpx buf[kFeGroups][kFft16Slots];      // 3 x 17 KB; phase 2 reuses it as 12 transposition tiles of [32][33] floats
+    float pw[kFeGroups][2][772];          // power spectra of the group's two frames, bins 0..768 (769..771 stay zero)
+    float mel_w[2816];                    // taps widened to 4-bin boundaries (MelTable::w4)
+    float red_max[kFeThreads / 32];
+    double red_s1[kFeThreads / 32];
+    double red_s2[kFeThreads / 32];
+};
+static_assert(sizeof(cpx) * kFeGroups * kFft16Slots >= (kFeThreads / 32) * 32 * 33 * sizeof(float), "tile aliasing");
+
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;\n" ::"r"(g + 1), "r"(kFft16Threads) : "memory"); }
+
+__global__ void __launch_bounds__(kFeThreads, 1)
+    logmel_kernel(const float* __restrict__ pcm, const float* __restrict__ window, const MelTable* __restrict__ mel,
+                  float* __restrict__ scratch /*[B][251][128] unclamped dB*/, float* __restrict__ db /*[B][128][251]*/,
+                  float* __restrict__ out_db /*optional copy*/, float* __restrict__ mu_sigma, int B, float top_db) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    FeSmem& s = *reinterpret_cast<FeSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int g = tid >> 7;
+    const int t = tid & 127;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    // per-thread constants of the whole kernel: twiddles (exact look-ups of exp(-2 pi i n / 2048)) and window samples
+    cpx tw2[15], tw3[2][7];
+    float win[16];
+#pragma unroll
+    for (int q = 1; q < 16; ++q) {
+        float sn, cs;
+        sincospif(static_cast<float>(fft16_tw2_angle(t, q)) * (1.0f / 1024.0f), &sn, &cs);
+        tw2[q - 1] = {cs, -sn};
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int q = 1; q < 8; ++q) {
+            float sn, cs;
+            sincospif(static_cast<float>(fft16_tw3_angle(t, h, q)) * (1.0f / 1024.0f), &sn, &cs);
+            tw3[h][q - 1] = {cs, -sn};
+        }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) win[q] = __ldg(window + t + 128 * q);
+    for (int i = tid; i < 2816; i += kFeThreads) s.mel_w[i] = mel->w4[i];
+    for (int i = tid; i < kFeGroups * 2 * 772; i += kFeThreads) (&s.pw[0][0][0])[i] = 0.f;   // zero-weight taps may read bins 769..771
+    __syncthreads();
+    // mel band t for the pair's first frame, band 127-t for the second: the two tap counts sum to about the same for
+    // every thread (2..36 taps per band, growing with the band index), so the four warps of a group finish together.
+    // Taps and weights are read four at a time (16-byte loads on 4-bin boundaries; the widening taps have weight 0, which
+    // leaves the sum bit-identical): scalar loads at per-lane offsets cost 3.3 wavefronts each (ncu, round 2).
+    const int ma = t, mb = kMels - 1 - t;
+    const int sa = __ldg(&mel->start4[ma]), ca = __ldg(&mel->count4[ma]), oa = __ldg(&mel->off4[ma]);
+    const int sb = __ldg(&mel->start4[mb]), cb = __ldg(&mel->count4[mb]), ob = __ldg(&mel->off4[mb]);
+    cpx* buf = s.buf[g];
+
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* x = pcm + static_cast<size_t>(b) * kSeg;
+        float* scr = scratch + static_cast<size_t>(b) * kFrames * kMels;
+        float local_max = -INFINITY;
+        // raw samples of a frame pair: x[t + 128q] of frame 2p (ra) and of frame 2p+1 (rb); loaded one pair AHEAD (issued
+        // after pass 3, consumed at the top of the next iteration) so that the L2 latency hides behind the power / mel stage
+        float ra[16], rb[16];
+        auto load_pair = [&](int p) {
+            const int fa = 2 * p;
+            const bool has_b = fa + 1 < kFrames;
+            const bool interior = (fa >= 2) && (fa + 1 <= kFrames - 3);   // no reflection needed for either frame
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int ja = fa * 512 + t + 128 * q;                   // position in the reflect-padded signal
+                if (interior) {
+                    ra[q] = __ldg(x + ja - 1024);
+                    rb[q] = __ldg(x + ja - 512);
+                } else {
+                    ra[q] = __ldg(x + reflect_index(ja));
+                    rb[q] = has_b ? __ldg(x + reflect_index(ja + 512)) : 0.f;
+                }
+            }
+        };
+        load_pair(g);
+        for (int p = g; p < kPairs; p += kFeGroups) {
+            const int fa = 2 * p;
+            const bool has_b = fa + 1 < kFrames;
+            cpx v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = {ra[q] * win[q], rb[q] * win[q]};
+            fft16_pass1(t, v, buf);
+            group_bar(g);
+            fft16_pass2(t, tw2, buf);
+            group_bar(g);
+            fft16_pass3(t, tw3, buf);
+            group_bar(g);
+            if (p + kFeGroups < kPairs) load_pair(p + kFeGroups);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const int k = t + 128 * i;
+                if (k <= 768) {
+                    float pa, pb;
+                    fft16_split_power(buf, k, pa, pb);
+                    s.pw[g][0][k] = pa;
+                    s.pw[g][1][k] = pb;
+                }
+            }
+            group_bar(g);
+            {
+                const float4* pp = reinterpret_cast<const float4*>(s.pw[g][0] + sa);
+                const float4* ww = reinterpret_cast<const float4*>(s.mel_w + oa);
+                float acc = 0.f;
+                for (int i = 0; i < ca / 4; ++i) {
+                    const float4 pv = pp[i], wv = ww[i];
+                    acc = fmaf(pv.x, wv.x, acc);
+                    acc = fmaf(pv.y, wv.y, acc);
+                    acc = fmaf(pv.z, wv.z, acc);
+                    acc = fmaf(pv.w, wv.w, acc);
+                }
+                const float d = 10.0f * log10f(fmaxf(acc, 1e-10f));
+                scr[fa * kMels + ma] = d;
+                local_max = fmaxf(local_max, d);
+            }
+            if (has_b) {
+                const float4* pp = reinterpret_cast<const float4*>(s.pw[g][1] + sb);
+                const float4* ww = reinterpret_cast<const float4*>(s.mel_w + ob);
+                float acc = 0.f;
+                for (int i = 0; i < cb / 4; ++i) {
+                    const float4 pv = pp[i], wv = ww[i];
+                    acc = fmaf(pv.x, wv.x, acc);
+                    acc = fmaf(pv.y, wv.y, acc);
+                    acc = fmaf(pv.z, wv.z, acc);
+                    acc = fmaf(pv.w, wv.w, acc);
+                }
+                const float d = 10.0f * log10f(fmaxf(acc, 1e-10f));
+                scr[(fa + 1) * kMels + mb] = d;
+                local_max = fmaxf(local_max, d);
+            }
+            // the next pair's pass-1 stores only touch `buf` (all its readers passed the barrier above); pw is rewritten
+            // after three more group barriers
+        }
+        // ---- phase 2: segment max -> clamp, statistics, [frame][mel] -> [mel][frame]
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+        if (lane == 0) s.red_max[warp] = local_max;
+        __syncthreads();                                   // also orders this CTA's scratch writes before its reads below
+        float seg_max = s.red_max[0];
+#pragma unroll
+        for (int i = 1; i < kFeThreads / 32; ++i) seg_max = fmaxf(seg_max, s.red_max[i]);
+        const float floor_db = seg_max - top_db;
+        float (*tile)[33] = reinterpret_cast<float (*)[33]>(reinterpret_cast<float*>(s.buf) + warp * 32 * 33);
+        float* dst = db + static_cast<size_t>(b) * kMels * kFrames;
+        float* dst2 = out_db ? out_db + static_cast<size_t>(b) * kMels * kFrames : nullptr;
+        double s1 = 0.0, s2 = 0.0;
+        // 8 frame blocks x 4 mel blocks of 32x32; warp w takes tiles w, w + 12, ...
+        for (int tl = warp; tl < 32; tl += kFeThreads / 32) {
+            const int f0 = (tl >> 2) * 32, m0 = (tl & 3) * 32;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                const int f = f0 + r;
+                float vv = 0.f;
+                if (f < kFrames) {
+                    vv = fmaxf(scr[f * kMels + m0 + lane], floor_db);
+                    s1 += vv;
+                    s2 += static_cast<double>(vv) * vv;
+                }
+                tile[r][lane] = vv;
+            }
+            __syncwarp();
+            const int f = f0 + lane;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                if (f < kFrames) {
+                    const float vv = tile[lane][r];
+                    dst[(m0 + r) * kFrames + f] = vv;
+                    if (dst2) dst2[(m0 + r) * kFrames + f] = vv;
+                }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+            s.red_s1[warp] = s1;
+            s.red_s2[warp] = s2;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            constexpr int n = kMels * kFrames;
+            double a = 0, q = 0;
+            for (int i = 0; i < kFeThreads / 32; ++i) {
+                a += s.red_s1[i];
+                q += s.red_s2[i];
+            }
+            const double mean = a / n;
+            double var = (q - a * mean) / (n - 1);
+            if (var < 0) var = 0;
+            mu_sigma[2 * b] = static_cast<float>(mean);
+            mu_sigma[2 * b + 1] = static_cast<float>(sqrt(var));
+        }
+        __syncthreads();                                   // tiles alias the FFT buffers of the next segment
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ T to_out(float v);
 template <>
@@ -361,23 +581,40 @@ __global__ void fill_u32_kernel(unsigned* p, unsigned v, int n) {
 size_t stft_smem_bytes() { return sizeof(StftSmem); }
 
 cudaError_t frontend_logmel_launch(const float* pcm, int B, const float* window, const MelTable* mel, float* db_work,
-                                   unsigned* segmax, float* out_db, float* mu_sigma, cudaStream_t stream, long long* launches) {
-    {
-        static std::atomic<bool> done[64];   // per device; two contexts may launch from two host threads
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
+                                   unsigned* segmax, float* out_db, float* mu_sigma, float* scratch, cudaStream_t stream,
+                                   long long* launches) {
+    static const bool v1 = [] {
+        const char* e = getenv("SAD_FE_V1");     // A/B switch: the round-1 front end (three launches, radix 8-8-8-4)
+        return e && atoi(e) != 0;
+    }();
+    static std::atomic<bool> done[64];   // per device; two contexts may launch from two host threads
+    static std::atomic<int> sms[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!done[dev].load(std::memory_order_acquire)) {
+        e = cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(StftSmem)));
         if (e != cudaSuccess) return e;
-        if (dev < 0 || dev >= 64 || !done[dev].load(std::memory_order_acquire)) {
-            e = cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(sizeof(StftSmem)));
-            if (e != cudaSuccess) return e;
-            if (dev >= 0 && dev < 64) done[dev].store(true, std::memory_order_release);
-        }
+        e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(FeSmem)));
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        sms[dev].store(n, std::memory_order_relaxed);
+        done[dev].store(true, std::memory_order_release);
     }
-    fill_u32_kernel<<<(B + 255) / 256, 256, 0, stream>>>(segmax, 0u, B);   // 0 orders below every float
-    stft_mel_kernel<<<dim3(kFrameGroups, B), kFftThreads, sizeof(StftSmem), stream>>>(pcm, window, mel, db_work, segmax);
-    db_clamp_stats_kernel<<<B, 512, 0, stream>>>(db_work, segmax, out_db, mu_sigma, 80.0f);
-    if (launches) *launches += 3;
+    if (v1 || !scratch) {
+        fill_u32_kernel<<<(B + 255) / 256, 256, 0, stream>>>(segmax, 0u, B);   // 0 orders below every float
+        stft_mel_kernel<<<dim3(kFrameGroups, B), kFftThreads, sizeof(StftSmem), stream>>>(pcm, window, mel, db_work, segmax);
+        db_clamp_stats_kernel<<<B, 512, 0, stream>>>(db_work, segmax, out_db, mu_sigma, 80.0f);
+        if (launches) *launches += 3;
+        return cudaGetLastError();
+    }
+    const int n_sm = sms[dev].load(std::memory_order_relaxed);
+    logmel_kernel<<<B < n_sm ? B : n_sm, kFeThreads, sizeof(FeSmem), stream>>>(pcm, window, mel, scratch, db_work, out_db, mu_sigma,
+                                                                             B, 80.0f);
+    if (launches) *launches += 1;
     return cudaGetLastError();
 }
 

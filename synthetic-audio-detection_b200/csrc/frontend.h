@@ -15,6 +15,12 @@ struct MelTable {
     int count[128];
     int off[128];
     float w[1536];
+    // the same bands widened to 4-bin boundaries with zero weights (logmel_kernel reads taps and weights with 16-byte
+    // loads): start4 = start & ~3, count4 a multiple of 4, weights at w4[off4 ...] (off4 a multiple of 4)
+    int start4[128];
+    int count4[128];
+    int off4[128];
+    float w4[2816];
 };
 
 // Two-tap anti-aliased bilinear weights (ATen upsample_bilinear2d_aa), 251 -> 512 columns, 128 -> 512 rows.
@@ -27,8 +33,11 @@ struct ResizeTable {
 
 size_t stft_smem_bytes();
 
+// db_work [B][128][251] receives the final (clamped) log-mel dB, out_db (optional) a copy, mu_sigma [B][2] the mean and
+// unbiased std.  scratch [B][251][128]: frame-major unclamped dB of the one-launch kernel (nullptr or SAD_FE_V1=1: the
+// round-1 three-launch path, which needs segmax [B]).
 cudaError_t frontend_logmel_launch(const float* pcm, int B, const float* window, const MelTable* mel, float* db_work,
-                                   unsigned* segmax, float* out_db, float* mu_sigma, cudaStream_t stream,
+                                   unsigned* segmax, float* out_db, float* mu_sigma, float* scratch, cudaStream_t stream,
                                    long long* launches);
 cudaError_t image_launch_f32(const float* db, const float* mu_sigma, const ResizeTable* rt, float* img, int B,
                              cudaStream_t stream, long long* launches);

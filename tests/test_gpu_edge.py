@@ -92,8 +92,8 @@ def test_profile_counters():
     e.forward_pcm(x, 0.5)
     ms, n = e.profile_read()
     e.profile_enable(False)
-    # front end (3), image, stem, 2 fused layer1 blocks + 12 convs (downsample folded into conv2), head + merge
-    assert e.launches - n0 == 3 + 1 + 1 + 14 + 2
+    # front end (1), image, stem, 2 fused layer1 blocks + 12 convs (downsample folded into conv2), head + merge
+    assert e.launches - n0 == 1 + 1 + 1 + 14 + 2
     assert sum(1 for v in n[:40] if v) == 15 and n[e.PROF_FRONTEND] == 1 and n[e.PROF_HEAD] == 1
     assert all(v >= 0 for v in ms) and sum(ms) > 0
 

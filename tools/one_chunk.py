@@ -3,10 +3,10 @@
 through a 6-head engine (the first warms up).  Profiling target:
 
     python tools/one_chunk.py > gpurun_out/plain.log 2>&1 &&
-    ncu --set full --clock-control none --import-source on -s 22 -c 21 -o gpurun_out/r02_full python tools/one_chunk.py
+    ncu --set full --clock-control none --import-source on -s 20 -c 19 -o gpurun_out/r02_full python tools/one_chunk.py
 
-Launch order per chunk: fill, stft_mel, db_clamp_stats, image, stem_fused, 2 x block_rows, 4 x conv_umma<128,2,TR>,
-8 x conv_umma2<256>, head_mlp, merge_decide (21); one synth kernel precedes the first chunk."""
+Launch order per chunk: logmel, image, stem_fused, 2 x block_rows, 4 x conv_umma<128,2,TR>,
+8 x conv_umma2<256>, head_mlp, merge_decide (19); one synth kernel precedes the first chunk."""
 import os
 import sys
 
