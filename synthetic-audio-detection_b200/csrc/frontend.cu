@@ -429,32 +429,50 @@ template <>
 __device__ __forceinline__ act_t to_out<act_t>(float v) { return act_from_float(v); }
 
 // Standardise + separable 2-tap resize (horizontal first, taps accumulated with one fma each, as ATen does).
-// grid (512 rows, B), 256 threads.  The two source rows of an output row are standardised ONCE into shared memory
-// (502 IEEE divisions per CTA instead of 4 per output pixel), then every thread produces two output columns.
+// grid (512 / kImgRows, B), 256 threads.  A CTA produces kImgRows = 8 consecutive output rows: they read at most 4 source
+// rows (the vertical scale is 4), which are standardised ONCE into shared memory (<= 1004 IEEE divisions per CTA instead of
+// 4 per output pixel; one CTA per output row spent most of its time on launch / drain: 65 536 CTAs per chunk).
+// Per pixel the arithmetic is unchanged.
+constexpr int kImgRows = 8;
 template <typename T>
 __global__ void __launch_bounds__(256) image_kernel(const float* __restrict__ db, const float* __restrict__ mu_sigma,
                                                     const ResizeTable* __restrict__ rt, T* __restrict__ img) {
-    __shared__ float rows[2][256];
-    const int b = blockIdx.y, y = blockIdx.x;
+    __shared__ float rows[4][256];
+    __shared__ int x0s[512];
+    __shared__ float wxs[1024];
+    const int b = blockIdx.y, yb = blockIdx.x * kImgRows;
     const float mu = mu_sigma[2 * b];
     const float den = mu_sigma[2 * b + 1] + 1e-6f;
     const float* src = db + static_cast<size_t>(b) * kMels * kFrames;
-    const int y0 = rt->h_idx[y];
-    const int y1 = min(y0 + 1, kMels - 1);
-    const float wy0 = rt->h_w[2 * y], wy1 = rt->h_w[2 * y + 1];
-    if (threadIdx.x < kFrames) {
-        rows[0][threadIdx.x] = __fdiv_rn(src[y0 * kFrames + threadIdx.x] - mu, den);
-        rows[1][threadIdx.x] = __fdiv_rn(src[y1 * kFrames + threadIdx.x] - mu, den);
+    const int r_lo = rt->h_idx[yb];                                   // first source row any of the 8 output rows reads
+    for (int i = threadIdx.x; i < 4 * 256; i += 256) {
+        const int r = i >> 8, x = i & 255;
+        const int sr = min(r_lo + r, kMels - 1);
+        if (x < kFrames) rows[r][x] = __fdiv_rn(src[sr * kFrames + x] - mu, den);
+    }
+    for (int x = threadIdx.x; x < 512; x += 256) {
+        x0s[x] = rt->w_idx[x];
+        wxs[2 * x] = rt->w_w[2 * x];
+        wxs[2 * x + 1] = rt->w_w[2 * x + 1];
     }
     __syncthreads();
-    for (int x = threadIdx.x; x < 512; x += 256) {
-        const int x0 = rt->w_idx[x];
-        const int x1 = min(x0 + 1, kFrames - 1);
-        const float wx0 = rt->w_w[2 * x], wx1 = rt->w_w[2 * x + 1];
-        const float t0 = __fmaf_rn(rows[0][x1], wx1, __fmul_rn(rows[0][x0], wx0));
-        const float t1 = __fmaf_rn(rows[1][x1], wx1, __fmul_rn(rows[1][x0], wx0));
-        const float v = __fmaf_rn(t1, wy1, __fmul_rn(t0, wy0));
-        img[(static_cast<size_t>(b) * 512 + y) * 512 + x] = to_out<T>(v);
+#pragma unroll
+    for (int ry = 0; ry < kImgRows; ++ry) {
+        const int y = yb + ry;
+        const int y0 = rt->h_idx[y];
+        const int y1 = min(y0 + 1, kMels - 1);
+        const float wy0 = rt->h_w[2 * y], wy1 = rt->h_w[2 * y + 1];
+        const float* ra = rows[y0 - r_lo];
+        const float* rb = rows[y1 - r_lo];
+        for (int x = threadIdx.x; x < 512; x += 256) {
+            const int x0 = x0s[x];
+            const int x1 = min(x0 + 1, kFrames - 1);
+            const float wx0 = wxs[2 * x], wx1 = wxs[2 * x + 1];
+            const float t0 = __fmaf_rn(ra[x1], wx1, __fmul_rn(ra[x0], wx0));
+            const float t1 = __fmaf_rn(rb[x1], wx1, __fmul_rn(rb[x0], wx0));
+            const float v = __fmaf_rn(t1, wy1, __fmul_rn(t0, wy0));
+            img[(static_cast<size_t>(b) * 512 + y) * 512 + x] = to_out<T>(v);
+        }
     }
 }
 
@@ -620,13 +638,13 @@ cudaError_t frontend_logmel_launch(const float* pcm, int B, const float* window,
 
 cudaError_t image_launch_f32(const float* db, const float* mu_sigma, const ResizeTable* rt, float* img, int B,
                              cudaStream_t stream, long long* launches) {
-    image_kernel<float><<<dim3(512, B), 256, 0, stream>>>(db, mu_sigma, rt, img);
+    image_kernel<float><<<dim3(512 / kImgRows, B), 256, 0, stream>>>(db, mu_sigma, rt, img);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
 cudaError_t image_launch_bf16(const float* db, const float* mu_sigma, const ResizeTable* rt, act_t* img, int B,
                               cudaStream_t stream, long long* launches) {
-    image_kernel<act_t><<<dim3(512, B), 256, 0, stream>>>(db, mu_sigma, rt, img);
+    image_kernel<act_t><<<dim3(512 / kImgRows, B), 256, 0, stream>>>(db, mu_sigma, rt, img);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -13,28 +13,40 @@ namespace sad {
 
 namespace {
 
-// grid (B, H), 256 threads: one CTA per (segment, head) -- the kernel is latency-bound, so it wants many CTAs
-// (measured: batching 4 or 8 segments per CTA to re-use the 1.5 MB of L2-resident weights was 2x slower).
-// feats: NHWC bf16 [H*B][256 px][F]; weights transposed [in][out] fp32 so a thread reads 4 consecutive outputs with
+// grid (ceil(B / kSegs), H), 256 threads: one CTA per (head, group of kSegs segments).  Every weight a thread loads is
+// used for all kSegs segments, so the L2 -> SM weight stream is 1.5 MB per kSegs segments instead of per segment
+// (ncu, round 2: with one segment per CTA the kernel moves 1.15 GB of weights per chunk out of L2 and takes 105 us
+// against a 31 us floor for reading the features).  Per segment the arithmetic (K split, summation order) does not
+// depend on kSegs, so results are bit-identical for every grouping.  MEASURED: grouping 2 or 4 segments is SLOWER
+// (fewer, longer CTAs: the pooling and GEMV phases of a CTA are serial and nothing overlaps them), so kSegs = 1 ships;
+// the switch stays for the next attempt (more warps per CTA, or the pooling fused into layer4's epilogue).
+// feats: NHWC [H*B][256 px][F] (act_t); weights transposed [in][out] fp32 so a thread reads 4 consecutive outputs with
 // one 16-byte load; the K dimension is split over thread groups and reduced through shared memory.
 // F = trunk feature width: 512 (resnet18/34) or 2048 (Bottleneck nets).
+#ifndef SAD_HEAD_SEGS
+#define SAD_HEAD_SEGS 1   // measured on B200 (6 heads, chunk 128): 1 -> 1.97 ms per step, 2 -> 2.43, 4 -> 2.34
+#endif
+__host__ __device__ constexpr int head_segs(int F) { return F <= 512 ? SAD_HEAD_SEGS : (SAD_HEAD_SEGS > 2 ? 2 : SAD_HEAD_SEGS); }   // segments per CTA (static shared memory <= 48 KB)
+
 template <int F>
 __global__ void __launch_bounds__(256) head_mlp_kernel(const act_t* __restrict__ feats, HeadWeights hw, int B,
                                                        float* __restrict__ head_logits) {
     constexpr int kC8 = F / 8;            // 16-byte channel groups per pixel
     constexpr int kG = 256 / kC8;         // pixel groups in the pooling phase (4 for F=512, 1 for F=2048)
     constexpr int kPx = 256 / kG;         // pixels per group
-    __shared__ __align__(16) float part_flat[2048];   // partial sums (pool: kG pixel groups x F; layers: K splits x 512)
-    float (*part)[512] = reinterpret_cast<float (*)[512]>(part_flat);
-    __shared__ __align__(16) float pooled[F];
-    __shared__ __align__(16) float h1[512];
-    __shared__ __align__(16) float h2[256];
-    __shared__ float red[2][8];
-    const int b = blockIdx.x, h = blockIdx.y, t = threadIdx.x;
-    const size_t n = static_cast<size_t>(h) * B + b;
+    constexpr int kSegs = head_segs(F);
+    __shared__ __align__(16) float part_flat[kSegs][2048];   // partial sums (pool: kG pixel groups x F; layers: K splits x 512)
+    __shared__ __align__(16) float act_buf[kSegs][F];        // pooled features, then (after a barrier each) h1 and h2
+    float (*pooled)[F] = act_buf;
+    float (*h1)[F] = act_buf;                                // first 512 entries of a row
+    float (*h2)[F] = act_buf;                                // first 256 entries of a row
+    __shared__ float red[kSegs][2][8];
+    const int b0 = blockIdx.x * kSegs, h = blockIdx.y, t = threadIdx.x;
+    const int nseg = B - b0 < kSegs ? B - b0 : kSegs;
 
     // ---- global average pool over the 16x16 map: thread = (pixel group g of 64 px, 8 channels c8)
-    {
+    for (int sg = 0; sg < nseg; ++sg) {
+        const size_t n = static_cast<size_t>(h) * B + b0 + sg;
         const int c8 = t % kC8, g = t / kC8;
         const uint4* f = reinterpret_cast<const uint4*>(feats + n * 256 * F) + c8;   // kC8 uint4 per pixel
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -49,68 +61,95 @@ __global__ void __launch_bounds__(256) head_mlp_kernel(const act_t* __restrict__
             }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) part_flat[g * F + c8 * 8 + j] = acc[j];
+        for (int j = 0; j < 8; ++j) part_flat[sg][g * F + c8 * 8 + j] = acc[j];
     }
     __syncthreads();
-    for (int c = t; c < F; c += 256) {
-        float sum = part_flat[c];
+    for (int sg = 0; sg < kSegs; ++sg)
+        for (int c = t; c < F; c += 256) {
+            float sum = 0.f;
+            if (sg < nseg) {
+                sum = part_flat[sg][c];
 #pragma unroll
-        for (int g = 1; g < kG; ++g) sum += part_flat[g * F + c];
-        pooled[c] = sum * (1.0f / 256.0f);
-    }
+                for (int g = 1; g < kG; ++g) sum += part_flat[sg][g * F + c];
+            }
+            pooled[sg][c] = sum * (1.0f / 256.0f);          // missing segments of a ragged tail run on zeros
+        }
     __syncthreads();
 
     // ---- Linear(F,512)+BN folded, ReLU: thread = (K half kh, 4 outputs o4)
     {
         const int o4 = t & 127, kh = t >> 7;
         const float4* w1 = reinterpret_cast<const float4*>(hw.w1t + static_cast<size_t>(h) * F * 512) + o4;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 a[kSegs];
+#pragma unroll
+        for (int sg = 0; sg < kSegs; ++sg) a[sg] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
         for (int i = kh * (F / 2); i < (kh + 1) * (F / 2); ++i) {
-            const float x = pooled[i];
             const float4 w = __ldg(w1 + i * 128);
-            a.x = fmaf(x, w.x, a.x); a.y = fmaf(x, w.y, a.y); a.z = fmaf(x, w.z, a.z); a.w = fmaf(x, w.w, a.w);
+#pragma unroll
+            for (int sg = 0; sg < kSegs; ++sg) {
+                const float x = pooled[sg][i];
+                a[sg].x = fmaf(x, w.x, a[sg].x); a[sg].y = fmaf(x, w.y, a[sg].y);
+                a[sg].z = fmaf(x, w.z, a[sg].z); a[sg].w = fmaf(x, w.w, a[sg].w);
+            }
         }
-        *reinterpret_cast<float4*>(&part[kh][o4 * 4]) = a;
+#pragma unroll
+        for (int sg = 0; sg < kSegs; ++sg) *reinterpret_cast<float4*>(&part_flat[sg][kh * 512 + o4 * 4]) = a[sg];
     }
     __syncthreads();
-    for (int c = t; c < 512; c += 256) h1[c] = fmaxf(part[0][c] + part[1][c] + hw.b1[h * 512 + c], 0.f);
+    for (int sg = 0; sg < kSegs; ++sg)
+        for (int c = t; c < 512; c += 256)
+            h1[sg][c] = fmaxf(part_flat[sg][c] + part_flat[sg][512 + c] + hw.b1[h * 512 + c], 0.f);
     __syncthreads();
 
     // ---- Linear(512,256)+BN folded, ReLU: thread = (K quarter kq, 4 outputs o4)
     {
         const int o4 = t & 63, kq = t >> 6;
         const float4* w2 = reinterpret_cast<const float4*>(hw.w2t + static_cast<size_t>(h) * 512 * 256) + o4;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 a[kSegs];
+#pragma unroll
+        for (int sg = 0; sg < kSegs; ++sg) a[sg] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
         for (int i = kq * 128; i < kq * 128 + 128; ++i) {
-            const float x = h1[i];
             const float4 w = __ldg(w2 + i * 64);
-            a.x = fmaf(x, w.x, a.x); a.y = fmaf(x, w.y, a.y); a.z = fmaf(x, w.z, a.z); a.w = fmaf(x, w.w, a.w);
+#pragma unroll
+            for (int sg = 0; sg < kSegs; ++sg) {
+                const float x = h1[sg][i];
+                a[sg].x = fmaf(x, w.x, a[sg].x); a[sg].y = fmaf(x, w.y, a[sg].y);
+                a[sg].z = fmaf(x, w.z, a[sg].z); a[sg].w = fmaf(x, w.w, a[sg].w);
+            }
         }
-        *reinterpret_cast<float4*>(&part[kq][o4 * 4]) = a;
+#pragma unroll
+        for (int sg = 0; sg < kSegs; ++sg) *reinterpret_cast<float4*>(&part_flat[sg][kq * 512 + o4 * 4]) = a[sg];
     }
     __syncthreads();
-    h2[t] = fmaxf(((part[0][t] + part[1][t]) + part[2][t]) + part[3][t] + hw.b2[h * 256 + t], 0.f);
+    for (int sg = 0; sg < kSegs; ++sg)
+        h2[sg][t] = fmaxf(((part_flat[sg][t] + part_flat[sg][512 + t]) + part_flat[sg][1024 + t]) + part_flat[sg][1536 + t] +
+                          hw.b2[h * 256 + t], 0.f);
     __syncthreads();
 
     // ---- Linear(256,2): block reduction
     const float* w3 = hw.w3 + static_cast<size_t>(h) * 2 * 256;   // [2][256] as in nn.Linear
-    float z0 = h2[t] * w3[t], z1 = h2[t] * w3[256 + t];
+    const float w30 = w3[t], w31 = w3[256 + t];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        z0 += __shfl_xor_sync(0xffffffffu, z0, o);
-        z1 += __shfl_xor_sync(0xffffffffu, z1, o);
-    }
-    if ((t & 31) == 0) {
-        red[0][t >> 5] = z0;
-        red[1][t >> 5] = z1;
+    for (int sg = 0; sg < kSegs; ++sg) {
+        float z0 = h2[sg][t] * w30, z1 = h2[sg][t] * w31;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            z0 += __shfl_xor_sync(0xffffffffu, z0, o);
+            z1 += __shfl_xor_sync(0xffffffffu, z1, o);
+        }
+        if ((t & 31) == 0) {
+            red[sg][0][t >> 5] = z0;
+            red[sg][1][t >> 5] = z1;
+        }
     }
     __syncthreads();
-    if (t < 2) {
-        float z = hw.b3[h * 2 + t];
-        for (int i = 0; i < 8; ++i) z += red[t][i];
-        head_logits[n * 2 + t] = z;   // index 0 = Real, 1 = Synthetic
+    if (t < 2 * nseg) {
+        const int sg = t >> 1, k = t & 1;
+        float z = hw.b3[h * 2 + k];
+        for (int i = 0; i < 8; ++i) z += red[sg][k][i];
+        head_logits[(static_cast<size_t>(h) * B + b0 + sg) * 2 + k] = z;   // index 0 = Real, 1 = Synthetic
     }
 }
 
@@ -200,8 +239,8 @@ __global__ void __launch_bounds__(256) clip_reduce_kernel(const float* __restric
 
 cudaError_t head_mlp_launch(const act_t* feats, const HeadWeights& hw, int B, int H, int features, float* head_logits,
                             cudaStream_t stream, long long* launches) {
-    if (features == 512) head_mlp_kernel<512><<<dim3(B, H), 256, 0, stream>>>(feats, hw, B, head_logits);
-    else if (features == 2048) head_mlp_kernel<2048><<<dim3(B, H), 256, 0, stream>>>(feats, hw, B, head_logits);
+    if (features == 512) head_mlp_kernel<512><<<dim3((B + head_segs(512) - 1) / head_segs(512), H), 256, 0, stream>>>(feats, hw, B, head_logits);
+    else if (features == 2048) head_mlp_kernel<2048><<<dim3((B + head_segs(2048) - 1) / head_segs(2048), H), 256, 0, stream>>>(feats, hw, B, head_logits);
     else return cudaErrorInvalidValue;
     if (launches) *launches += 1;
     return cudaGetLastError();
