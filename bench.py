@@ -51,7 +51,9 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference", "torch_cuda"])
     ap.add_argument("--batch", type=int, default=None, help="segments per GPU per step (2048; 4096 with --frontend-only)")
     ap.add_argument("--heads", type=int, default=6)
-    ap.add_argument("--max-batch", type=int, default=128, help="segments per internal pass (workspace size)")
+    ap.add_argument("--max-batch", type=int, default=148,
+                    help="segments per internal pass (workspace size); a multiple of the SM count keeps every persistent kernel's "
+                         "work evenly divided (measured: 148 -> +0.8 % over 128)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="segments per step of the CPU arms")
     ap.add_argument("--lib-sample", type=int, default=256, help="segments per step of the cuDNN library bar")
     ap.add_argument("--frontend-only", action="store_true", help="configs[1]: PCM -> log-mel dB only")

@@ -73,3 +73,16 @@ def test_world2_gloo_gathers_all_clips(tmp_path, chunk):
         np.testing.assert_allclose(r["p"], want_p, rtol=0, atol=1e-7)
         np.testing.assert_array_equal(r["l"], want_l)
     assert int(r0["nseg"]) + int(r1["nseg"]) == total
+
+
+def test_corpus_clip_lengths_are_ragged_prefix_stable_and_exact():
+    """configs[4]: 118 750 ragged clips whose lengths sum to exactly 3.8 M segments; a subset corpus is a PREFIX of the
+    full one (what lets the 1/16-subset runs be compared with the full run bit for bit)."""
+    from sad_b200 import corpus as CO
+    full = CO.clip_lengths(118750)
+    assert int(full.sum()) == 3_800_000 and full.min() >= 16 and full.max() <= 48 and len(set(full.tolist())) > 10
+    sub = CO.clip_lengths(7422)
+    np.testing.assert_array_equal(sub, full[:7422])
+    assert int(sub.sum()) == 7422 * 32
+    odd = CO.clip_lengths(7)
+    assert len(odd) == 7 and int(odd.sum()) == 7 * 32

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Smallest program that shows every kernel of the fused path at the bench's shape: two chunks of 128 synthetic segments
+"""Smallest program that shows every kernel of the fused path at the bench's shape: two chunks of 148 synthetic segments (one per SM)
 through a 6-head engine (the first warms up).  Profiling target:
 
     python tools/one_chunk.py > gpurun_out/plain.log 2>&1 &&
@@ -21,9 +21,9 @@ from sad_b200.engine import Engine             # noqa: E402
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 heads = int(os.environ.get("HEADS", "6"))
-eng = Engine(heads, dev, max_batch=128)
+eng = Engine(heads, dev, max_batch=148)
 eng.load_merged_state_dict(S.random_merged_state_dict(heads, seed=0))
-x = S.synth_pcm(256, 0, dev)
+x = S.synth_pcm(296, 0, dev)
 lo, pr, la = eng.forward_pcm(x, 0.5)
 torch.cuda.synchronize()
 print("launches", eng.launches, "labels", la[:8].tolist(), "logit[0]", [round(v, 4) for v in lo[0].tolist()])

@@ -52,8 +52,8 @@ def main():
     ap.add_argument("--clips", type=int, default=118750)
     ap.add_argument("--mean-segments", type=int, default=32)
     ap.add_argument("--heads", type=int, default=6)
-    ap.add_argument("--chunk", type=int, default=2048, help="segments generated + processed per pass")
-    ap.add_argument("--max-batch", type=int, default=128)
+    ap.add_argument("--chunk", type=int, default=2072, help="segments generated + processed per pass (14 x 148)")
+    ap.add_argument("--max-batch", type=int, default=148)
     ap.add_argument("--out", default=None, help="JSON summary; per-clip results go to the same path with .npz")
     ap.add_argument("--compare", nargs="+", default=None, help="JSON summaries of finished runs: check that per-clip "
                     "results are bit-identical (shorter runs against the prefix of longer ones)")

@@ -7,7 +7,7 @@ G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 # round tag and the gpurun_out artefacts of that round: bench line, reference-arm line, launch list, full capture
 R = sys.argv[1] if len(sys.argv) > 1 else "r02"
 SRC = {"r01": ("bench_r01.json", "bench_r01_ref.json", "launches_r01.csv", "prof_r01_final.ncu-rep"),
-       "r02": ("r2c_bench.json", "r2c_bench_ref.json", "r02_launches.csv", "r02_full.ncu-rep")}[R]
+       "r02": ("r2z_bench.json", "r2z_bench_ref.json", "r02_launches.csv", "r02_full.ncu-rep")}[R]
 shutil.copy(os.path.join(G, SRC[0]), os.path.join(P, f"{R}_bench_final.json"))
 shutil.copy(os.path.join(G, SRC[1]), os.path.join(P, f"{R}_bench_reference_arm.json"))
 # ---- launch list
@@ -35,7 +35,7 @@ rows = list(csv.reader(raw.splitlines())); hdr, units, data = rows[0], rows[1], 
 g = lambda d, n: d[hdr.index(n)]
 tb = lambda v, u: float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
 ur, uw = units[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_write.sum")]
-out = [f"# ncu --set full --clock-control none, {R} kernels; one chunk (128 segments x 6 heads) of",
+out = [f"# ncu --set full --clock-control none, {R} kernels; one chunk (148 segments x 6 heads in r02, 128 in r01) of",
        "# tools/one_chunk.py (r02) / bench.py --batch 256 (r01).  Replayed, cold-cache, unthrottled clocks.",
        "kernel,grid,duration_us,dram_read_MB,dram_write_MB,dram_pct_of_peak,tensor_pipe_pct,sm_throughput_pct,regs,smem_wavefronts,smem_bank_conflicts"]
 cb = []
@@ -53,7 +53,7 @@ open(os.path.join(P, f"{R}_ncu_full_summary.csv"), "w").write("\n".join(out) + "
 print("\n".join(out[3:]))
 json.dump({"kernel": "conv_umma_kernel / conv_umma2_kernel / block_rows_kernel / stem_fused_kernel (launches of one chunk of 128 segments x 6 heads)",
            "dram_bytes_per_launch_mean": sum(cb) / len(cb), "launches": len(cb),
-           "source": f"profiles/{R}_ncu_full_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum)", "chunk": 128, "heads": 6},
+           "source": f"profiles/{R}_ncu_full_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum)", "chunk": 128 if R == "r01" else 148, "heads": 6},
           open(os.path.join(P, f"{R}_roofline_traffic.json"), "w"), indent=1)
 d = json.load(open(os.path.join(G, SRC[0])))
 print({k: d[k] for k in ["value", "ms_per_step", "gpu_launches", "clocks", "e2e", "cpu_baseline"]})
