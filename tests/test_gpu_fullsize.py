@@ -21,7 +21,7 @@ B, H = 2048, 6
 @pytest.fixture(scope="module")
 def setup():
     dev = torch.device("cuda", 0)
-    eng = Engine(H, dev, max_batch=128)
+    eng = Engine(H, dev, max_batch=148)              # the bench's internal chunk: 13 chunks of 148 + one of 124
     sd = S.random_merged_state_dict(H, seed=3)
     eng.load_merged_state_dict(sd)
     x = S.synth_pcm(B, first=0, device=dev)
@@ -37,6 +37,17 @@ def test_batch_and_chunk_independence(setup):
     lo2, pr2, la2 = eng.forward_pcm(x[idx].contiguous(), 0.5)
     assert torch.equal(lo2, lo[idx]) and torch.equal(pr2, pr[idx]) and torch.equal(la2, la[idx])
     assert torch.isfinite(lo).all()
+
+
+def test_chunk_size_independence(setup):
+    """The same segments through a context with a different internal chunk (128, the round-1 value) give the same bits:
+    what lets per-clip results be compared across runs, chunkings and GPU counts."""
+    eng, sd, x, lo, pr, la = setup
+    eng2 = Engine(H, x.device, max_batch=128)
+    eng2.load_merged_state_dict(sd)
+    lo2, _, la2 = eng2.forward_pcm(x[:300].contiguous(), 0.5)
+    eng2.close()
+    assert torch.equal(lo2, lo[:300]) and torch.equal(la2, la[:300])
 
 
 def test_decision_rule_and_sigmoid_on_device_outputs(setup):
@@ -60,7 +71,7 @@ def test_clip_reduce_and_host_entry(setup):
     cp2, _ = eng.clip_reduce(pr, (clip // 2).contiguous(), B // 64, 0.5)
     np.testing.assert_allclose(cp2.cpu().numpy(), cp.view(B // 64, 2, H + 1).mean(1).cpu().numpy(), rtol=0, atol=1e-6)
     xh = x[:300].cpu().pin_memory()
-    lo_h, pr_h, la_h = eng.forward_host(xh, 0.5)                      # 3 chunks: 128 + 128 + 44
+    lo_h, pr_h, la_h = eng.forward_host(xh, 0.5)                      # 3 chunks: 148 + 148 + 4
     assert torch.equal(lo_h, lo[:300].cpu()) and torch.equal(la_h, la[:300].cpu())
 
 
