@@ -64,6 +64,8 @@ def parse():
     a = ap.parse_args()
     if a.batch is None:
         a.batch = 4096 if a.frontend_only else 2048
+    if a.frontend_only and "--steps" not in sys.argv:
+        a.steps = 100                 # 5 ms per step: long enough for the 200 ms clock sampler to see the timed region
     return a
 
 
