@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libsad_b200.so")
 LIB_F16 = os.path.join(HERE, "libsad_b200_f16.so")   # same sources with -DSAD_ACT_F16 (csrc/act.cuh)
-SOURCES = ["api.cu", "conv_umma.cu", "conv_umma2.cu", "conv_rows.cu", "block_rows.cu", "stem_fused.cu", "frontend.cu",
+SOURCES = ["api.cu", "conv_umma.cu", "conv_umma2.cu", "conv_rows.cu", "conv_rows2.cu", "block_rows.cu", "stem_fused.cu", "frontend.cu",
            "ingest.cu", "head.cu", "synth.cu"]
 HEADERS = ["conv_umma.h", "frontend.h", "ingest.h", "ingest_taps.h", "head.h", "stem_fused.h", "ptx.cuh", "fft2048.cuh",
            "synth.h", "act.cuh", "fft2048r16.cuh", os.path.join("..", "..", "include", "sad_b200.h")]

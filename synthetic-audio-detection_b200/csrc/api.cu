@@ -262,6 +262,7 @@ struct sad_ctx {
     bf16* d_ident128 = nullptr;         // [H][128][128] identity: the residual of a TR conv enters as two extra K blocks
     float* d_bias_fused[kMaxConvs] = {nullptr}; // [H][Cout] = bias(conv2) + bias(downsample) for the conv2 that absorbs it
     int rows_mode = 1;                  // layer1 row-stationary kernel (conv_rows.cu): 0 = use the generic kernel instead
+    int rows2 = 0;                      // 1: single 64-channel row convs run on CTA pairs (conv_rows2.cu); 2: layer1 BasicBlocks too (two launches instead of block_rows)
 
     // one workspace per context: every call waits for the previous call's last kernel, whatever stream it ran on
     cudaEvent_t ev_last = nullptr;
@@ -534,6 +535,8 @@ bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const b
     if (n_tile >= 128) {
         if (!sad::encode_weight_map(&L->bh_map, c->d_w[ci], K, 1LL * c->H * s.cout, n_tile / 2, c->err, sizeof(c->err)))
             return false;
+    } else if (is_rows_layer(c, ci)) {   // conv_rows2.cu: each CTA of a pair loads its 96 of the 192 B rows in boxes of 32
+        if (!sad::encode_weight_map(&L->bh_map, c->d_w[ci], K, 1LL * c->H * s.cout, 32, c->err, sizeof(c->err))) return false;
     } else {
         L->bh_map = L->b_map;
     }
@@ -613,7 +616,7 @@ bool is_rows_layer(const sad_ctx* c, int ci);
 cudaError_t launch_conv(sad_ctx* c, int ci, const sad::ConvLaunch& L, int heads, cudaStream_t st, bool block) {
     if (block) return sad::block_rows_launch(L, heads, c->num_sms, st);
     if (ci > 0 && c->rows_mode && is_rows_layer(c, ci))
-        return sad::conv_rows_launch(L, heads, c->num_sms, st);
+        return c->rows2 ? sad::conv_rows2_launch(L, heads, c->num_sms, st) : sad::conv_rows_launch(L, heads, c->num_sms, st);
     if (c->two_cta && L.n_tile >= (c->two_cta >= 2 ? 128 : 256) && L.m_tiles_per_img % 2 == 0)
         return sad::conv_umma2_launch(L, c->num_sms, st);
     return sad::conv_umma_launch(L, c->num_sms, st);
@@ -800,6 +803,7 @@ int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const c
     if (const char* e = getenv("SAD_FUSE_BLOCK")) c->fuse_block = atoi(e);
     if (const char* e = getenv("SAD_TR128")) c->tr128 = atoi(e);
     if (const char* e = getenv("SAD_2CTA")) c->two_cta = atoi(e);
+    if (const char* e = getenv("SAD_ROWS2")) c->rows2 = atoi(e);
     *out = c;   // returned even on failure so the caller can read sad_last_error, then sad_destroy
     ON_DEVICE(c);
 
@@ -869,7 +873,7 @@ int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const c
     if (!sad::encode_pix_map(&c->stem1.out_map, c->d_buf[BX], 64, HB * 128 * 128, 128, c->err, sizeof(c->err))) return SAD_ECUDA;
     c->stem1.img = c->d_img;
     c->stem1.H = n_heads;
-    c->plan = build_plan(*net, c->fuse_ds != 0, c->fuse_block != 0, &c->final_buf);
+    c->plan = build_plan(*net, c->fuse_ds != 0, c->fuse_block != 0 && c->rows2 < 2, &c->final_buf);
     c->plan_launch.resize(c->plan.size());
     for (size_t i = 0; i < c->plan.size(); ++i) {
         const Step& s = c->plan[i];
@@ -1273,6 +1277,9 @@ int sad_debug_conv(sad_ctx* c, int head, int layer, const void* in, const void* 
     if (L.n_tile >= 128 &&
         !sad::encode_weight_map(&L.bh_map, c->d_w[layer] + static_cast<size_t>(head) * s.cout * K, K, s.cout, L.n_tile / 2, c->err,
                                 sizeof(c->err)))
+        return SAD_ECUDA;
+    if (is_rows_layer(c, layer) &&
+        !sad::encode_weight_map(&L.bh_map, c->d_w[layer] + static_cast<size_t>(head) * s.cout * K, K, s.cout, 32, c->err, sizeof(c->err)))
         return SAD_ECUDA;
     L.bias = c->d_bias[layer] + static_cast<size_t>(head) * s.cout;
     set_batch(&L, B, 1);

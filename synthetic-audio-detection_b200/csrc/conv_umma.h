@@ -88,6 +88,8 @@ cudaError_t conv_umma2_launch(const ConvLaunch& p, int num_sms, cudaStream_t str
 // (block_rows.cu: conv1 on the even CTA, conv2 + identity on the odd one, the intermediate goes through peer smem).
 cudaError_t conv_rows_launch(const ConvLaunch& p, int heads, int num_sms, cudaStream_t stream);
 cudaError_t block_rows_launch(const ConvLaunch& p, int heads, int num_sms, cudaStream_t stream);
+// conv_rows on CTA pairs (conv_rows2.cu: cta_group::2, UMMA 256x192x16, aliased accumulator ring); needs bh_map = weights with box {64, 32}.
+cudaError_t conv_rows2_launch(const ConvLaunch& p, int heads, int num_sms, cudaStream_t stream);
 
 // Tensor-map construction (api.cu): resolves cuTensorMapEncodeTiled through the runtime so that the
 // library does not link against libcuda and still loads on a machine without a driver.

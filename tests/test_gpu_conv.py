@@ -184,3 +184,63 @@ def test_bottleneck_conv_layer(idx):
     bad = (err > tol).float().mean().item()
     print(f"resnet50 {name} [{cin}->{cout} k{k} s{stride} @{hin}]: max abs err {err.max():.4f}, frac out of tol {bad:.2e}")
     assert bad == 0.0
+
+
+# ---------------------------------------------------------------- layer1 on CTA pairs (conv_rows2.cu, SAD_ROWS2)
+def _engine_rows2(monkeypatch, mode, n_heads=2, max_batch=8):
+    """A private engine created with SAD_ROWS2 set (the switch is read at sad_create time)."""
+    from sad_b200.engine import Engine
+    monkeypatch.setenv("SAD_ROWS2", str(mode))
+    e = Engine(n_heads, torch.device("cuda", 0), max_batch=max_batch)
+    e.load_merged_state_dict(G.merged_sd(n_heads))
+    return e
+
+
+@pytest.mark.parametrize("idx", [1, 2, 3, 4])
+def test_layer1_conv_on_cta_pairs(idx, monkeypatch):
+    """The four layer1 convolutions through conv_rows2_kernel (cta_group::2, UMMA 256x192x16, aliased accumulator ring
+    with two partial accumulators for 2 of every 6 rows, phantom rows at the strip borders), odd and even image counts."""
+    name, cin, cout, k, stride, hin, hout = _geometry(idx)
+    head = 1
+    sd = G.merged_sd(2)
+    p = f"sub_models.{head}.base."
+    w, b = E.fold_bn(sd[p + name + ".weight"], sd, p + BNS[idx][1])
+    wq = w.to(torch.bfloat16).float()
+    e = _engine_rows2(monkeypatch, 1)
+    for B in (1, 4):
+        g = torch.Generator().manual_seed(900 + idx + B)
+        x = torch.randn(B, cin, hin, hin, generator=g).to(torch.bfloat16)
+        use_res = name.endswith("conv2")
+        res = torch.randn(B, cout, hout, hout, generator=g).to(torch.bfloat16) if use_res else None
+        want = F.conv2d(x.float(), wq, b, stride=1, padding=1)
+        if use_res:
+            want = want + res.float()
+        want = F.relu(want)
+        got = e.debug_conv(head, idx, x.permute(0, 2, 3, 1).contiguous().cuda(),
+                           res.permute(0, 2, 3, 1).contiguous().cuda() if use_res else None, (B, hout, hout, cout), True)
+        torch.cuda.synchronize()
+        err = (got.float().cpu().permute(0, 3, 1, 2) - want).abs()
+        bad = (err > 2.0 ** -7 * want.abs() + 2e-2).float().mean().item()
+        # every output row, also the split ones (rows 4, 5 mod 6 of a strip) and the strip borders (rows 0, 63, 64, 127)
+        print(f"conv_rows2 {name} B={B}: max abs err {err.max():.4f}, worst row {int(err.amax(dim=(0, 1, 3)).argmax())}")
+        assert bad == 0.0
+    e.close()
+
+
+def test_whole_path_on_cta_pairs_matches_reference_and_is_batch_independent(monkeypatch):
+    """SAD_ROWS2=2: both layer1 BasicBlocks as two conv_rows2 launches each instead of the fused block_rows kernel.
+    Logits vs the reference golden (2e-2), close to the default engine (same arithmetic up to fp32 summation order of
+    the split rows), and bit-identical for a segment whatever the batch around it."""
+    g = G.golden("ensemble_n2.npz")
+    x = G.segs(g["seg_ids"]).cuda()
+    e2 = _engine_rows2(monkeypatch, 2)
+    lo2, _, la2 = e2.forward_pcm(x, 0.5)
+    d = (lo2.cpu().numpy() - g["merged_logits"])
+    lo0, _, _ = G.engine(2).forward_pcm(x, 0.5)
+    print(f"rows2: max |logit diff| vs reference {abs(d).max():.4f}; vs the fused-block engine {(lo2 - lo0).abs().max().item():.5f}")
+    assert abs(d).max() <= 2e-2
+    assert (lo2 - lo0).abs().max().item() <= 5e-3
+    sub = x[[5, 2]].contiguous()
+    lo_sub, _, _ = e2.forward_pcm(sub, 0.5)
+    assert torch.equal(lo_sub[0], lo2[5]) and torch.equal(lo_sub[1], lo2[2])
+    e2.close()
