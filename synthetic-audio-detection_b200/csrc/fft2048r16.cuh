@@ -70,6 +70,22 @@ SAD_HD void fft16_pass1(int t, cpx* v /*[16]: x[t + 128q], overwritten*/, cpx* b
 #endif
     for (int q = 0; q < 16; ++q) buf[pad16(16 * t + q)] = v[dft16_out(q)];
 }
+template <typename Tw>
+SAD_HD void fft16_pass2_tw(int t, Tw tw2 /* tw2(q) -> W_256^{(t & 15) q}, q = 1..15 */, cpx* buf) {
+    cpx v[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 16; ++q) {
+        const cpx x = buf[pad16(t + 128 * q)];
+        v[q] = q == 0 ? x : cmul(x, tw2(q ? q : 1));
+    }
+    dft16(v);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 16; ++q) buf[pad16(t + 128 * q)] = v[dft16_out(q)];      // in place
+}
 SAD_HD void fft16_pass2(int t, const cpx* tw2, cpx* buf) {
     cpx v[16];
 #if defined(__CUDA_ARCH__)
@@ -84,6 +100,30 @@ SAD_HD void fft16_pass2(int t, const cpx* tw2, cpx* buf) {
 #pragma unroll
 #endif
     for (int q = 0; q < 16; ++q) buf[pad16(t + 128 * q)] = v[dft16_out(q)];      // in place: V[q] -> the slot input q came from
+}
+template <typename Tw>
+SAD_HD void fft16_pass3_tw(int t, Tw tw3 /* tw3(h, q) -> W_2048^{(t + 128 h) q}, q = 1..7 */, cpx* buf) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int h = 0; h < 2; ++h) {
+        const int j = t + 128 * h;
+        const int base = (j & 15) + ((j >> 4) << 7);               // slot of e2 = j + 256 q is base + 16 q
+        cpx v[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < 8; ++q) {
+            const cpx x = buf[pad16(base + 16 * q)];
+            v[q] = q == 0 ? x : cmul(x, tw3(h, q ? q : 1));
+        }
+        dft8(v);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < 8; ++q)
+            if (q != 4) buf[pad16(base + 16 * q)] = v[q];          // bins 1024..1279 (q = 4) are never read
+    }
 }
 SAD_HD void fft16_pass3(int t, const cpx (*tw3)[7], cpx* buf) {
 #if defined(__CUDA_ARCH__)

@@ -209,21 +209,38 @@ __global__ void __launch_bounds__(512) db_clamp_stats_kernel(float* __restrict__
 // the clamp, mean / unbiased std, and the final [mel][frame] layout.  Replaces fill_u32 + stft_mel_kernel +
 // db_clamp_stats_kernel (three launches, the unclamped dB written, re-read, re-written and read again by the image
 // kernel, a global atomic max per CTA).
-//   CTA = 384 threads = 3 groups of 128; a group transforms one frame PAIR at a time (126 pairs = 42 rounds x 3 groups,
-//   no idle round) and synchronises on its own named barrier, so the three groups hide each other's barrier and
+//   CTA = 896 threads = 7 groups of 128; a group transforms one frame PAIR at a time (126 pairs = 18 rounds x 7 groups,
+//   no idle round) and synchronises on its own named barrier, so the groups hide each other's barrier and
 //   shared-memory latency.  Persistent: CTA c handles segments c, c + gridDim.x, ...
 //   Phase 1 writes unclamped dB FRAME-major to a scratch buffer (thread = mel band: coalesced 512-byte rows; the
 //   segment's 128 KB stay in L2); phase 2 (same CTA, after a block-wide max) clamps, accumulates the statistics in
 //   fp64 and transposes 32x32 tiles through shared memory into the [mel][frame] layout the reference produces.
-constexpr int kFeGroups = 3;
-constexpr int kFeThreads = kFft16Threads * kFeGroups;   // 384
-constexpr int kPairs = (kFrames + 1) / 2;               // 126
-static_assert(kPairs % kFeGroups == 0, "frame pairs must divide evenly over the groups");
+// Build-time shape of the CTA, measured on B200 (bench.py --frontend-only, batch 4096, segments/s):
+//   3 groups, constants in registers (168 regs), prefetch   783 k     6 groups (80 regs, 200 B spilled), prefetch   814 k
+//   4 groups, tw3 + window in smem (128 regs), prefetch     865 k     6 groups (80 regs), no prefetch               868 k
+//   5 groups, all constants in smem (96 regs), prefetch     883 k     7 groups (72 regs), no prefetch               914 k
+// More resident warps beat holding constants / the next pair's samples in registers; at 7 groups (28 warps) the
+// shared-memory pipe is the limit (~2 100 wavefronts per FFT against ~2 500 cycles).
+#ifndef SAD_FE_GROUPS
+#define SAD_FE_GROUPS 7
+#endif
+#ifndef SAD_FE_PREFETCH
+#define SAD_FE_PREFETCH 0
+#endif
+constexpr int kFeGroups = SAD_FE_GROUPS;                // 128-thread FFT groups per CTA
+constexpr int kFeThreads = kFft16Threads * kFeGroups;   // 896
+constexpr int kPairs = (kFrames + 1) / 2;               // 126 frame pairs = 18 rounds x 7 groups (also even for 3 and 6)
+constexpr bool kFeSmemConst = kFeGroups > 3;
+constexpr bool kFeSmemTw2 = kFeGroups > 4;               // pass-2 twiddles in smem too (5+ groups: <= 102 registers)
+constexpr bool kFePrefetch = SAD_FE_PREFETCH != 0;
 
 struct __align__(16) FeSmem {
-    cpx buf[kFeGroups][kFft16Slots];      // 3 x 17 KB; phase 2 reuses it as 12 transposition tiles of [32][33] floats
+    cpx buf[kFeGroups][kFft16Slots];      // 17 KB per group; phase 2 reuses it as one [32][33]-float transposition tile per warp
     float pw[kFeGroups][2][772];          // power spectra of the group's two frames, bins 0..768 (769..771 stay zero)
     float mel_w[2816];                    // taps widened to 4-bin boundaries (MelTable::w4)
+    cpx tw3[kFeSmemConst ? 14 : 1][kFft16Threads];   // [h*7 + q-1][t]: pass-3 twiddles when they do not fit in registers
+    float win[kFeSmemConst ? 16 : 1][kFft16Threads]; // [q][t]: Hann window samples t + 128 q
+    cpx tw2[kFeSmemTw2 ? 15 : 1][16];                // [q-1][k]: pass-2 twiddles (5+ groups)
     float red_max[kFeThreads / 32];
     double red_s1[kFeThreads / 32];
     double red_s2[kFeThreads / 32];
@@ -244,13 +261,17 @@ __global__ void __launch_bounds__(kFeThreads, 1)
     const int warp = tid >> 5, lane = tid & 31;
 
     // per-thread constants of the whole kernel: twiddles (exact look-ups of exp(-2 pi i n / 2048)) and window samples
-    cpx tw2[15], tw3[2][7];
-    float win[16];
+    cpx tw2[kFeSmemTw2 ? 1 : 15], tw3[kFeSmemConst ? 1 : 2][7];
+    float win[kFeSmemConst ? 1 : 16];
 #pragma unroll
     for (int q = 1; q < 16; ++q) {
         float sn, cs;
         sincospif(static_cast<float>(fft16_tw2_angle(t, q)) * (1.0f / 1024.0f), &sn, &cs);
-        tw2[q - 1] = {cs, -sn};
+        if constexpr (kFeSmemTw2) {
+            if (tid < 16) s.tw2[q - 1][tid] = {cs, -sn};
+        } else {
+            tw2[q - 1] = {cs, -sn};
+        }
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h)
@@ -258,10 +279,20 @@ __global__ void __launch_bounds__(kFeThreads, 1)
         for (int q = 1; q < 8; ++q) {
             float sn, cs;
             sincospif(static_cast<float>(fft16_tw3_angle(t, h, q)) * (1.0f / 1024.0f), &sn, &cs);
-            tw3[h][q - 1] = {cs, -sn};
+            if constexpr (kFeSmemConst) {
+                if (g == 0) s.tw3[h * 7 + q - 1][t] = {cs, -sn};
+            } else {
+                tw3[h][q - 1] = {cs, -sn};
+            }
         }
 #pragma unroll
-    for (int q = 0; q < 16; ++q) win[q] = __ldg(window + t + 128 * q);
+    for (int q = 0; q < 16; ++q) {
+        if constexpr (kFeSmemConst) {
+            if (g == 0) s.win[q][t] = __ldg(window + t + 128 * q);
+        } else {
+            win[q] = __ldg(window + t + 128 * q);
+        }
+    }
     for (int i = tid; i < 2816; i += kFeThreads) s.mel_w[i] = mel->w4[i];
     for (int i = tid; i < kFeGroups * 2 * 772; i += kFeThreads) (&s.pw[0][0][0])[i] = 0.f;   // zero-weight taps may read bins 769..771
     __syncthreads();
@@ -297,20 +328,32 @@ __global__ void __launch_bounds__(kFeThreads, 1)
                 }
             }
         };
-        load_pair(g);
+        if (kFePrefetch) load_pair(g);
         for (int p = g; p < kPairs; p += kFeGroups) {
             const int fa = 2 * p;
             const bool has_b = fa + 1 < kFrames;
+            if (!kFePrefetch) load_pair(p);
             cpx v[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = {ra[q] * win[q], rb[q] * win[q]};
+            for (int q = 0; q < 16; ++q) {
+                const float w = kFeSmemConst ? s.win[kFeSmemConst ? q : 0][t] : win[kFeSmemConst ? 0 : q];
+                v[q] = {ra[q] * w, rb[q] * w};
+            }
             fft16_pass1(t, v, buf);
             group_bar(g);
-            fft16_pass2(t, tw2, buf);
+            if constexpr (kFeSmemTw2) {
+                fft16_pass2_tw(t, [&](int q) { return s.tw2[q - 1][t & 15]; }, buf);
+            } else {
+                fft16_pass2(t, tw2, buf);
+            }
             group_bar(g);
-            fft16_pass3(t, tw3, buf);
+            if constexpr (kFeSmemConst) {
+                fft16_pass3_tw(t, [&](int h, int q) { return s.tw3[h * 7 + q - 1][t]; }, buf);
+            } else {
+                fft16_pass3(t, tw3, buf);
+            }
             group_bar(g);
-            if (p + kFeGroups < kPairs) load_pair(p + kFeGroups);
+            if (kFePrefetch && p + kFeGroups < kPairs) load_pair(p + kFeGroups);
 #pragma unroll
             for (int i = 0; i < 7; ++i) {
                 const int k = t + 128 * i;
