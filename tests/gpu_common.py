@@ -48,7 +48,7 @@ def rel_db_err(a, b):
 def decision_margin(logits):
     """Smallest max-norm logit perturbation that changes the decision of rule IR:207-213 at threshold 0.5 (sigmoid(0)).
     Real (z_real >= 0, every z_syn < 0): any logit reaching 0 flips it -> min |z|.  Otherwise the label is the arg-max
-    of the synthetic logits: it changes when the two largest meet (half their gap each, counted as the gap) or when the
+    of the synthetic logits: it changes when the two largest meet (each moves half their gap) or when the
     row becomes Real, which needs EVERY violated condition repaired -> the largest violation."""
     z = np.asarray(logits, np.float64)
     syn, real = z[:, :-1], z[:, -1]
@@ -57,7 +57,7 @@ def decision_margin(logits):
     to_real = np.maximum(np.maximum(-real, 0), np.maximum(syn.max(axis=1), 0))
     if syn.shape[1] > 1:
         srt = np.sort(syn, axis=1)
-        gap = srt[:, -1] - srt[:, -2]
+        gap = 0.5 * (srt[:, -1] - srt[:, -2])
     else:
         gap = np.full(z.shape[0], np.inf)
     return np.where(is_real, m_real, np.minimum(gap, to_real))
