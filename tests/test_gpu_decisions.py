@@ -81,3 +81,27 @@ def test_continuous_corpus_flips_stay_inside_the_logit_tolerance():
     print(f"continuous corpus: max |logit diff| {d.max():.4f}; agreement {agree.mean():.4f}; margins of differing "
           f"segments {np.round(margin[~agree], 4).tolist()}; margin histogram: {_histogram(margin)}")
     assert np.all(margin[~agree] <= LOGIT_TOL)
+
+
+def test_headline_shape_against_the_reference():
+    """BASELINE.json configs[3] as the bench runs it -- ONE batch of 2048 segments, 6 heads, internal chunk 148 -- against
+    the live reference's logits and labels for all 2048 held-out segments (tests/golden/decisions_n6.npz), through the
+    device entry and through the host entry (pinned PCM -> H2D -> compute -> D2H), which must agree bit for bit."""
+    n_heads = 6
+    g = G.golden(f"decisions_n{n_heads}.npz")
+    n = g["merged_logits"].shape[0]
+    assert n == 2048
+    x = torch.cat([FX.family_segments(256, int(g["first"]) + b0, n_classes=n_heads + 1)[0] for b0 in range(0, n, 256)])
+    from sad_b200.engine import Engine
+    e = Engine(n_heads, torch.device("cuda", 0), max_batch=148)
+    e.load_merged_state_dict(FX.decision_state_dict(n_heads))
+    lo, pr, la = e.forward_pcm(x.cuda(), 0.5)
+    lo_h, pr_h, la_h = e.forward_host(x.pin_memory(), 0.5)
+    e.close()
+    assert torch.equal(lo.cpu(), lo_h) and torch.equal(pr.cpu(), pr_h) and torch.equal(la.cpu(), la_h)
+    d = np.abs(lo_h.numpy() - g["merged_logits"])
+    agree = la_h.numpy().astype(np.int64) == g["labels"].astype(np.int64)
+    print(f"headline shape (2048 x 6 heads, chunk 148): max |logit diff| {d.max():.4f}; decisions identical on "
+          f"{int(agree.sum())} / {n}")
+    assert d.max() <= LOGIT_TOL
+    assert agree.mean() >= MIN_AGREEMENT
