@@ -244,3 +244,35 @@ def test_whole_path_on_cta_pairs_matches_reference_and_is_batch_independent(monk
     lo_sub, _, _ = e2.forward_pcm(sub, 0.5)
     assert torch.equal(lo_sub[0], lo2[5]) and torch.equal(lo_sub[1], lo2[2])
     e2.close()
+
+
+@pytest.mark.parametrize("idx", [2, 6, 9, 14, 19])
+def test_conv_layer_fp16_build(idx):
+    """One convolution per kernel family on the fp16 build of the library (csrc/act.cuh): layer1 rows (2), layer2 with the
+    folded downsample (6) and with the identity as K blocks (9), the 2-CTA layers 3 and 4 (14, 19).  Operands rounded to
+    fp16 on both sides, so only accumulation order and the fp16 rounding of the output differ."""
+    name, cin, cout, k, stride, hin, hout = _geometry(idx)
+    head = 1
+    sd = G.merged_sd(2)
+    p = f"sub_models.{head}.base."
+    w, b = E.fold_bn(sd[p + name + ".weight"], sd, p + BNS[idx][1])
+    wq = w.to(torch.float16).float()
+    B = 2
+    g = torch.Generator().manual_seed(300 + idx)
+    x = torch.randn(B, cin, hin, hin, generator=g).to(torch.float16)
+    use_res = name.endswith("conv2")
+    res = torch.randn(B, cout, hout, hout, generator=g).to(torch.float16) if use_res else None
+    want = F.conv2d(x.float(), wq, b, stride=stride, padding=k // 2)
+    if use_res:
+        want = want + res.float()
+    want = F.relu(want)
+    e = G.engine(2, dtype="fp16")
+    got = e.debug_conv(head, idx, x.permute(0, 2, 3, 1).contiguous().cuda(),
+                       res.permute(0, 2, 3, 1).contiguous().cuda() if use_res else None, (B, hout, hout, cout), True)
+    torch.cuda.synchronize()
+    assert got.dtype == torch.float16
+    err = (got.float().cpu().permute(0, 3, 1, 2) - want).abs()
+    tol = 2.0 ** -10 * want.abs() + 3e-3        # fp16 output rounding (2^-11 rel) with margin + accumulation slack
+    bad = (err > tol).float().mean().item()
+    print(f"fp16 {name}: max abs err {err.max():.5f} (|want| max {want.abs().max():.2f}), frac out of tol {bad:.2e}")
+    assert bad == 0.0

@@ -157,3 +157,14 @@ def test_preprocess_waveform_fails_loudly_without_gpu(tmp_path):
         IR.preprocess_waveform(str(tmp_path / "a.wav"), IR.AudioConfig())
     with pytest.raises(NotImplementedError):
         IR.preprocess_waveform(str(tmp_path / "a.wav"), IR.AudioConfig(sample_rate=16000))
+
+
+def test_default_activation_dtype_per_backbone(monkeypatch):
+    """bf16 -- the dtype BASELINE.json names -- for the BasicBlock nets, fp16 for the Bottleneck nets."""
+    from sad_b200 import engine as ENG
+    assert [ENG.default_dtype(b) for b in ("resnet18", "resnet34", "resnet50", "resnet101", "resnet152")] == \
+        ["bf16", "bf16", "fp16", "fp16", "fp16"]
+    from sad_b200 import _lib
+    with pytest.raises(ValueError):
+        _lib.load("fp8")
+    assert _lib.load("bf16") is not _lib.load("fp16")
