@@ -259,6 +259,8 @@ struct sad_ctx {
     int fuse_ds = 1;                    // fold each block's 1x1/s2 downsample conv into conv2 as extra K blocks
     int fuse_block = 1;                 // layer1 BasicBlocks run as one launch on CTA pairs (block_rows.cu)
     int tr128 = 1;                      // N = 128 layers as weights x pixels with 256-column UMMA (conv_umma.cu, TR)
+    int tr_res = 0;                     // 1: TR convs add the identity in the epilogue (TMA-loaded [32 px][32 ch] tiles) instead of as two extra K blocks
+                                        // through the tensor core -- 10% fewer MMAs for that conv, but MEASURED slower (epilogue-bound: 1 100 vs 1 155 TFLOP/s, -0.5% whole path)
     bf16* d_ident128 = nullptr;         // [H][128][128] identity: the residual of a TR conv enters as two extra K blocks
     float* d_bias_fused[kMaxConvs] = {nullptr}; // [H][Cout] = bias(conv2) + bias(downsample) for the conv2 that absorbs it
     int rows_mode = 1;                  // layer1 row-stationary kernel (conv_rows.cu): 0 = use the generic kernel instead
@@ -542,7 +544,12 @@ bool make_launch(sad_ctx* c, sad::ConvLaunch* L, int ci, const bf16* in, const b
     }
     L->b2h_map = L->bh_map;
     L->transposed = (c->tr128 && n_tile == 128 && s.cout == 128 && (Wo * Wo / 128) % 2 == 0 && block2 < 0) ? 1 : 0;
-    if (L->transposed && res && fused_ds < 0) {
+    if (L->transposed && res && fused_ds < 0 && c->tr_res) {
+        // identity branch in the epilogue: the warp that owns 32 channels x 32 pixels TMA-loads the matching residual tile
+        // ([32 px][32 ch], dense 64-byte rows) into the free half of its staging buffer and every lane adds its channel
+        // column.  Saves the two identity K blocks (10% of this conv's tensor work) but makes the epilogue the bottleneck: off by default.
+        if (!sad::encode_pix_map32(&L->res32_map, res, s.cout, pixels, c->err, sizeof(c->err))) return false;
+    } else if (L->transposed && res && fused_ds < 0) {
         // identity branch through the tensor core: out += x * I as Cout/64 extra K blocks (the transposed epilogue has
         // channels on lanes and no cheap way to read a pixel-major residual); fp32 accumulation, exact for bf16 x
         if (!sad::encode_act_map(&L->a2_map, res, s.cout, Wo, Wo, n_imgs, s.cout, 1LL * Wo * s.cout, 1LL * Wo * Wo * s.cout, Wo,
@@ -802,6 +809,7 @@ int sad_create_ex(sad_ctx** out, int device, int n_heads, int max_batch, const c
     if (const char* e = getenv("SAD_FUSE_DS")) c->fuse_ds = atoi(e);
     if (const char* e = getenv("SAD_FUSE_BLOCK")) c->fuse_block = atoi(e);
     if (const char* e = getenv("SAD_TR128")) c->tr128 = atoi(e);
+    if (const char* e = getenv("SAD_TR_RES")) c->tr_res = atoi(e);
     if (const char* e = getenv("SAD_2CTA")) c->two_cta = atoi(e);
     if (const char* e = getenv("SAD_ROWS2")) c->rows2 = atoi(e);
     *out = c;   // returned even on failure so the caller can read sad_last_error, then sad_destroy

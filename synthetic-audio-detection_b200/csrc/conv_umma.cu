@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
     uint64_t* empty_bar = bars + C::kStages;        // [kStages]
     uint64_t* tmem_full = bars + 2 * C::kStages;    // [2]
     uint64_t* tmem_empty = tmem_full + 2;           // [2]
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* res_bar = tmem_empty + 2;             // [4 warps][kOutBufs]  TR epilogue: residual tile landed (TMA)
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_bar + 4 * C::kOutBufs);
+    static_assert((2 * C::kStages + 4 + 4 * C::kOutBufs) * 8 + 4 <= 256, "barrier block");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
         tma_prefetch_desc(&p.b_map);
         tma_prefetch_desc(&p.out_map);
         if (TR) tma_prefetch_desc(&p.out32_map);
+        if (TR && p.residual) tma_prefetch_desc(&p.res32_map);
         if (p.k2_blocks) {
             tma_prefetch_desc(&p.a2_map);
             tma_prefetch_desc(&p.b2_map);
@@ -106,6 +109,8 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
             mbar_init(&tmem_full[a], 1);
             mbar_init(&tmem_empty[a], 4 * C::kEpiGroups);
         }
+        if (TR)
+            for (int i = 0; i < 4 * C::kOutBufs; ++i) mbar_init(&res_bar[i], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_base_slot);
@@ -239,23 +244,48 @@ __global__ void __launch_bounds__(Cfg<N_TILE, MT>::kThreadsCfg, 1) conv_umma_ker
                 const float bias = __ldg(p.bias + head * p.Cout + co);
                 const long long pix_base = (static_cast<long long>(head) * p.imgs_per_head + img) * (p.m_tiles_per_img * kBlockM) +
                                            static_cast<long long>(m_t) * kBlockM;  // 256 consecutive pixels
+                const bool has_res = p.residual != nullptr;
+                constexpr int kChunks = MT * kBlockM / 32;
+                // residual tile of chunk j lands in the upper 2 KB of staging buffer (nstore + j) % kOutBufs; the loads
+                // run kOutBufs - 1 chunks ahead of their use (they do not depend on the accumulator)
+                auto issue_res = [&](int j, uint32_t ns) {
+                    const uint32_t b = ns % C::kOutBufs;
+                    mbar_expect_tx(&res_bar[quarter * C::kOutBufs + b], 2048);
+                    tma_load_2d(my_out + b * 4096 + 2048, &p.res32_map, &res_bar[quarter * C::kOutBufs + b],
+                                n_t * N_TILE + quarter * 32, static_cast<int>(pix_base) + 32 * j);
+                };
+                if (has_res && lane == 0)
+                    for (int j = 0; j < C::kOutBufs - 1 && j < kChunks; ++j) issue_res(j, nstore + j);
                 mbar_wait(&tmem_full[acc], (it / C::kAccBufs) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::kAccCols;
 #pragma unroll 1
-                for (int j = 0; j < MT * kBlockM / 32; ++j, ++nstore) {
+                for (int j = 0; j < kChunks; ++j, ++nstore) {
                     uint32_t v[32];
                     tmem_ld32(taddr + 32 * j, v);
                     tmem_ld_wait();
-                    if (j == MT * kBlockM / 32 - 1) {  // accumulators are in registers: hand TMEM back
+                    if (j == kChunks - 1) {            // accumulators are in registers: hand TMEM back
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                     }
-                    if (lane == 0) tma_store_wait_read<C::kOutBufs - 1>();
+                    if (lane == 0) {
+                        tma_store_wait_read<C::kOutBufs - 1>();     // buffer nstore % kOutBufs (and the one ahead) may be rewritten
+                        if (has_res && j + C::kOutBufs - 1 < kChunks) issue_res(j + C::kOutBufs - 1, nstore + C::kOutBufs - 1);
+                    }
                     __syncwarp();
-                    uint8_t* stage = my_out + (nstore % C::kOutBufs) * 4096;
+                    const uint32_t bsel = nstore % C::kOutBufs;
+                    uint8_t* stage = my_out + bsel * 4096;
                     const uint32_t st_addr = smem_u32(stage) + lane * 2;          // [px][32 ch]: this thread's channel column
+                    if (has_res) {
+                        mbar_wait(&res_bar[quarter * C::kOutBufs + bsel], (nstore / C::kOutBufs) & 1);
+#pragma unroll
+                        for (int px = 0; px < 32; ++px) {
+                            uint16_t rv;
+                            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(rv) : "r"(st_addr + 2048 + px * 64) : "memory");
+                            v[px] = __float_as_uint(__uint_as_float(v[px]) + act_lo(static_cast<uint32_t>(rv)));
+                        }
+                    }
 #pragma unroll
                     for (int px = 0; px < 32; px += 2) {
                         const float f0 = __uint_as_float(v[px]) + bias, f1 = __uint_as_float(v[px + 1]) + bias;

@@ -14,6 +14,7 @@ struct alignas(64) ConvLaunch {
     CUtensorMap out_map;    // output viewed as {Cout, pixels}: box {64 ch, 32 px}, SWIZZLE_128B (TMA store)
     CUtensorMap out32_map;  // output as {Cout, pixels} with box {32 ch, 32 px}, no swizzle (transposed-product epilogue)
     CUtensorMap res_map;    // residual viewed as {Cout, pixels}: box {64 ch, 128 px} (TMA load); valid iff residual
+    CUtensorMap res32_map;  // residual as {Cout, pixels} with box {32 ch, 32 px}, no swizzle (transposed-product epilogue)
     CUtensorMap a2_map;     // optional second input (fused 1x1/stride-2 downsample branch): parity-(0,0) view of the block input
     CUtensorMap b2_map;     // its weights [heads*Cout][Cin2] bf16; the extra k2_blocks K-steps accumulate into the same tile
     CUtensorMap bh_map;     // b_map / b2_map with box {64, n_tile/2}: each CTA of a 2-CTA pair loads half of the N rows
@@ -33,7 +34,7 @@ struct alignas(64) ConvLaunch {
     int relu;
     int shared_input;       // 1: every head reads image `img` (stem); 0: head h reads image h*B+img
     int k2_blocks;          // Cin2 / 64 extra K blocks read through a2_map / b2_map (0 = none)
-    int transposed;         // N = 128 layers: multiply as weights x pixels (conv_umma.cu, TR); needs residual == nullptr
+    int transposed;         // N = 128 layers: multiply as weights x pixels (conv_umma.cu, TR); a residual is added in the epilogue through res32_map
 };
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per (kernel, device).  The kernel is a
