@@ -24,6 +24,7 @@
 //   (cp.async.bulk) version is the next step.
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 #include "ingest.h"
@@ -196,6 +197,235 @@ __global__ void __launch_bounds__(1024) ingest_resample_phase_kernel(const In* _
         }
 }
 
+// ---- `quad` variant: four adjacent outputs per thread, persistent blocks, the stream staged by cp.async ------------------
+//
+// A thread's four outputs j .. j+3 read bands that start s_0 <= s_1 <= s_2 <= s_3 <= s_0 + quad_shift_max frames into the
+// staged span, so ONE window of TE floats -- read as TE/4 aligned 16-byte loads -- feeds all four: 7 LDS.128 for four
+// outputs in place of 4 x 18 LDS.32.  Each output's taps are kept in registers shifted to its place in that window
+// (W[g][sh_g + k] = w_g[k], zero elsewhere: the products with zero weights are exact, the sum order of the other
+// kernels is kept, so the results are the same to the bit).
+//
+// The raw interleaved PCM of the next kDepth items is in flight (cp.async, 16 bytes per request, zero-filled outside the
+// stream) into a ring of shared buffers while the block filters the current item, so HBM stays busy with ONE resident
+// block per SM (the tap registers allow no more) -- with the loads staged through registers instead, the first use of a
+// loaded value stalled the warp in front of the filter loop and the kernel ran at 0.6x of the one-phase kernel.  Per
+// item: wait for its raw chunks, convert + mix them into the float span (index 0 = the first frame the item needs, so a
+// thread's window alignment never changes), refill the freed raw slot, filter.  Mono or stereo streams whose base is
+// 16-byte aligned; everything else keeps the one-phase kernel.
+constexpr int kQuadDepth = 3;
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// one 16-byte chunk of the stream -> its mono frames (the arithmetic of mono4); returns how many
+template <typename In>
+__device__ __forceinline__ int chunk_to_mono(const int4 v, int channels, float (&o)[8]) {
+    const int r[4] = {v.x, v.y, v.z, v.w};
+    if constexpr (sizeof(In) == 2) {
+        constexpr float s = 1.0f / 32768.0f;
+        if (channels == 2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                o[i] = (static_cast<float>(static_cast<short>(r[i] & 0xFFFF)) * s + static_cast<float>(static_cast<short>(r[i] >> 16)) * s) * 0.5f;
+            return 4;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            o[2 * i] = static_cast<float>(static_cast<short>(r[i] & 0xFFFF)) * s;
+            o[2 * i + 1] = static_cast<float>(static_cast<short>(r[i] >> 16)) * s;
+        }
+        return 8;
+    } else {
+        if (channels == 2) {
+            o[0] = (__int_as_float(r[0]) + __int_as_float(r[1])) * 0.5f;
+            o[1] = (__int_as_float(r[2]) + __int_as_float(r[3])) * 0.5f;
+            return 2;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = __int_as_float(r[i]);
+        return 4;
+    }
+}
+
+template <typename In, int TE>
+__global__ void __launch_bounds__(384, 1) ingest_resample_quad_kernel(const In* __restrict__ pcm, long long n_frames, int channels,
+                                                                       ResamplePlan plan, const int* __restrict__ tap_first,
+                                                                       const float* __restrict__ tap_w, float* __restrict__ out,
+                                                                       long long n_real, long long out_len, int rounds,
+                                                                       int span_floats, int n_chunks, long long n_items, bool out16) {
+    extern __shared__ float4 smem4[];
+    float* const span = reinterpret_cast<float*>(smem4);             // [span_floats], a multiple of 4
+    const int4* const raw = reinterpret_cast<const int4*>(smem4) + span_floats / 4;   // [kQuadDepth][n_chunks]
+    const uint32_t raw_addr = static_cast<uint32_t>(__cvta_generic_to_shared(raw));
+    const int nt = blockDim.x, t = threadIdx.x;
+    const int bpf = static_cast<int>(sizeof(In)) * channels;        // bytes per frame: 2, 4 or 8
+    const int fpc = 16 / bpf;                                       // frames per 16-byte chunk
+    const int frames_round = 4 * nt / plan.new_f;                   // 4 * nt is a multiple of new_f
+    const int round_stride = frames_round * plan.orig_f;            // floats; a multiple of 4 when rounds > 1
+    const long long per_item = 4LL * nt * rounds;
+    const long long frames_item = static_cast<long long>(frames_round) * rounds;
+    if (static_cast<long long>(blockIdx.x) >= n_items) return;
+    const int items_mine = static_cast<int>((n_items - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const char* const bytes = reinterpret_cast<const char*>(pcm);
+
+    auto first_frame = [&](long long it) { return it * frames_item * plan.orig_f + plan.first0 - plan.width; };
+    auto issue = [&](int n, int slot) {                              // raw chunks of this block's n-th item -> ring slot
+        const long long a_lo = first_frame(blockIdx.x + static_cast<long long>(n) * gridDim.x) & ~static_cast<long long>(fpc - 1);
+        for (int i = t; i < n_chunks; i += nt) {
+            const long long f = a_lo + static_cast<long long>(fpc) * i;
+            long long nb = f < 0 ? 0 : (n_frames - f) * bpf;        // bytes of the stream from frame f on
+            nb = nb < 0 ? 0 : nb > 16 ? 16 : nb;
+            cp_async16_zfill(raw_addr + static_cast<uint32_t>(slot * n_chunks + i) * 16u, nb > 0 ? bytes + f * bpf : bytes,
+                             static_cast<int>(nb));
+        }
+    };
+#pragma unroll
+    for (int d = 0; d < kQuadDepth; ++d) {
+        if (d < items_mine) issue(d, d);
+        cp_async_commit();
+    }
+
+    // this thread's window and the four shifted tap sets
+    int pos[4], ph[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int m = (4 * t + g) / plan.new_f;
+        ph[g] = (4 * t + g) - m * plan.new_f;
+        pos[g] = m * plan.orig_f + tap_first[ph[g]] - plan.first0;
+    }
+    const int base = pos[0] & ~3;
+    float W[4][TE];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int sh = pos[g] - base;
+        const float* w = tap_w + static_cast<size_t>(ph[g]) * plan.max_taps;
+#pragma unroll
+        for (int i = 0; i < TE; ++i) {
+            const int k = i - sh;
+            W[g][i] = (k >= 0 && k < plan.max_taps) ? w[k] : 0.f;
+        }
+    }
+
+    int slot = 0;
+    for (int n = 0; n < items_mine; ++n) {
+        const long long item = blockIdx.x + static_cast<long long>(n) * gridDim.x;
+        cp_async_wait<kQuadDepth - 1>();                            // this thread's chunks of item n have landed
+        __syncthreads();                                            // ... and everyone's; the previous filter pass is over
+        {
+            const int skip = static_cast<int>(first_frame(item) & static_cast<long long>(fpc - 1));
+            const int4* src = raw + slot * n_chunks;
+            for (int i = t; i < n_chunks; i += nt) {
+                float o[8];
+                const int cnt = chunk_to_mono<In>(src[i], channels, o);
+                const int s0 = fpc * i - skip;
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (e < cnt && s0 + e >= 0 && s0 + e < span_floats) span[s0 + e] = o[e];
+            }
+        }
+        __syncthreads();
+        if (n + kQuadDepth < items_mine) issue(n + kQuadDepth, slot);
+        cp_async_commit();
+        slot = slot + 1 == kQuadDepth ? 0 : slot + 1;
+
+        const long long j_item = item * per_item + 4LL * t;
+        for (int i = 0; i < rounds; ++i) {
+            const float4* x = reinterpret_cast<const float4*>(span + base + i * round_stride);
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < TE / 4; ++c) {
+                const float4 v = x[c];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    acc[g] = fmaf(W[g][4 * c + 0], v.x, acc[g]);
+                    acc[g] = fmaf(W[g][4 * c + 1], v.y, acc[g]);
+                    acc[g] = fmaf(W[g][4 * c + 2], v.z, acc[g]);
+                    acc[g] = fmaf(W[g][4 * c + 3], v.w, acc[g]);
+                }
+            }
+            const long long j = j_item + 4LL * nt * i;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                if (j + g >= n_real) acc[g] = 0.f;                                     // IR:150-154
+            if (out16 && j + 3 < out_len) {
+                *reinterpret_cast<float4*>(out + j) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    if (j + g < out_len) out[j + g] = acc[g];
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+template <typename In, int TE>
+cudaError_t launch_quad(const In* pcm, long long n_frames, int channels, const ResamplePlan& plan, const int* tap_first,
+                        const float* tap_w, float* out, long long n_real, long long out_len, int threads, int rounds,
+                        int span_floats, int n_chunks, cudaStream_t stream) {
+    const size_t smem = static_cast<size_t>(span_floats) * sizeof(float) + static_cast<size_t>(kQuadDepth) * n_chunks * 16;
+    const long long per_item = 4LL * threads * rounds;
+    const long long n_items = (out_len + per_item - 1) / per_item;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(ingest_resample_quad_kernel<In, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);      // one block per SM (168 registers x 320 threads)
+    const bool out16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    ingest_resample_quad_kernel<In, TE><<<grid, threads, smem, stream>>>(pcm, n_frames, channels, plan, tap_first, tap_w, out, n_real,
+                                                                         out_len, rounds, span_floats, n_chunks, n_items, out16);
+    return cudaGetLastError();
+}
+
+// The quad kernel applies when the window of four adjacent outputs (alignment slack 3 + quad_shift_max + taps) fits 28
+// floats (the 32-float instantiation spills), a block of <= 384 threads holds whole periods of the phase pattern and the
+// stream is mono or stereo on a 16-byte aligned base; SAD_INGEST_QUAD=0 turns it off.
+template <typename In>
+bool try_quad(const In* pcm, long long n_frames, int channels, const ResamplePlan& plan, const int* tap_first, const float* tap_w,
+              float* out, long long n_real, long long out_len, cudaStream_t stream, cudaError_t* err) {
+    static const bool enabled = [] { const char* v = getenv("SAD_INGEST_QUAD"); return !(v && v[0] == '0'); }();
+    if (!enabled || plan.quad_shift_max < 0 || channels > 2 || n_frames < 1 || (reinterpret_cast<uintptr_t>(pcm) & 15) != 0) return false;
+    const int need = 3 + plan.quad_shift_max + plan.max_taps;
+    if (need > 28) return false;
+    const int TE = need <= 20 ? 20 : need <= 24 ? 24 : 28;
+    int period = plan.new_f;                                         // threads per period of the phase pattern: new_f / gcd(new_f, 4)
+    for (int g = 0; g < 2 && period % 2 == 0; ++g) period /= 2;
+    int threads = 0;
+    for (int lo : {256, 128}) {
+        threads = (lo + period - 1) / period * period;
+        if (threads <= 384) break;
+        threads = 0;
+    }
+    if (!threads) return false;
+    const int fpc = 16 / (static_cast<int>(sizeof(In)) * channels);
+    const int frames_round = 4 * threads / plan.new_f;
+    const int max_rounds = (frames_round * plan.orig_f) % 4 == 0 ? 8 : 1;
+    int rounds = max_rounds, span_floats = 0, n_chunks = 0;
+    auto size_for = [&](int r) {
+        const long long need_floats = (static_cast<long long>(frames_round) * r - 1) * plan.orig_f + plan.first_spread + TE;
+        span_floats = static_cast<int>((need_floats + 3) / 4 * 4);
+        n_chunks = static_cast<int>((need_floats + fpc - 1 + fpc - 1) / fpc);       // the first chunk may start fpc - 1 frames early
+        return static_cast<size_t>(span_floats) * 4 + static_cast<size_t>(kQuadDepth) * n_chunks * 16;
+    };
+    while (rounds >= 1 && size_for(rounds) > 120 * 1024) rounds >>= 1;
+    // short streams: smaller items, so that every SM gets a few
+    while (rounds > 1 && (out_len + 4LL * threads * rounds - 1) / (4LL * threads * rounds) < 4 * 148) rounds >>= 1;
+    if (rounds >= 1) size_for(rounds);
+    if (rounds < 1) return false;
+    switch (TE) {
+        case 20: *err = launch_quad<In, 20>(pcm, n_frames, channels, plan, tap_first, tap_w, out, n_real, out_len, threads, rounds, span_floats, n_chunks, stream); break;
+        case 24: *err = launch_quad<In, 24>(pcm, n_frames, channels, plan, tap_first, tap_w, out, n_real, out_len, threads, rounds, span_floats, n_chunks, stream); break;
+        default: *err = launch_quad<In, 28>(pcm, n_frames, channels, plan, tap_first, tap_w, out, n_real, out_len, threads, rounds, span_floats, n_chunks, stream); break;
+    }
+    return true;
+}
+
 template <typename In, int T>
 cudaError_t launch_phase(const In* pcm, long long n_frames, int channels, const ResamplePlan& plan, const int* tap_first,
                          const float* tap_w, float* out, long long n_real, long long out_len, int threads, int rounds,
@@ -257,6 +487,13 @@ cudaError_t ingest_launch(const void* pcm, int sample_format, long long n_frames
             ingest_copy_kernel<float><<<grid4, kBlock, 0, stream>>>(static_cast<const float*>(pcm), n_frames, channels, out, out_len, aligned);
     } else {
         cudaError_t e = cudaSuccess;
+        const bool quad = sample_format == 0
+            ? try_quad(static_cast<const int16_t*>(pcm), n_frames, channels, *plan, tap_first, tap_w, out, n_real, out_len, stream, &e)
+            : try_quad(static_cast<const float*>(pcm), n_frames, channels, *plan, tap_first, tap_w, out, n_real, out_len, stream, &e);
+        if (quad) {
+            if (launches) *launches += 1;
+            return e;
+        }
         const bool fast = sample_format == 0
             ? try_phase(static_cast<const int16_t*>(pcm), n_frames, channels, *plan, tap_first, tap_w, out, n_real, out_len, stream, &e)
             : try_phase(static_cast<const float*>(pcm), n_frames, channels, *plan, tap_first, tap_w, out, n_real, out_len, stream, &e);

@@ -103,3 +103,46 @@ def test_preprocess_waveform_and_cli_from_cd_audio(tmp_path):
     for i, seg in enumerate(res["segments"]):
         if margin[i] > 0.02:                                  # the bf16 trunk may flip a decision only inside its tolerance
             assert seg["label"] == R.label_name(int(labels[i]), 2, names[:-1], names[-1])
+
+
+_QUAD_PROBE = r"""
+import hashlib, sys
+import numpy as np, torch
+sys.path.insert(0, %r)
+from oracle import fixtures as FX
+from tests import gpu_common as G
+e = G.engine(2)
+for sr, ch, frames, fmt, odd in %r:
+    pcm = FX.synth_pcm16(frames, ch, sr, seed=5)
+    x = torch.from_numpy(pcm if fmt == "s16" else pcm.astype(np.float32) / 32768.0).cuda()
+    if odd:                                                  # a stream that starts one element into an allocation
+        buf = torch.empty(frames * ch + 1, dtype=x.dtype, device="cuda")
+        buf[1:].copy_(x.reshape(-1))
+        x = buf[1:].reshape(frames, ch)
+    y = e.ingest(x, sr)
+    print(sr, ch, frames, fmt, odd, y.numel(), hashlib.sha256(y.cpu().numpy().tobytes()).hexdigest())
+"""
+
+
+def test_quad_kernel_is_bit_identical_to_the_one_phase_kernel():
+    """The four-outputs-per-thread resampler (ingest.cu, `quad`) adds only products with zero weights to the sums of the
+    one-phase-per-thread kernel: the two must agree to the bit, for every ratio the quad kernel takes, both sample
+    formats, unaligned streams and lengths that end inside an item.  SAD_INGEST_QUAD=0 selects the older kernel."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cases = [(44100, 2, 400_003, "s16", 0), (44100, 2, 100_001, "s16", 1), (44100, 1, 90_000, "f32", 1),
+             (48000, 2, 300_007, "s16", 0), (48000, 3, 50_001, "f32", 0), (22050, 2, 120_001, "s16", 0),
+             (11025, 1, 70_001, "s16", 0), (16000, 1, 66_001, "f32", 0), (8000, 2, 40_003, "s16", 0),
+             (24000, 2, 99_999, "s16", 0), (37800, 2, 77_777, "s16", 0), (44100, 2, 3, "s16", 0),
+             (96000, 2, 200_001, "s16", 0)]                       # 96 kHz: 37 taps, not a quad ratio; same kernel either way
+    outs = []
+    for flag in ("1", "0"):
+        env = dict(os.environ, SAD_INGEST_QUAD=flag, PYTHONPATH=root)
+        r = subprocess.run([sys.executable, "-c", _QUAD_PROBE % (root, cases)], env=env, capture_output=True, text=True,
+                           timeout=600, cwd=root)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines())
+    assert len(outs[0]) == len(cases)
+    for a, b in zip(*outs):
+        assert a == b, (a, b)
