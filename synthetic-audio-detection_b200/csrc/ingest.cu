@@ -10,18 +10,21 @@
 // stride orig).  All but ~12*orig/min(orig,new) of those taps sit where the Hann window argument is clamped and are
 // below 1e-32: build_resample_taps (host) keeps the unclamped band per phase, the kernel below sums only that band.
 //
-//   Fast kernel (`phase` variant): a block owns blockDim * R consecutive outputs, blockDim a multiple of the number of
-//   phases, so a thread keeps ONE phase: its <= T taps live in registers for all R outputs.  The mono-mixed input span
-//   of the block is staged once in shared memory (coalesced reads of the interleaved PCM, each frame converted and mixed
-//   once), so per output the SM does T shared-memory reads and T FMAs and HBM sees every byte once.
-//   Fallback (`generic`): one output per thread, taps from global memory, for ratios with > 1024 phases or > 80 taps.
-//   Measured (B200, 25 min of stereo int16): 1.8-2.2 TB/s for 44.1 / 48 / 96 / 16 kHz input, 5.8 TB/s when no resampling is
-//   needed.  The FIR runs on CUDA cores at one shared-memory load per FMA: 18 LDS per output with 2-way conflicts caps the
-//   kernel near 2.4 TB/s.  A variant with two adjacent outputs per thread on 8-byte window loads (4x fewer LDS wavefronts)
-//   measured the SAME 1.8 TB/s at 96 registers / 2 blocks per SM -- stage -> sync -> compute leaves HBM idle while a block
-//   computes -- so it was dropped; hoisting four staging loads ahead of their first use (more registers, fewer resident
-//   blocks) was 20% SLOWER: occupancy, not per-thread latency, carries this kernel.  A persistent, double-buffered
-//   (cp.async.bulk) version is the next step.
+//   `pair` kernel (44.1 / 48 kHz and every lower rate; mono or stereo on a 16-byte aligned base): persistent blocks, the
+//   raw PCM of the next item staged by cp.async while the current one is filtered, two adjacent outputs per thread
+//   on one window of 16-byte shared loads with the taps in registers.  Measured (B200, 25 min of stereo int16,
+//   tools/ingest_bench.py): 3.6 TB/s at 44.1 and 48 kHz (55 % of the measured HBM copy bandwidth), 3.2-3.9 TB/s at
+//   8-24 kHz.  ncu on the way there: the first cut was instruction-issue bound (73 % issue slots, 131 instructions per
+//   output against 24 useful FMAs: a conversion pass with a division and two guarded stores per frame, 64-bit index
+//   arithmetic per round, the shared base address rebuilt from S2R at every use); the version below executes ~45.
+//   `phase` kernel (88.2 / 96 kHz, other channel counts, unaligned streams): a block owns blockDim * R consecutive outputs,
+//   blockDim a multiple of the number of phases, so a thread keeps ONE phase: its <= T taps live in registers for all R
+//   outputs.  The mono-mixed input span of the block is staged once in shared memory (coalesced reads of the interleaved
+//   PCM, each frame converted and mixed once): T shared loads and T FMAs per output, stage -> sync -> compute.
+//   1.8-2.1 TB/s; it was what every rate ran on before (18 LDS per output with 2-way conflicts, HBM idle while a block
+//   computes).
+//   `generic` fallback: one output per thread, taps from global memory, for ratios with > 1024 phases or > 80 taps.
+//   No resampling (32 kHz input): mix + pad only, 5.9 TB/s (90 %).
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -197,110 +200,128 @@ __global__ void __launch_bounds__(1024) ingest_resample_phase_kernel(const In* _
         }
 }
 
-// ---- `quad` variant: four adjacent outputs per thread, persistent blocks, the stream staged by cp.async ------------------
+// ---- `pair` variant: two adjacent outputs per thread, persistent blocks, the stream staged by cp.async -------------------
 //
-// A thread's four outputs j .. j+3 read bands that start s_0 <= s_1 <= s_2 <= s_3 <= s_0 + quad_shift_max frames into the
-// staged span, so ONE window of TE floats -- read as TE/4 aligned 16-byte loads -- feeds all four: 7 LDS.128 for four
-// outputs in place of 4 x 18 LDS.32.  Each output's taps are kept in registers shifted to its place in that window
-// (W[g][sh_g + k] = w_g[k], zero elsewhere: the products with zero weights are exact, the sum order of the other
-// kernels is kept, so the results are the same to the bit).
+// A thread's outputs j and j+1 read bands that start s_0 <= s_1 <= s_0 + pair_shift_max frames into the staged span, so
+// ONE window of TE floats -- read as TE/4 aligned 16-byte loads -- feeds both: 6 LDS.128 for two outputs in place of
+// 2 x 18 LDS.32, and a quarter warp's windows lie within 128 bytes of each other (no bank conflicts; with four outputs
+// per thread they span 176 and every load costs two wavefronts).  Each output's taps are kept in registers shifted to
+// its place in that window (W[g][sh_g + k] = w_g[k], zero elsewhere: the products with zero weights are exact and the
+// sum order of the other kernels is kept, so the results are the same to the bit).
 //
-// The raw interleaved PCM of the next kDepth items is in flight (cp.async, 16 bytes per request, zero-filled outside the
-// stream) into a ring of shared buffers while the block filters the current item, so HBM stays busy with ONE resident
-// block per SM (the tap registers allow no more) -- with the loads staged through registers instead, the first use of a
-// loaded value stalled the warp in front of the filter loop and the kernel ran at 0.6x of the one-phase kernel.  Per
-// item: wait for its raw chunks, convert + mix them into the float span (index 0 = the first frame the item needs, so a
-// thread's window alignment never changes), refill the freed raw slot, filter.  Mono or stereo streams whose base is
-// 16-byte aligned; everything else keeps the one-phase kernel.
-constexpr int kQuadDepth = 3;
+// The raw interleaved PCM of the next item(s) (kPairDepth slots) is in flight (cp.async, 16 bytes per request, zero-filled outside
+// the stream) into a ring of shared buffers while the block filters the current item -- with the loads staged through
+// registers instead, the first use of a loaded value stalled the warp in front of the filter loop.  Per item: wait for
+// its raw chunks, convert + mix them into the float span, refill the freed raw slot, filter.  The span holds one
+// sub-span per round (the outputs 2 * blockDim apart), each starting on a 16-byte boundary with the few frames it shares
+// with the next one written twice, so that a thread's window alignment is the same in every round and item whatever
+// the rate ratio.  Two blocks per SM (<= 102 registers) overlap one block's conversion with the other's filter pass.
+// Mono or stereo streams whose base is 16-byte aligned; everything else keeps the one-phase kernel.
+constexpr int kPairDepth = 2;
+constexpr int kPairThreads = 320;
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float4 ld_shared_f32x4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// one 16-byte chunk of the stream -> its mono frames (the arithmetic of mono4); returns how many
-template <typename In>
-__device__ __forceinline__ int chunk_to_mono(const int4 v, int channels, float (&o)[8]) {
-    const int r[4] = {v.x, v.y, v.z, v.w};
-    if constexpr (sizeof(In) == 2) {
-        constexpr float s = 1.0f / 32768.0f;
-        if (channels == 2) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                o[i] = (static_cast<float>(static_cast<short>(r[i] & 0xFFFF)) * s + static_cast<float>(static_cast<short>(r[i] >> 16)) * s) * 0.5f;
-            return 4;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            o[2 * i] = static_cast<float>(static_cast<short>(r[i] & 0xFFFF)) * s;
-            o[2 * i + 1] = static_cast<float>(static_cast<short>(r[i] >> 16)) * s;
-        }
-        return 8;
+struct PairGeometry {
+    int rounds;          // rounds of 2 * blockDim outputs per item
+    int round_stride;    // input frames between the sub-spans of two rounds
+    int sub_floats;      // floats per sub-span (a multiple of 4): round_stride + overlap, at least
+    int overlap;         // frames of the next round a sub-span also holds
+    int n_chunks;        // 16-byte chunks of raw PCM per item
+};
+
+// One frame of the staged raw PCM (shared address) as a mono float.  Every operation is exact for int16 (a sum of two
+// 16-bit values scaled by a power of two), so this equals mono_mix to the bit; the float mix is the same (a + b) * 0.5f.
+template <typename In, int CH>
+__device__ __forceinline__ float raw_frame_to_mono(uint32_t addr) {
+    if constexpr (sizeof(In) == 4 && CH == 2) {
+        float a, b;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(a), "=f"(b) : "r"(addr));
+        return (a + b) * 0.5f;
+    } else if constexpr (sizeof(In) == 4) {
+        float a;
+        asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(a) : "r"(addr));
+        return a;
+    } else if constexpr (CH == 2) {
+        int v;
+        asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(v) : "r"(addr));
+        return static_cast<float>(__dp2a_lo(v, 0x0101, 0)) * (0.5f / 32768.0f);                 // lo + hi in one instruction
     } else {
-        if (channels == 2) {
-            o[0] = (__int_as_float(r[0]) + __int_as_float(r[1])) * 0.5f;
-            o[1] = (__int_as_float(r[2]) + __int_as_float(r[3])) * 0.5f;
-            return 2;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = __int_as_float(r[i]);
-        return 4;
+        int v;
+        asm volatile("ld.shared.s16 %0, [%1];\n" : "=r"(v) : "r"(addr));
+        return static_cast<float>(v) * (1.0f / 32768.0f);
     }
 }
 
-template <typename In, int TE>
-__global__ void __launch_bounds__(384, 1) ingest_resample_quad_kernel(const In* __restrict__ pcm, long long n_frames, int channels,
-                                                                       ResamplePlan plan, const int* __restrict__ tap_first,
-                                                                       const float* __restrict__ tap_w, float* __restrict__ out,
-                                                                       long long n_real, long long out_len, int rounds,
-                                                                       int span_floats, int n_chunks, long long n_items, bool out16) {
+template <typename In, int CH, int TE, int MINB>
+__global__ void __launch_bounds__(kPairThreads, MINB) ingest_resample_pair_kernel(const In* __restrict__ pcm, long long n_frames,
+                                                                                   ResamplePlan plan, PairGeometry geo,
+                                                                                   const int* __restrict__ tap_first,
+                                                                                   const float* __restrict__ tap_w, float* __restrict__ out,
+                                                                                   long long n_real, long long out_len, long long n_items,
+                                                                                   bool out8) {
+    constexpr int bpf = static_cast<int>(sizeof(In)) * CH;          // bytes per frame: 2, 4 or 8
+    constexpr int fpc = 16 / bpf;                                   // frames per 16-byte chunk
     extern __shared__ float4 smem4[];
-    float* const span = reinterpret_cast<float*>(smem4);             // [span_floats], a multiple of 4
-    const int4* const raw = reinterpret_cast<const int4*>(smem4) + span_floats / 4;   // [kQuadDepth][n_chunks]
-    const uint32_t raw_addr = static_cast<uint32_t>(__cvta_generic_to_shared(raw));
+    float* const span = reinterpret_cast<float*>(smem4);             // [rounds][sub_floats]
+    uint32_t span_addr = static_cast<uint32_t>(__cvta_generic_to_shared(span));
+    asm volatile("mov.u32 %0, %0;\n" : "+r"(span_addr));            // opaque: keeps the address in a register (ptxas otherwise
+                                                                     // recomputes it from S2R CgaCtaId at every use)
+    const uint32_t raw_addr = span_addr + static_cast<uint32_t>(geo.rounds * geo.sub_floats) * 4u;   // [kPairDepth][n_chunks] x 16 bytes
     const int nt = blockDim.x, t = threadIdx.x;
-    const int bpf = static_cast<int>(sizeof(In)) * channels;        // bytes per frame: 2, 4 or 8
-    const int fpc = 16 / bpf;                                       // frames per 16-byte chunk
-    const int frames_round = 4 * nt / plan.new_f;                   // 4 * nt is a multiple of new_f
-    const int round_stride = frames_round * plan.orig_f;            // floats; a multiple of 4 when rounds > 1
-    const long long per_item = 4LL * nt * rounds;
-    const long long frames_item = static_cast<long long>(frames_round) * rounds;
+    const int per_item = 2 * nt * geo.rounds;
+    const long long frames_item = static_cast<long long>(geo.round_stride) * geo.rounds;
     if (static_cast<long long>(blockIdx.x) >= n_items) return;
     const int items_mine = static_cast<int>((n_items - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const char* const bytes = reinterpret_cast<const char*>(pcm);
 
-    auto first_frame = [&](long long it) { return it * frames_item * plan.orig_f + plan.first0 - plan.width; };
-    auto issue = [&](int n, int slot) {                              // raw chunks of this block's n-th item -> ring slot
-        const long long a_lo = first_frame(blockIdx.x + static_cast<long long>(n) * gridDim.x) & ~static_cast<long long>(fpc - 1);
-        for (int i = t; i < n_chunks; i += nt) {
-            const long long f = a_lo + static_cast<long long>(fpc) * i;
-            long long nb = f < 0 ? 0 : (n_frames - f) * bpf;        // bytes of the stream from frame f on
-            nb = nb < 0 ? 0 : nb > 16 ? 16 : nb;
-            cp_async16_zfill(raw_addr + static_cast<uint32_t>(slot * n_chunks + i) * 16u, nb > 0 ? bytes + f * bpf : bytes,
-                             static_cast<int>(nb));
+    // first input frame of this block's n-th item; consecutive items of the block are ff_step frames apart
+    const long long ff_step = frames_item * gridDim.x;
+    const long long ff0 = frames_item * blockIdx.x + plan.first0 - plan.width;
+    auto issue = [&](long long ff, int slot) {                       // raw chunks of the item that starts at frame ff -> ring slot
+        const long long a_lo = ff & ~static_cast<long long>(fpc - 1);
+        const uint32_t dst = raw_addr + static_cast<uint32_t>(slot * geo.n_chunks) * 16u;
+        if (a_lo >= 0 && a_lo + static_cast<long long>(fpc) * geo.n_chunks <= n_frames) {          // wholly inside the stream
+            const char* src = bytes + a_lo * bpf;
+            for (int i = t; i < geo.n_chunks; i += nt) cp_async16_zfill(dst + static_cast<uint32_t>(i) * 16u, src + i * 16, 16);
+        } else {
+            for (int i = t; i < geo.n_chunks; i += nt) {
+                const long long f = a_lo + static_cast<long long>(fpc) * i;
+                long long nb = f < 0 ? 0 : (n_frames - f) * bpf;    // bytes of the stream from frame f on
+                nb = nb < 0 ? 0 : nb > 16 ? 16 : nb;
+                cp_async16_zfill(dst + static_cast<uint32_t>(i) * 16u, nb > 0 ? bytes + f * bpf : bytes, static_cast<int>(nb));
+            }
         }
     };
 #pragma unroll
-    for (int d = 0; d < kQuadDepth; ++d) {
-        if (d < items_mine) issue(d, d);
+    for (int d = 0; d < kPairDepth; ++d) {
+        if (d < items_mine) issue(ff0 + d * ff_step, d);
         cp_async_commit();
     }
 
-    // this thread's window and the four shifted tap sets
-    int pos[4], ph[4];
+    // this thread's window inside a sub-span and the two shifted tap sets
+    int pos[2], ph[2];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const int m = (4 * t + g) / plan.new_f;
-        ph[g] = (4 * t + g) - m * plan.new_f;
+    for (int g = 0; g < 2; ++g) {
+        const int m = (2 * t + g) / plan.new_f;
+        ph[g] = (2 * t + g) - m * plan.new_f;
         pos[g] = m * plan.orig_f + tap_first[ph[g]] - plan.first0;
     }
     const int base = pos[0] & ~3;
-    float W[4][TE];
+    float W[2][TE];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < 2; ++g) {
         const int sh = pos[g] - base;
         const float* w = tap_w + static_cast<size_t>(ph[g]) * plan.max_taps;
 #pragma unroll
@@ -309,120 +330,151 @@ __global__ void __launch_bounds__(384, 1) ingest_resample_quad_kernel(const In* 
             W[g][i] = (k >= 0 && k < plan.max_taps) ? w[k] : 0.f;
         }
     }
+    const uint32_t win_addr = span_addr + static_cast<uint32_t>(base) * 4u;
 
     int slot = 0;
-    for (int n = 0; n < items_mine; ++n) {
-        const long long item = blockIdx.x + static_cast<long long>(n) * gridDim.x;
-        cp_async_wait<kQuadDepth - 1>();                            // this thread's chunks of item n have landed
+    long long ff = ff0;                                              // first frame of item n
+    long long j_item = static_cast<long long>(blockIdx.x) * per_item + 2LL * t;   // this thread's first output of item n
+    const long long j_step = static_cast<long long>(per_item) * gridDim.x;
+    for (int n = 0; n < items_mine; ++n, ff += ff_step, j_item += j_step) {
+        cp_async_wait<kPairDepth - 1>();                            // this thread's chunks of item n have landed
         __syncthreads();                                            // ... and everyone's; the previous filter pass is over
         {
-            const int skip = static_cast<int>(first_frame(item) & static_cast<long long>(fpc - 1));
-            const int4* src = raw + slot * n_chunks;
-            for (int i = t; i < n_chunks; i += nt) {
-                float o[8];
-                const int cnt = chunk_to_mono<In>(src[i], channels, o);
-                const int s0 = fpc * i - skip;
+            // raw -> float span, one sub-span per round: frames [i * round_stride, + sub_floats) of the item (the last
+            // `overlap` of them are converted again as the head of the next round).  A thread keeps its offset k and
+            // walks the rounds: two address increments per frame.
+            const int skip = static_cast<int>(ff & static_cast<long long>(fpc - 1));
+            const uint32_t src0 = raw_addr + static_cast<uint32_t>(slot * geo.n_chunks) * 16u + static_cast<uint32_t>(skip) * bpf;
+            const uint32_t src_step = static_cast<uint32_t>(geo.round_stride) * bpf, dst_step = static_cast<uint32_t>(geo.sub_floats) * 4u;
+            for (int k = t; k < geo.sub_floats; k += nt) {
+                uint32_t src = src0 + static_cast<uint32_t>(k) * bpf, dst = span_addr + static_cast<uint32_t>(k) * 4u;
+                int i = 0;
+                for (; i + 4 <= geo.rounds; i += 4) {               // four loads in flight, then four stores
+                    float v[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    if (e < cnt && s0 + e >= 0 && s0 + e < span_floats) span[s0 + e] = o[e];
+                    for (int u = 0; u < 4; ++u) v[u] = raw_frame_to_mono<In, CH>(src + static_cast<uint32_t>(u) * src_step);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) st_shared_f32(dst + static_cast<uint32_t>(u) * dst_step, v[u]);
+                    src += 4u * src_step;
+                    dst += 4u * dst_step;
+                }
+                for (; i < geo.rounds; ++i) {
+                    st_shared_f32(dst, raw_frame_to_mono<In, CH>(src));
+                    src += src_step;
+                    dst += dst_step;
+                }
             }
         }
         __syncthreads();
-        if (n + kQuadDepth < items_mine) issue(n + kQuadDepth, slot);
+        if (n + kPairDepth < items_mine) issue(ff + kPairDepth * ff_step, slot);
         cp_async_commit();
-        slot = slot + 1 == kQuadDepth ? 0 : slot + 1;
+        slot = slot + 1 == kPairDepth ? 0 : slot + 1;
 
-        const long long j_item = item * per_item + 4LL * t;
-        for (int i = 0; i < rounds; ++i) {
-            const float4* x = reinterpret_cast<const float4*>(span + base + i * round_stride);
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool whole = out8 && j_item - 2LL * t + per_item <= n_real;   // no padding, no tail inside this item
+        float* o = out + j_item;
+        uint32_t xa = win_addr;
+#pragma unroll 2
+        for (int i = 0; i < geo.rounds; ++i) {
+            float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
             for (int c = 0; c < TE / 4; ++c) {
-                const float4 v = x[c];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    acc[g] = fmaf(W[g][4 * c + 0], v.x, acc[g]);
-                    acc[g] = fmaf(W[g][4 * c + 1], v.y, acc[g]);
-                    acc[g] = fmaf(W[g][4 * c + 2], v.z, acc[g]);
-                    acc[g] = fmaf(W[g][4 * c + 3], v.w, acc[g]);
-                }
+                const float4 v = ld_shared_f32x4(xa + 16u * c);
+                acc0 = fmaf(W[0][4 * c + 0], v.x, acc0);
+                acc1 = fmaf(W[1][4 * c + 0], v.x, acc1);
+                acc0 = fmaf(W[0][4 * c + 1], v.y, acc0);
+                acc1 = fmaf(W[1][4 * c + 1], v.y, acc1);
+                acc0 = fmaf(W[0][4 * c + 2], v.z, acc0);
+                acc1 = fmaf(W[1][4 * c + 2], v.z, acc1);
+                acc0 = fmaf(W[0][4 * c + 3], v.w, acc0);
+                acc1 = fmaf(W[1][4 * c + 3], v.w, acc1);
             }
-            const long long j = j_item + 4LL * nt * i;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-                if (j + g >= n_real) acc[g] = 0.f;                                     // IR:150-154
-            if (out16 && j + 3 < out_len) {
-                *reinterpret_cast<float4*>(out + j) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            if (whole) {
+                *reinterpret_cast<float2*>(o) = make_float2(acc0, acc1);
             } else {
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    if (j + g < out_len) out[j + g] = acc[g];
+                const long long j = j_item + 2LL * nt * i;
+                if (j >= n_real) acc0 = 0.f;                                           // IR:150-154
+                if (j + 1 >= n_real) acc1 = 0.f;
+                if (j < out_len) o[0] = acc0;
+                if (j + 1 < out_len) o[1] = acc1;
             }
+            o += 2 * nt;
+            xa += static_cast<uint32_t>(geo.sub_floats) * 4u;
         }
     }
     cp_async_wait<0>();
 }
 
-template <typename In, int TE>
-cudaError_t launch_quad(const In* pcm, long long n_frames, int channels, const ResamplePlan& plan, const int* tap_first,
-                        const float* tap_w, float* out, long long n_real, long long out_len, int threads, int rounds,
-                        int span_floats, int n_chunks, cudaStream_t stream) {
-    const size_t smem = static_cast<size_t>(span_floats) * sizeof(float) + static_cast<size_t>(kQuadDepth) * n_chunks * 16;
-    const long long per_item = 4LL * threads * rounds;
+template <typename In, int CH, int TE, int MINB>
+cudaError_t launch_pair(const In* pcm, long long n_frames, const ResamplePlan& plan, const PairGeometry& geo,
+                        const int* tap_first, const float* tap_w, float* out, long long n_real, long long out_len, int threads,
+                        size_t smem, int sms, cudaStream_t stream) {
+    const long long per_item = 2LL * threads * geo.rounds;
     const long long n_items = (out_len + per_item - 1) / per_item;
-    int dev = 0, sms = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(ingest_resample_quad_kernel<In, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(ingest_resample_pair_kernel<In, CH, TE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);      // one block per SM (168 registers x 320 threads)
-    const bool out16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    ingest_resample_quad_kernel<In, TE><<<grid, threads, smem, stream>>>(pcm, n_frames, channels, plan, tap_first, tap_w, out, n_real,
-                                                                         out_len, rounds, span_floats, n_chunks, n_items, out16);
+    const long long cap = static_cast<long long>(sms) * MINB;
+    const unsigned grid = static_cast<unsigned>(n_items < cap ? n_items : cap);
+    const bool out8 = (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+    ingest_resample_pair_kernel<In, CH, TE, MINB><<<grid, threads, smem, stream>>>(pcm, n_frames, plan, geo, tap_first, tap_w, out,
+                                                                                   n_real, out_len, n_items, out8);
     return cudaGetLastError();
 }
 
-// The quad kernel applies when the window of four adjacent outputs (alignment slack 3 + quad_shift_max + taps) fits 28
-// floats (the 32-float instantiation spills), a block of <= 384 threads holds whole periods of the phase pattern and the
-// stream is mono or stereo on a 16-byte aligned base; SAD_INGEST_QUAD=0 turns it off.
+// The pair kernel applies when the window of two adjacent outputs (alignment slack 3 + pair_shift_max + taps) fits 28
+// floats (44.1 / 48 kHz and every rate below; at 88.2 / 96 kHz, 34-37 taps, the 44-float instantiation needs 158 registers,
+// one block per SM, and measured 0.91x of the one-phase kernel), a block of <= 320 threads holds whole periods of the phase pattern and the stream is mono or stereo on a
+// 16-byte aligned base; SAD_INGEST_PAIR=0 turns it off.
 template <typename In>
-bool try_quad(const In* pcm, long long n_frames, int channels, const ResamplePlan& plan, const int* tap_first, const float* tap_w,
+bool try_pair(const In* pcm, long long n_frames, int channels, const ResamplePlan& plan, const int* tap_first, const float* tap_w,
               float* out, long long n_real, long long out_len, cudaStream_t stream, cudaError_t* err) {
-    static const bool enabled = [] { const char* v = getenv("SAD_INGEST_QUAD"); return !(v && v[0] == '0'); }();
-    if (!enabled || plan.quad_shift_max < 0 || channels > 2 || n_frames < 1 || (reinterpret_cast<uintptr_t>(pcm) & 15) != 0) return false;
-    const int need = 3 + plan.quad_shift_max + plan.max_taps;
+    static const bool enabled = [] { const char* v = getenv("SAD_INGEST_PAIR"); return !(v && v[0] == '0'); }();
+    if (!enabled || plan.pair_shift_max < 0 || channels > 2 || n_frames < 1 || (reinterpret_cast<uintptr_t>(pcm) & 15) != 0) return false;
+    const int need = 3 + plan.pair_shift_max + plan.max_taps;
     if (need > 28) return false;
     const int TE = need <= 20 ? 20 : need <= 24 ? 24 : 28;
-    int period = plan.new_f;                                         // threads per period of the phase pattern: new_f / gcd(new_f, 4)
-    for (int g = 0; g < 2 && period % 2 == 0; ++g) period /= 2;
-    int threads = 0;
-    for (int lo : {256, 128}) {
-        threads = (lo + period - 1) / period * period;
-        if (threads <= 384) break;
-        threads = 0;
-    }
-    if (!threads) return false;
+    const int period = plan.new_f % 2 == 0 ? plan.new_f / 2 : plan.new_f;   // threads per period of the phase pattern
+    if (period > kPairThreads) return false;
+    const int threads = kPairThreads / period * period;
+    if (threads < 128) return false;
+    int dev = 0, sms = 0;
+    if ((*err = cudaGetDevice(&dev)) != cudaSuccess || (*err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+        return true;
+    constexpr int min_blocks = 2;
     const int fpc = 16 / (static_cast<int>(sizeof(In)) * channels);
-    const int frames_round = 4 * threads / plan.new_f;
-    const int max_rounds = (frames_round * plan.orig_f) % 4 == 0 ? 8 : 1;
-    int rounds = max_rounds, span_floats = 0, n_chunks = 0;
+    const int frames_round = 2 * threads / plan.new_f;
+    PairGeometry geo{};
+    geo.round_stride = frames_round * plan.orig_f;
+    const int need_round = (frames_round - 1) * plan.orig_f + plan.first_spread + TE;   // frames a round's windows reach over
+    geo.sub_floats = (need_round + 3) / 4 * 4;
+    if (geo.sub_floats < geo.round_stride) geo.sub_floats = (geo.round_stride + 3) / 4 * 4;
+    geo.overlap = geo.sub_floats - geo.round_stride;
+    size_t smem = 0;
     auto size_for = [&](int r) {
-        const long long need_floats = (static_cast<long long>(frames_round) * r - 1) * plan.orig_f + plan.first_spread + TE;
-        span_floats = static_cast<int>((need_floats + 3) / 4 * 4);
-        n_chunks = static_cast<int>((need_floats + fpc - 1 + fpc - 1) / fpc);       // the first chunk may start fpc - 1 frames early
-        return static_cast<size_t>(span_floats) * 4 + static_cast<size_t>(kQuadDepth) * n_chunks * 16;
+        geo.rounds = r;
+        const long long need_item = static_cast<long long>(r - 1) * geo.round_stride + geo.sub_floats;
+        geo.n_chunks = static_cast<int>((need_item + fpc - 1 + fpc - 1) / fpc);     // the first chunk may start fpc - 1 frames early
+        smem = static_cast<size_t>(r) * geo.sub_floats * 4 + static_cast<size_t>(kPairDepth) * geo.n_chunks * 16;
+        return smem;
     };
-    while (rounds >= 1 && size_for(rounds) > 120 * 1024) rounds >>= 1;
-    // short streams: smaller items, so that every SM gets a few
-    while (rounds > 1 && (out_len + 4LL * threads * rounds - 1) / (4LL * threads * rounds) < 4 * 148) rounds >>= 1;
-    if (rounds >= 1) size_for(rounds);
+    const size_t budget = 100 * 1024;                                // two blocks per SM
+    int rounds = 16;
+    while (rounds >= 1 && size_for(rounds) > budget) rounds >>= 1;
+    // short streams: smaller items, so that every resident block gets a few
+    while (rounds > 1 && (out_len + 2LL * threads * rounds - 1) / (2LL * threads * rounds) < 4LL * sms * min_blocks) rounds >>= 1;
     if (rounds < 1) return false;
+    size_for(rounds);
+#define SAD_PAIR_CASE(TE_, MINB_)                                                                                                     \
+    *err = channels == 2 ? launch_pair<In, 2, TE_, MINB_>(pcm, n_frames, plan, geo, tap_first, tap_w, out, n_real, out_len, threads,  \
+                                                          smem, sms, stream)                                                          \
+                         : launch_pair<In, 1, TE_, MINB_>(pcm, n_frames, plan, geo, tap_first, tap_w, out, n_real, out_len, threads,  \
+                                                          smem, sms, stream)
     switch (TE) {
-        case 20: *err = launch_quad<In, 20>(pcm, n_frames, channels, plan, tap_first, tap_w, out, n_real, out_len, threads, rounds, span_floats, n_chunks, stream); break;
-        case 24: *err = launch_quad<In, 24>(pcm, n_frames, channels, plan, tap_first, tap_w, out, n_real, out_len, threads, rounds, span_floats, n_chunks, stream); break;
-        default: *err = launch_quad<In, 28>(pcm, n_frames, channels, plan, tap_first, tap_w, out, n_real, out_len, threads, rounds, span_floats, n_chunks, stream); break;
+        case 20: SAD_PAIR_CASE(20, 2); break;
+        case 24: SAD_PAIR_CASE(24, 2); break;
+        default: SAD_PAIR_CASE(28, 2); break;
     }
+#undef SAD_PAIR_CASE
     return true;
 }
 
@@ -487,10 +539,10 @@ cudaError_t ingest_launch(const void* pcm, int sample_format, long long n_frames
             ingest_copy_kernel<float><<<grid4, kBlock, 0, stream>>>(static_cast<const float*>(pcm), n_frames, channels, out, out_len, aligned);
     } else {
         cudaError_t e = cudaSuccess;
-        const bool quad = sample_format == 0
-            ? try_quad(static_cast<const int16_t*>(pcm), n_frames, channels, *plan, tap_first, tap_w, out, n_real, out_len, stream, &e)
-            : try_quad(static_cast<const float*>(pcm), n_frames, channels, *plan, tap_first, tap_w, out, n_real, out_len, stream, &e);
-        if (quad) {
+        const bool pair = sample_format == 0
+            ? try_pair(static_cast<const int16_t*>(pcm), n_frames, channels, *plan, tap_first, tap_w, out, n_real, out_len, stream, &e)
+            : try_pair(static_cast<const float*>(pcm), n_frames, channels, *plan, tap_first, tap_w, out, n_real, out_len, stream, &e);
+        if (pair) {
             if (launches) *launches += 1;
             return e;
         }

@@ -16,10 +16,10 @@ struct ResamplePlan {
     int width;           // torchaudio's one-sided kernel reach in input frames
     int taps_full;       // 2*width + orig_f: length of torchaudio's dense kernel
     int max_taps;        // taps kept per phase (the band where the Hann window argument is not clamped)
-    // geometry of the bands, for the kernel that computes four adjacent outputs per thread (ingest.cu):
+    // geometry of the bands, for the kernel that computes two adjacent outputs per thread (ingest.cu):
     int first0;          // first kept tap of phase 0
     int first_spread;    // max over phases of (first kept tap) - first0
-    int quad_shift_max;  // max distance in input frames between the band starts of outputs j and j+3 (j % 4 == 0);
+    int pair_shift_max;  // max distance in input frames between the band starts of outputs j and j+1 (j even);
                          // -1 when band starts are not non-decreasing in j
 };
 
@@ -97,10 +97,10 @@ inline bool build_resample_taps(int sr_in, ResamplePlan* plan, std::vector<int>*
     for (int p = 0; p < nw; ++p)
         if ((*first)[p] - plan->first0 > plan->first_spread) plan->first_spread = (*first)[p] - plan->first0;
     auto start = [&](long long j) { return (j / nw) * orig + (*first)[j % nw]; };
-    plan->quad_shift_max = 0;
-    for (long long j = 0; j < 4LL * nw + 4; ++j) {
-        if (start(j + 1) < start(j)) { plan->quad_shift_max = -1; break; }
-        if (j % 4 == 0 && start(j + 3) - start(j) > plan->quad_shift_max) plan->quad_shift_max = static_cast<int>(start(j + 3) - start(j));
+    plan->pair_shift_max = 0;
+    for (long long j = 0; j < 2LL * nw + 2; ++j) {
+        if (start(j + 1) < start(j)) { plan->pair_shift_max = -1; break; }
+        if (j % 2 == 0 && start(j + 1) - start(j) > plan->pair_shift_max) plan->pair_shift_max = static_cast<int>(start(j + 1) - start(j));
     }
     return true;
 }

@@ -105,7 +105,7 @@ def test_preprocess_waveform_and_cli_from_cd_audio(tmp_path):
             assert seg["label"] == R.label_name(int(labels[i]), 2, names[:-1], names[-1])
 
 
-_QUAD_PROBE = r"""
+_PAIR_PROBE = r"""
 import hashlib, sys
 import numpy as np, torch
 sys.path.insert(0, %r)
@@ -124,10 +124,11 @@ for sr, ch, frames, fmt, odd in %r:
 """
 
 
-def test_quad_kernel_is_bit_identical_to_the_one_phase_kernel():
-    """The four-outputs-per-thread resampler (ingest.cu, `quad`) adds only products with zero weights to the sums of the
-    one-phase-per-thread kernel: the two must agree to the bit, for every ratio the quad kernel takes, both sample
-    formats, unaligned streams and lengths that end inside an item.  SAD_INGEST_QUAD=0 selects the older kernel."""
+def test_pair_kernel_is_bit_identical_to_the_one_phase_kernel():
+    """The two-outputs-per-thread resampler (ingest.cu, `pair`) adds only products with zero weights to the sums of the
+    one-phase-per-thread kernel: the two must agree to the bit, for every kind of ratio the pair kernel takes, both
+    sample formats, mono and stereo, unaligned streams (which keep the older kernel) and lengths that end inside an
+    item.  SAD_INGEST_PAIR=0 selects the older kernel everywhere."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -135,11 +136,12 @@ def test_quad_kernel_is_bit_identical_to_the_one_phase_kernel():
              (48000, 2, 300_007, "s16", 0), (48000, 3, 50_001, "f32", 0), (22050, 2, 120_001, "s16", 0),
              (11025, 1, 70_001, "s16", 0), (16000, 1, 66_001, "f32", 0), (8000, 2, 40_003, "s16", 0),
              (24000, 2, 99_999, "s16", 0), (37800, 2, 77_777, "s16", 0), (44100, 2, 3, "s16", 0),
-             (96000, 2, 200_001, "s16", 0)]                       # 96 kHz: 37 taps, not a quad ratio; same kernel either way
+             (96000, 2, 200_001, "s16", 0), (88200, 1, 150_001, "f32", 0), (44100, 2, 9_000_001, "s16", 0),
+             (48000, 1, 5_000_003, "s16", 0), (16000, 2, 3_000_001, "f32", 0)]   # the long ones use full-size items
     outs = []
     for flag in ("1", "0"):
-        env = dict(os.environ, SAD_INGEST_QUAD=flag, PYTHONPATH=root)
-        r = subprocess.run([sys.executable, "-c", _QUAD_PROBE % (root, cases)], env=env, capture_output=True, text=True,
+        env = dict(os.environ, SAD_INGEST_PAIR=flag, PYTHONPATH=root)
+        r = subprocess.run([sys.executable, "-c", _PAIR_PROBE % (root, cases)], env=env, capture_output=True, text=True,
                            timeout=600, cwd=root)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip().splitlines())

@@ -1,7 +1,7 @@
 """Throughput of sad_ingest per input rate (stereo int16, stream larger than L2): GB/s of input + output bytes.
 
-    python tools/ingest_bench.py                # quad kernel where it applies
-    SAD_INGEST_QUAD=0 python tools/ingest_bench.py
+    python tools/ingest_bench.py                # pair kernel where it applies
+    SAD_INGEST_PAIR=0 python tools/ingest_bench.py
 """
 import json
 import os
@@ -17,7 +17,7 @@ def main():
     peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))
     eng = Engine(2, max_batch=1)                            # ingest needs no weights
     rows = []
-    for sr in (44100, 48000, 22050, 16000, 8000, 24000, 96000, 32000):
+    for sr in (44100, 48000, 22050, 16000, 8000, 24000, 96000, 88200, 32000):
         frames = sr * 1500                                     # 25 min of audio
         pcm = torch.randint(-20000, 20000, (frames, 2), dtype=torch.int16, device="cuda")
         for _ in range(3):
@@ -34,7 +34,7 @@ def main():
         rows.append({"sr_in": sr, "ms": round(ms, 4), "GBps": round(nbytes / 1e9 / (ms / 1e3), 1),
                      "frac_hbm": round(nbytes / 1e9 / (ms / 1e3) / peaks["hbm_gbs"], 3)})
         del pcm, y
-    print(json.dumps({"quad": os.environ.get("SAD_INGEST_QUAD", "1"), "rows": rows}))
+    print(json.dumps({"pair": os.environ.get("SAD_INGEST_PAIR", "1"), "rows": rows}))
 
 
 if __name__ == "__main__":
