@@ -10,14 +10,14 @@
 // stride orig).  All but ~12*orig/min(orig,new) of those taps sit where the Hann window argument is clamped and are
 // below 1e-32: build_resample_taps (host) keeps the unclamped band per phase, the kernel below sums only that band.
 //
-//   `pair` kernel (44.1 / 48 kHz and every lower rate; mono or stereo on a 16-byte aligned base): persistent blocks, the
+//   `pair` kernel (every rate up to 96 kHz; mono or stereo on a 16-byte aligned base): persistent blocks, the
 //   raw PCM of the next item staged by cp.async while the current one is filtered, two adjacent outputs per thread
 //   on one window of 16-byte shared loads with the taps in registers.  Measured (B200, 25 min of stereo int16,
 //   tools/ingest_bench.py): 3.6 TB/s at 44.1 and 48 kHz (55 % of the measured HBM copy bandwidth), 3.2-3.9 TB/s at
-//   8-24 kHz.  ncu on the way there: the first cut was instruction-issue bound (73 % issue slots, 131 instructions per
+//   8-24 kHz, 2.3-2.4 TB/s at 88.2 / 96 kHz (one output per thread there).  ncu on the way there: the first cut was instruction-issue bound (73 % issue slots, 131 instructions per
 //   output against 24 useful FMAs: a conversion pass with a division and two guarded stores per frame, 64-bit index
 //   arithmetic per round, the shared base address rebuilt from S2R at every use); the version below executes ~45.
-//   `phase` kernel (88.2 / 96 kHz, other channel counts, unaligned streams): a block owns blockDim * R consecutive outputs,
+//   `phase` kernel (other channel counts, unaligned streams, 192 kHz): a block owns blockDim * R consecutive outputs,
 //   blockDim a multiple of the number of phases, so a thread keeps ONE phase: its <= T taps live in registers for all R
 //   outputs.  The mono-mixed input span of the block is staged once in shared memory (coalesced reads of the interleaved
 //   PCM, each frame converted and mixed once): T shared loads and T FMAs per output, stage -> sync -> compute.
@@ -264,8 +264,8 @@ __device__ __forceinline__ float raw_frame_to_mono(uint32_t addr) {
     }
 }
 
-template <typename In, int CH, int TE, int MINB>
-__global__ void __launch_bounds__(kPairThreads, MINB) ingest_resample_pair_kernel(const In* __restrict__ pcm, long long n_frames,
+template <typename In, int CH, int TE, int G>
+__global__ void __launch_bounds__(kPairThreads, 2) ingest_resample_pair_kernel(const In* __restrict__ pcm, long long n_frames,
                                                                                    ResamplePlan plan, PairGeometry geo,
                                                                                    const int* __restrict__ tap_first,
                                                                                    const float* __restrict__ tap_w, float* __restrict__ out,
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(kPairThreads, MINB) ingest_resample_pair_kerne
                                                                      // recomputes it from S2R CgaCtaId at every use)
     const uint32_t raw_addr = span_addr + static_cast<uint32_t>(geo.rounds * geo.sub_floats) * 4u;   // [kPairDepth][n_chunks] x 16 bytes
     const int nt = blockDim.x, t = threadIdx.x;
-    const int per_item = 2 * nt * geo.rounds;
+    const int per_item = G * nt * geo.rounds;
     const long long frames_item = static_cast<long long>(geo.round_stride) * geo.rounds;
     if (static_cast<long long>(blockIdx.x) >= n_items) return;
     const int items_mine = static_cast<int>((n_items - blockIdx.x + gridDim.x - 1) / gridDim.x);
@@ -310,18 +310,18 @@ __global__ void __launch_bounds__(kPairThreads, MINB) ingest_resample_pair_kerne
         cp_async_commit();
     }
 
-    // this thread's window inside a sub-span and the two shifted tap sets
-    int pos[2], ph[2];
+    // this thread's window inside a sub-span and its G shifted tap sets
+    int pos[G], ph[G];
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-        const int m = (2 * t + g) / plan.new_f;
-        ph[g] = (2 * t + g) - m * plan.new_f;
+    for (int g = 0; g < G; ++g) {
+        const int m = (G * t + g) / plan.new_f;
+        ph[g] = (G * t + g) - m * plan.new_f;
         pos[g] = m * plan.orig_f + tap_first[ph[g]] - plan.first0;
     }
     const int base = pos[0] & ~3;
-    float W[2][TE];
+    float W[G][TE];
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < G; ++g) {
         const int sh = pos[g] - base;
         const float* w = tap_w + static_cast<size_t>(ph[g]) * plan.max_taps;
 #pragma unroll
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kPairThreads, MINB) ingest_resample_pair_kerne
 
     int slot = 0;
     long long ff = ff0;                                              // first frame of item n
-    long long j_item = static_cast<long long>(blockIdx.x) * per_item + 2LL * t;   // this thread's first output of item n
+    long long j_item = static_cast<long long>(blockIdx.x) * per_item + G * t;   // this thread's first output of item n
     const long long j_step = static_cast<long long>(per_item) * gridDim.x;
     for (int n = 0; n < items_mine; ++n, ff += ff_step, j_item += j_step) {
         cp_async_wait<kPairDepth - 1>();                            // this thread's chunks of item n have landed
@@ -370,79 +370,82 @@ __global__ void __launch_bounds__(kPairThreads, MINB) ingest_resample_pair_kerne
         cp_async_commit();
         slot = slot + 1 == kPairDepth ? 0 : slot + 1;
 
-        const bool whole = out8 && j_item - 2LL * t + per_item <= n_real;   // no padding, no tail inside this item
+        const bool whole = out8 && j_item - G * t + per_item <= n_real;   // no padding, no tail inside this item
         float* o = out + j_item;
         uint32_t xa = win_addr;
 #pragma unroll 2
         for (int i = 0; i < geo.rounds; ++i) {
-            float acc0 = 0.f, acc1 = 0.f;
+            float acc[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) acc[g] = 0.f;
 #pragma unroll
             for (int c = 0; c < TE / 4; ++c) {
                 const float4 v = ld_shared_f32x4(xa + 16u * c);
-                acc0 = fmaf(W[0][4 * c + 0], v.x, acc0);
-                acc1 = fmaf(W[1][4 * c + 0], v.x, acc1);
-                acc0 = fmaf(W[0][4 * c + 1], v.y, acc0);
-                acc1 = fmaf(W[1][4 * c + 1], v.y, acc1);
-                acc0 = fmaf(W[0][4 * c + 2], v.z, acc0);
-                acc1 = fmaf(W[1][4 * c + 2], v.z, acc1);
-                acc0 = fmaf(W[0][4 * c + 3], v.w, acc0);
-                acc1 = fmaf(W[1][4 * c + 3], v.w, acc1);
+                const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int g = 0; g < G; ++g) acc[g] = fmaf(W[g][4 * c + e], x[e], acc[g]);
             }
             if (whole) {
-                *reinterpret_cast<float2*>(o) = make_float2(acc0, acc1);
+                if constexpr (G == 2) *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1]);
+                else o[0] = acc[0];
             } else {
-                const long long j = j_item + 2LL * nt * i;
-                if (j >= n_real) acc0 = 0.f;                                           // IR:150-154
-                if (j + 1 >= n_real) acc1 = 0.f;
-                if (j < out_len) o[0] = acc0;
-                if (j + 1 < out_len) o[1] = acc1;
+                const long long j = j_item + static_cast<long long>(G) * nt * i;
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+                    if (j + g < out_len) o[g] = j + g < n_real ? acc[g] : 0.f;         // IR:150-154
             }
-            o += 2 * nt;
+            o += G * nt;
             xa += static_cast<uint32_t>(geo.sub_floats) * 4u;
         }
     }
     cp_async_wait<0>();
 }
 
-template <typename In, int CH, int TE, int MINB>
+template <typename In, int CH, int TE, int G>
 cudaError_t launch_pair(const In* pcm, long long n_frames, const ResamplePlan& plan, const PairGeometry& geo,
                         const int* tap_first, const float* tap_w, float* out, long long n_real, long long out_len, int threads,
                         size_t smem, int sms, cudaStream_t stream) {
-    const long long per_item = 2LL * threads * geo.rounds;
+    const long long per_item = static_cast<long long>(G) * threads * geo.rounds;
     const long long n_items = (out_len + per_item - 1) / per_item;
-    cudaError_t e = cudaFuncSetAttribute(ingest_resample_pair_kernel<In, CH, TE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(ingest_resample_pair_kernel<In, CH, TE, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    const long long cap = static_cast<long long>(sms) * MINB;
+    const long long cap = static_cast<long long>(sms) * 2;             // two resident blocks per SM
     const unsigned grid = static_cast<unsigned>(n_items < cap ? n_items : cap);
     const bool out8 = (reinterpret_cast<uintptr_t>(out) & 7) == 0;
-    ingest_resample_pair_kernel<In, CH, TE, MINB><<<grid, threads, smem, stream>>>(pcm, n_frames, plan, geo, tap_first, tap_w, out,
+    ingest_resample_pair_kernel<In, CH, TE, G><<<grid, threads, smem, stream>>>(pcm, n_frames, plan, geo, tap_first, tap_w, out,
                                                                                    n_real, out_len, n_items, out8);
     return cudaGetLastError();
 }
 
-// The pair kernel applies when the window of two adjacent outputs (alignment slack 3 + pair_shift_max + taps) fits 28
-// floats (44.1 / 48 kHz and every rate below; at 88.2 / 96 kHz, 34-37 taps, the 44-float instantiation needs 158 registers,
-// one block per SM, and measured 0.91x of the one-phase kernel), a block of <= 320 threads holds whole periods of the phase pattern and the stream is mono or stereo on a
-// 16-byte aligned base; SAD_INGEST_PAIR=0 turns it off.
+// The pair kernel applies when a block of <= 320 threads holds whole periods of the phase pattern and the stream is mono
+// or stereo on a 16-byte aligned base.  Two outputs per thread when their window (alignment slack 3 + pair_shift_max +
+// taps) fits 28 floats: 44.1 / 48 kHz and every rate below.  ONE output per thread on a 40-float window for the
+// 34-37-tap rates (88.2 / 96 kHz): two tap sets of 44 would need 158 registers, one block per SM, and measured 0.91x
+// of the one-phase kernel.  SAD_INGEST_PAIR=0 turns it off.
 template <typename In>
 bool try_pair(const In* pcm, long long n_frames, int channels, const ResamplePlan& plan, const int* tap_first, const float* tap_w,
               float* out, long long n_real, long long out_len, cudaStream_t stream, cudaError_t* err) {
     static const bool enabled = [] { const char* v = getenv("SAD_INGEST_PAIR"); return !(v && v[0] == '0'); }();
     if (!enabled || plan.pair_shift_max < 0 || channels > 2 || n_frames < 1 || (reinterpret_cast<uintptr_t>(pcm) & 15) != 0) return false;
-    const int need = 3 + plan.pair_shift_max + plan.max_taps;
-    if (need > 28) return false;
-    const int TE = need <= 20 ? 20 : need <= 24 ? 24 : 28;
-    const int period = plan.new_f % 2 == 0 ? plan.new_f / 2 : plan.new_f;   // threads per period of the phase pattern
+    int G = 2, need = 3 + plan.pair_shift_max + plan.max_taps;
+    if (need > 28) {
+        G = 1;
+        need = 3 + plan.max_taps;
+        if (need > 40) return false;
+    }
+    const int TE = G == 1 ? 40 : need <= 20 ? 20 : need <= 24 ? 24 : 28;
+    const int period = G == 2 && plan.new_f % 2 == 0 ? plan.new_f / 2 : plan.new_f;   // threads per period of the phase pattern
     if (period > kPairThreads) return false;
     const int threads = kPairThreads / period * period;
     if (threads < 128) return false;
     int dev = 0, sms = 0;
     if ((*err = cudaGetDevice(&dev)) != cudaSuccess || (*err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
         return true;
-    constexpr int min_blocks = 2;
     const int fpc = 16 / (static_cast<int>(sizeof(In)) * channels);
-    const int frames_round = 2 * threads / plan.new_f;
+    const int frames_round = G * threads / plan.new_f;
     PairGeometry geo{};
     geo.round_stride = frames_round * plan.orig_f;
     const int need_round = (frames_round - 1) * plan.orig_f + plan.first_spread + TE;   // frames a round's windows reach over
@@ -461,18 +464,20 @@ bool try_pair(const In* pcm, long long n_frames, int channels, const ResamplePla
     int rounds = 16;
     while (rounds >= 1 && size_for(rounds) > budget) rounds >>= 1;
     // short streams: smaller items, so that every resident block gets a few
-    while (rounds > 1 && (out_len + 2LL * threads * rounds - 1) / (2LL * threads * rounds) < 4LL * sms * min_blocks) rounds >>= 1;
+    const long long per_round = static_cast<long long>(G) * threads;
+    while (rounds > 1 && (out_len + per_round * rounds - 1) / (per_round * rounds) < 8LL * sms) rounds >>= 1;
     if (rounds < 1) return false;
     size_for(rounds);
-#define SAD_PAIR_CASE(TE_, MINB_)                                                                                                     \
-    *err = channels == 2 ? launch_pair<In, 2, TE_, MINB_>(pcm, n_frames, plan, geo, tap_first, tap_w, out, n_real, out_len, threads,  \
-                                                          smem, sms, stream)                                                          \
-                         : launch_pair<In, 1, TE_, MINB_>(pcm, n_frames, plan, geo, tap_first, tap_w, out, n_real, out_len, threads,  \
-                                                          smem, sms, stream)
+#define SAD_PAIR_CASE(TE_, G_)                                                                                                     \
+    *err = channels == 2 ? launch_pair<In, 2, TE_, G_>(pcm, n_frames, plan, geo, tap_first, tap_w, out, n_real, out_len, threads,  \
+                                                       smem, sms, stream)                                                          \
+                         : launch_pair<In, 1, TE_, G_>(pcm, n_frames, plan, geo, tap_first, tap_w, out, n_real, out_len, threads,  \
+                                                       smem, sms, stream)
     switch (TE) {
         case 20: SAD_PAIR_CASE(20, 2); break;
         case 24: SAD_PAIR_CASE(24, 2); break;
-        default: SAD_PAIR_CASE(28, 2); break;
+        case 28: SAD_PAIR_CASE(28, 2); break;
+        default: SAD_PAIR_CASE(40, 1); break;
     }
 #undef SAD_PAIR_CASE
     return true;

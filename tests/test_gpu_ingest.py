@@ -121,6 +121,14 @@ for sr, ch, frames, fmt, odd in %r:
         x = buf[1:].reshape(frames, ch)
     y = e.ingest(x, sr)
     print(sr, ch, frames, fmt, odd, y.numel(), hashlib.sha256(y.cpu().numpy().tobytes()).hexdigest())
+    if odd == 0 and frames < 200_000:
+        # the C ABI states no alignment for `out` either: an output that starts 4 bytes into an allocation
+        from sad_b200 import _lib
+        from sad_b200.engine import _ptr, _stream
+        buf = torch.full((y.numel() + 1,), float("nan"), device="cuda")
+        _lib.check(e.ctx, e.lib.sad_ingest(e.ctx, _ptr(x), 0 if fmt == "s16" else 1, frames, ch, sr, _ptr(buf[1:]),
+                                           _stream(e.device)), "sad_ingest")
+        assert torch.equal(buf[1:], y), (sr, ch, frames, "unaligned out")
 """
 
 
@@ -137,7 +145,10 @@ def test_pair_kernel_is_bit_identical_to_the_one_phase_kernel():
              (11025, 1, 70_001, "s16", 0), (16000, 1, 66_001, "f32", 0), (8000, 2, 40_003, "s16", 0),
              (24000, 2, 99_999, "s16", 0), (37800, 2, 77_777, "s16", 0), (44100, 2, 3, "s16", 0),
              (96000, 2, 200_001, "s16", 0), (88200, 1, 150_001, "f32", 0), (44100, 2, 9_000_001, "s16", 0),
-             (48000, 1, 5_000_003, "s16", 0), (16000, 2, 3_000_001, "f32", 0)]   # the long ones use full-size items
+             (48000, 1, 5_000_003, "s16", 0), (16000, 2, 3_000_001, "f32", 0),   # the long ones use full-size items
+             (44100, 2, 1, "s16", 0), (44100, 2, 882, "s16", 0), (44100, 1, 883, "s16", 0), (44100, 2, 1763, "f32", 0),
+             (48000, 1, 17, "s16", 0), (48000, 2, 959, "f32", 0), (16000, 2, 639, "s16", 0), (8000, 1, 161, "s16", 0),
+             (22050, 2, 176_401, "f32", 0), (24000, 1, 96_001, "s16", 0)]
     outs = []
     for flag in ("1", "0"):
         env = dict(os.environ, SAD_INGEST_PAIR=flag, PYTHONPATH=root)
