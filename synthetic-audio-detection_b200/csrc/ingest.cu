@@ -217,8 +217,6 @@ __global__ void __launch_bounds__(1024) ingest_resample_phase_kernel(const In* _
 // with the next one written twice, so that a thread's window alignment is the same in every round and item whatever
 // the rate ratio.  Two blocks per SM (<= 102 registers) overlap one block's conversion with the other's filter pass.
 // Mono or stereo streams whose base is 16-byte aligned; everything else keeps the one-phase kernel.
-constexpr int kPairDepth = 2;
-constexpr int kPairThreads = 320;
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -232,14 +230,6 @@ __device__ __forceinline__ float4 ld_shared_f32x4(uint32_t addr) {
 }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-struct PairGeometry {
-    int rounds;          // rounds of 2 * blockDim outputs per item
-    int round_stride;    // input frames between the sub-spans of two rounds
-    int sub_floats;      // floats per sub-span (a multiple of 4): round_stride + overlap, at least
-    int overlap;         // frames of the next round a sub-span also holds
-    int n_chunks;        // 16-byte chunks of raw PCM per item
-};
 
 // One frame of the staged raw PCM (shared address) as a mono float.  Every operation is exact for int16 (a sum of two
 // 16-bit values scaled by a power of two), so this equals mono_mix to the bit; the float mix is the same (a + b) * 0.5f.
@@ -429,51 +419,21 @@ template <typename In>
 bool try_pair(const In* pcm, long long n_frames, int channels, const ResamplePlan& plan, const int* tap_first, const float* tap_w,
               float* out, long long n_real, long long out_len, cudaStream_t stream, cudaError_t* err) {
     static const bool enabled = [] { const char* v = getenv("SAD_INGEST_PAIR"); return !(v && v[0] == '0'); }();
-    if (!enabled || plan.pair_shift_max < 0 || channels > 2 || n_frames < 1 || (reinterpret_cast<uintptr_t>(pcm) & 15) != 0) return false;
-    int G = 2, need = 3 + plan.pair_shift_max + plan.max_taps;
-    if (need > 28) {
-        G = 1;
-        need = 3 + plan.max_taps;
-        if (need > 40) return false;
-    }
-    const int TE = G == 1 ? 40 : need <= 20 ? 20 : need <= 24 ? 24 : 28;
-    const int period = G == 2 && plan.new_f % 2 == 0 ? plan.new_f / 2 : plan.new_f;   // threads per period of the phase pattern
-    if (period > kPairThreads) return false;
-    const int threads = kPairThreads / period * period;
-    if (threads < 128) return false;
+    if (!enabled || channels > 2 || n_frames < 1 || (reinterpret_cast<uintptr_t>(pcm) & 15) != 0) return false;
     int dev = 0, sms = 0;
     if ((*err = cudaGetDevice(&dev)) != cudaSuccess || (*err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
         return true;
-    const int fpc = 16 / (static_cast<int>(sizeof(In)) * channels);
-    const int frames_round = G * threads / plan.new_f;
-    PairGeometry geo{};
-    geo.round_stride = frames_round * plan.orig_f;
-    const int need_round = (frames_round - 1) * plan.orig_f + plan.first_spread + TE;   // frames a round's windows reach over
-    geo.sub_floats = (need_round + 3) / 4 * 4;
-    if (geo.sub_floats < geo.round_stride) geo.sub_floats = (geo.round_stride + 3) / 4 * 4;
-    geo.overlap = geo.sub_floats - geo.round_stride;
-    size_t smem = 0;
-    auto size_for = [&](int r) {
-        geo.rounds = r;
-        const long long need_item = static_cast<long long>(r - 1) * geo.round_stride + geo.sub_floats;
-        geo.n_chunks = static_cast<int>((need_item + fpc - 1 + fpc - 1) / fpc);     // the first chunk may start fpc - 1 frames early
-        smem = static_cast<size_t>(r) * geo.sub_floats * 4 + static_cast<size_t>(kPairDepth) * geo.n_chunks * 16;
-        return smem;
-    };
-    const size_t budget = 100 * 1024;                                // two blocks per SM
-    int rounds = 16;
-    while (rounds >= 1 && size_for(rounds) > budget) rounds >>= 1;
-    // short streams: smaller items, so that every resident block gets a few
-    const long long per_round = static_cast<long long>(G) * threads;
-    while (rounds > 1 && (out_len + per_round * rounds - 1) / (per_round * rounds) < 8LL * sms) rounds >>= 1;
-    if (rounds < 1) return false;
-    size_for(rounds);
+    PairChoice c{};
+    if (!choose_pair_geometry(plan, static_cast<int>(sizeof(In)) * channels, out_len, sms, &c)) return false;
+    const PairGeometry& geo = c.geo;
+    const int threads = c.threads;
+    const size_t smem = c.smem;
 #define SAD_PAIR_CASE(TE_, G_)                                                                                                     \
     *err = channels == 2 ? launch_pair<In, 2, TE_, G_>(pcm, n_frames, plan, geo, tap_first, tap_w, out, n_real, out_len, threads,  \
                                                        smem, sms, stream)                                                          \
                          : launch_pair<In, 1, TE_, G_>(pcm, n_frames, plan, geo, tap_first, tap_w, out, n_real, out_len, threads,  \
                                                        smem, sms, stream)
-    switch (TE) {
+    switch (c.window) {
         case 20: SAD_PAIR_CASE(20, 2); break;
         case 24: SAD_PAIR_CASE(24, 2); break;
         case 28: SAD_PAIR_CASE(28, 2); break;

@@ -1,12 +1,113 @@
 // CPU check of the ingest stage's host arithmetic (there is no GPU in the build container):
 //   ingest_host_check taps <sr_in>      -> "orig new width full max_taps", then per phase: first tap index and the taps
 //   ingest_host_check length <sr_in> <n_frames>...  -> output length and un-padded length per n_frames
-// tests/test_ingest_host.py compares both with the oracle's restatement of torchaudio (bit-exact float32 taps).
+//   ingest_host_check pair <sr_in> <bytes_per_frame> <n_frames> <sms>
+//       -> replays the index walk of the staged (`pair`) resampling kernel of ingest.cu with the geometry the host picks
+//          (choose_pair_geometry): raw chunks of an item -> per-round float sub-spans -> per-thread windows, and checks
+//          that tap k of every output reads exactly the frame torchaudio's kernel reads; prints the geometry and "ok <n>".
+// tests/test_ingest_host.py compares the first two with the oracle's restatement of torchaudio (bit-exact float32 taps)
+// and runs the third over the rate / format / length grid.
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 
 #include "ingest_taps.h"
+
+// Frames are identified by their index in the stream; kOutside marks frames the kernel reads as zero (before the
+// first / after the last) and kUnset marks shared-memory floats nothing was written to.
+static const long long kOutside = -1, kUnset = -2;
+
+static int replay_pair(int sr, int bytes_per_frame, long long n_frames, int sms) {
+    sad::ResamplePlan plan{};
+    std::vector<int> first;
+    std::vector<float> w;
+    if (!sad::build_resample_taps(sr, &plan, &first, &w)) {
+        printf("unsupported\n");
+        return 0;
+    }
+    long long n_real = 0;
+    const long long out_len = sad::ingest_length(n_frames, sr, &n_real);
+    sad::PairChoice c{};
+    if (!sad::choose_pair_geometry(plan, bytes_per_frame, out_len, sms, &c)) {
+        printf("not a pair ratio\n");
+        return 0;
+    }
+    const sad::PairGeometry& g = c.geo;
+    const int G = c.outputs, TE = c.window, nt = c.threads, fpc = 16 / bytes_per_frame;
+    printf("G %d TE %d threads %d rounds %d stride %d sub %d overlap %d chunks %d smem %zu\n", G, TE, nt, g.rounds, g.round_stride,
+           g.sub_floats, g.overlap, g.n_chunks, c.smem);
+    if (G * nt % plan.new_f || g.sub_floats % 4 || g.overlap != g.sub_floats - g.round_stride || c.smem > 113 * 1024) {
+        printf("bad geometry\n");
+        return 1;
+    }
+    const long long per_item = static_cast<long long>(G) * nt * g.rounds;
+    const long long n_items = (out_len + per_item - 1) / per_item;
+    const long long frames_item = static_cast<long long>(g.round_stride) * g.rounds;
+    std::vector<long long> raw(static_cast<size_t>(g.n_chunks) * fpc), span(static_cast<size_t>(g.rounds) * g.sub_floats);
+    long long checked = 0;
+    for (long long item = 0; item < n_items; ++item) {
+        const long long ff = item * frames_item + plan.first0 - plan.width;       // first frame of the item
+        const long long a_lo = ff & ~static_cast<long long>(fpc - 1);
+        const int skip = static_cast<int>(ff & (fpc - 1));
+        for (int i = 0; i < g.n_chunks; ++i)                                       // issue(): 16-byte chunks, zero-filled outside
+            for (int e = 0; e < fpc; ++e) {
+                const long long f = a_lo + static_cast<long long>(fpc) * i + e;
+                raw[static_cast<size_t>(i) * fpc + e] = (f >= 0 && f < n_frames) ? f : kOutside;
+            }
+        std::fill(span.begin(), span.end(), kUnset);
+        for (int k = 0; k < g.sub_floats; ++k)                                     // conversion pass
+            for (int i = 0; i < g.rounds; ++i) {
+                const size_t src = static_cast<size_t>(skip) + static_cast<size_t>(i) * g.round_stride + k;
+                if (src >= raw.size()) {
+                    printf("conversion reads past the staged chunks (item %lld round %d k %d)\n", item, i, k);
+                    return 1;
+                }
+                span[static_cast<size_t>(i) * g.sub_floats + k] = raw[src];
+            }
+        for (int t = 0; t < nt; ++t) {                                             // filter pass
+            int pos[2], ph[2];
+            for (int q = 0; q < G; ++q) {
+                const int m = (G * t + q) / plan.new_f;
+                ph[q] = (G * t + q) - m * plan.new_f;
+                pos[q] = m * plan.orig_f + first[ph[q]] - plan.first0;
+            }
+            const int base = pos[0] & ~3;
+            if (base + TE > g.sub_floats) {
+                printf("window of thread %d leaves its sub-span\n", t);
+                return 1;
+            }
+            for (int q = 0; q < G; ++q) {
+                const int sh = pos[q] - base;
+                if (sh < 0 || sh + plan.max_taps > TE) {
+                    printf("taps of thread %d output %d do not fit the window (shift %d)\n", t, q, sh);
+                    return 1;
+                }
+                for (int i = 0; i < g.rounds; ++i) {
+                    const long long j = item * per_item + static_cast<long long>(G) * nt * i + G * t + q;
+                    if (j >= n_real) continue;                                      // written as zero padding
+                    const long long m = j / plan.new_f;
+                    for (int k = 0; k < plan.max_taps; ++k) {
+                        const long long want = m * plan.orig_f + first[ph[q]] + k - plan.width;   // torchaudio's xpad index - width
+                        const long long got = span[static_cast<size_t>(i) * g.sub_floats + base + sh + k];
+                        const long long expect = (want >= 0 && want < n_frames) ? want : kOutside;
+                        if (got != expect) {
+                            printf("output %lld tap %d reads frame %lld, wants %lld\n", j, k, got, expect);
+                            return 1;
+                        }
+                    }
+                    ++checked;
+                }
+            }
+        }
+    }
+    if (checked != n_real) {
+        printf("covered %lld of %lld outputs\n", checked, n_real);
+        return 1;
+    }
+    printf("ok %lld\n", checked);
+    return 0;
+}
 
 int main(int argc, char** argv) {
     if (argc >= 3 && !strcmp(argv[1], "taps")) {
@@ -38,6 +139,7 @@ int main(int argc, char** argv) {
         }
         return 0;
     }
-    fprintf(stderr, "usage: ingest_host_check taps <sr> | length <sr> <frames>...\n");
+    if (argc >= 6 && !strcmp(argv[1], "pair")) return replay_pair(atoi(argv[2]), atoi(argv[3]), atoll(argv[4]), atoi(argv[5]));
+    fprintf(stderr, "usage: ingest_host_check taps <sr> | length <sr> <frames>... | pair <sr> <bytes_per_frame> <frames> <sms>\n");
     return 2;
 }

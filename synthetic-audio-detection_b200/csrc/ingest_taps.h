@@ -105,4 +105,72 @@ inline bool build_resample_taps(int sr_in, ResamplePlan* plan, std::vector<int>*
     return true;
 }
 
+// ---- geometry of the staged (`pair`) resampling kernel of ingest.cu, chosen on the host -----------------------------------
+// Kept here, free of CUDA, so that csrc/ingest_host_check.cpp can replay the kernel's index walk on the CPU.
+constexpr int kPairDepth = 2;        // slots of the raw-PCM ring in shared memory
+constexpr int kPairThreads = 320;    // largest block
+
+struct PairGeometry {
+    int rounds;          // rounds of G * blockDim outputs per item
+    int round_stride;    // input frames between the sub-spans of two rounds
+    int sub_floats;      // floats per sub-span (a multiple of 4): round_stride + overlap, at least
+    int overlap;         // frames of the next round a sub-span also holds
+    int n_chunks;        // 16-byte chunks of raw PCM per item
+};
+
+struct PairChoice {
+    int outputs;         // G: adjacent outputs per thread (2, or 1 for the 34-37-tap rates)
+    int window;          // TE: floats of the per-thread window (20, 24, 28 or 40)
+    int threads;         // block size: whole periods of the phase pattern
+    PairGeometry geo;
+    size_t smem;         // dynamic shared memory per block
+};
+
+// False when the ratio does not fit the kernel (band starts not monotone, window > 40 floats, phase period > 320 threads).
+// bytes_per_frame: 2, 4 or 8 (mono / stereo, int16 / float32).
+inline bool choose_pair_geometry(const ResamplePlan& plan, int bytes_per_frame, long long out_len, int sms, PairChoice* c) {
+    if (plan.pair_shift_max < 0) return false;
+    int G = 2, need = 3 + plan.pair_shift_max + plan.max_taps;     // alignment slack of a 16-byte window + the pair's shift + taps
+    if (need > 28) {
+        G = 1;
+        need = 3 + plan.max_taps;
+        if (need > 40) return false;
+    }
+    const int TE = G == 1 ? 40 : need <= 20 ? 20 : need <= 24 ? 24 : 28;
+    const int period = G == 2 && plan.new_f % 2 == 0 ? plan.new_f / 2 : plan.new_f;   // threads per period of the phase pattern
+    if (period > kPairThreads) return false;
+    const int threads = kPairThreads / period * period;
+    if (threads < 128) return false;
+    const int fpc = 16 / bytes_per_frame;
+    const int frames_round = G * threads / plan.new_f;
+    PairGeometry geo{};
+    geo.round_stride = frames_round * plan.orig_f;
+    const int need_round = (frames_round - 1) * plan.orig_f + plan.first_spread + TE;   // frames a round's windows reach over
+    geo.sub_floats = (need_round + 3) / 4 * 4;
+    if (geo.sub_floats < geo.round_stride) geo.sub_floats = (geo.round_stride + 3) / 4 * 4;
+    geo.overlap = geo.sub_floats - geo.round_stride;
+    size_t smem = 0;
+    auto size_for = [&](int r) {
+        geo.rounds = r;
+        const long long need_item = static_cast<long long>(r - 1) * geo.round_stride + geo.sub_floats;
+        geo.n_chunks = static_cast<int>((need_item + fpc - 1 + fpc - 1) / fpc);     // the first chunk may start fpc - 1 frames early
+        smem = static_cast<size_t>(r) * geo.sub_floats * 4 + static_cast<size_t>(kPairDepth) * geo.n_chunks * 16;
+        return smem;
+    };
+    const size_t budget = 100 * 1024;                                // two blocks per SM
+    int rounds = 16;
+    while (rounds >= 1 && size_for(rounds) > budget) rounds >>= 1;
+    // short streams: smaller items, so that every resident block gets a few
+    const long long per_round = static_cast<long long>(G) * threads;
+    while (rounds > 1 && (out_len + per_round * rounds - 1) / (per_round * rounds) < 8LL * sms) rounds >>= 1;
+    if (rounds < 1) return false;
+    size_for(rounds);
+    c->outputs = G;
+    c->window = TE;
+    c->threads = threads;
+    c->geo = geo;
+    c->smem = smem;
+    return true;
+}
+
 }  // namespace sad

@@ -56,3 +56,34 @@ def test_output_length_is_torchaudios_float32_ceil(checker):
             want = n if sr == 32000 else int(torch.ceil(torch.as_tensor(new * n / orig)).long())
             assert n_real == want == (n if sr == 32000 else R.resample_length(n, orig, new)), (sr, n)
             assert total == max(want, 128000)
+
+
+PAIR_GRID = [(44100, 4, 300_000, 148), (44100, 4, 9_000_001, 148), (44100, 2, 70_001, 148), (44100, 8, 1_000_003, 132),
+             (48000, 2, 100_001, 148), (48000, 4, 6_000_000, 148), (22050, 8, 70_001, 148), (22050, 4, 4_000_001, 148),
+             (16000, 8, 5_000_000, 148), (16000, 2, 639, 148), (8000, 2, 4_001, 148), (8000, 4, 2_000_000, 148),
+             (24000, 4, 96_001, 148), (12000, 4, 50_000, 148), (25600, 4, 123_457, 148), (37800, 4, 77_777, 148),
+             (47250, 4, 500_001, 148), (64000, 4, 300_001, 148), (88200, 2, 150_001, 148), (96000, 4, 500_000, 148),
+             (96000, 8, 9_000_000, 148), (44100, 4, 1, 148), (44100, 4, 882, 148), (44100, 4, 883, 1)]
+
+
+@pytest.mark.parametrize("sr,bytes_per_frame,frames,sms", PAIR_GRID)
+def test_pair_kernel_geometry_reads_the_right_frames(checker, sr, bytes_per_frame, frames, sms):
+    """The staged (`pair`) resampler of csrc/ingest.cu, replayed on the CPU with the geometry its host side picks
+    (ingest_taps.h choose_pair_geometry): raw 16-byte chunks of an item -> per-round float sub-spans -> per-thread
+    16-byte windows.  Every tap of every output must land on the input frame torchaudio's dense kernel pairs it with,
+    frames outside the stream must read as zero, and every output below the un-padded length must be produced once."""
+    r = subprocess.run([checker, "pair", str(sr), str(bytes_per_frame), str(frames), str(sms)], capture_output=True, text=True)
+    lines = r.stdout.strip().split("\n")
+    assert r.returncode == 0, r.stdout[-500:]
+    geo = dict(zip(lines[0].split()[::2], map(int, lines[0].split()[1::2])))
+    assert geo["G"] == (1 if sr in (88200, 96000, 64000) else 2)
+    assert geo["threads"] % 32 == 0 or sr == 25600                 # 5 phases: 320 threads anyway
+    assert geo["smem"] <= 100 * 1024                                 # two blocks per SM
+    n_real = -(-32000 * frames // sr)                                # ceil; the float32 rounding of torchaudio matters only
+    assert lines[1].startswith("ok ") and abs(int(lines[1].split()[1]) - n_real) <= 1   # above 2^24 samples
+
+
+@pytest.mark.parametrize("sr", [11025, 192000, 12345])
+def test_ratios_the_pair_kernel_leaves_to_the_one_phase_kernel(checker, sr):
+    out = subprocess.run([checker, "pair", str(sr), "4", "100000", "148"], capture_output=True, text=True, check=True).stdout
+    assert out.strip() in ("not a pair ratio", "unsupported")
