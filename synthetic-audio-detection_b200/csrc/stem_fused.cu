@@ -25,6 +25,8 @@
 // Work unit = (image, head pair, strip of 32 pooled rows); persistent CTAs, round-robin.
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "conv_umma.h"
 #include "ptx.cuh"
 #include "stem_fused.h"
@@ -61,6 +63,15 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {   // FMNMX3:
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
+
+// Pixel x of a conv row sits in row pix_row(x) of the pixel tile (= TMEM column pix_row(x) of the accumulator): inside
+// every block of 16 pixels the 8 even ones come first, then the 8 odd ones.  A builder thread writes the two pixels
+// 2i and 2i+1; with pixel x in row x the eight lanes of a quarter warp hit rows 0, 2, 4, .. 14 -- only four distinct
+// values of (row & 7), i.e. four distinct 16-byte columns of the 128-byte swizzle: every tile store was a 2-way bank
+// conflict (ncu, round 2: 26 M of the kernel's 34 M conflict wavefronts).  De-interleaved, the quarter warp's even
+// pixels land in rows 16b .. 16b+7 and its odd ones in 16b+8 .. 16b+15: eight distinct columns, no conflict.  The
+// epilogue reads accumulator columns by compile-time index, so the permutation costs it nothing.
+__host__ __device__ constexpr int pix_row(int x) { return (x & ~15) | ((x & 1) << 3) | ((x & 15) >> 1); }
 
 __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_constant__ StemLaunch p) {
     extern __shared__ uint8_t smem_raw[];
@@ -157,8 +168,8 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
         uint32_t off_e[7], off_o[7];                    // swizzled chunk offsets of this thread's two pixel rows
 #pragma unroll
         for (int ky = 0; ky < 7; ++ky) {
-            off_e[ky] = smem_u32(p_sm) + sw128_offset(2 * i, ky);
-            off_o[ky] = smem_u32(p_sm) + sw128_offset(2 * i + 1, ky);
+            off_e[ky] = smem_u32(p_sm) + sw128_offset(pix_row(2 * i), ky);
+            off_o[ky] = smem_u32(p_sm) + sw128_offset(pix_row(2 * i + 1), ky);
         }
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
             const int r0 = u % units_per_group;
@@ -170,7 +181,11 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
             // loaded -- one conv row AHEAD, so their L2 latency hides behind this row's buffer wait and stores
             // (ncu, round 2: the UMMA thread spent its time waiting for the builders, and the builders 45% of theirs
             // on the first use of freshly loaded pixels).
-            uint4 ce[7], co[7];                           // even pixel x = 2i / odd pixel x = 2i+1, per ky
+            // ce / co are ROTATING files of seven registers: chunk ky of conv row t lives in slot (ky + 2t) % 7, so the two
+            // new image rows of row t overwrite the slots rows 0 and 1 of row t-1 left and nothing is moved -- the loop over
+            // rows is unrolled by seven with the slot numbers as compile-time constants (ncu, round 2: the version that
+            // shifted the arrays down by two per row executed 208 register moves of its 322 instructions per row).
+            uint4 ce[7], co[7];                           // even pixel x = 2i / odd pixel x = 2i+1
             uint32_t nw[2][6];                            // raw words of the next row's two new image rows
             auto load_row = [&](int iy, uint32_t (&w)[6]) {
                 uint2 q0 = make_uint2(0u, 0u), q1 = q0, q2 = q0;
@@ -190,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                 o = make_uint4(__funnelshift_r(w[1], w[2], 16), __funnelshift_r(w[2], w[3], 16),
                                __funnelshift_r(w[3], w[4], 16), __funnelshift_r(w[4], w[5], 16));
             };
-            {   // first conv row of the unit: all seven image rows
+            {   // first conv row of the unit: all seven image rows (slot ky = chunk ky)
                 const int r = 2 * py0 - 1;
 #pragma unroll
                 for (int ky = 0; ky < 7; ++ky) {
@@ -201,17 +216,14 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                 load_row(2 * (r + 1) + 2, nw[0]);
                 load_row(2 * (r + 1) + 3, nw[1]);
             }
-            for (int t = 0; t < kConvRowsPerUnit; ++t, ++arow) {
+            // one conv row; U = t % 7 fixes the slot of every chunk at compile time
+            auto conv_row = [&](auto uc, int t) {
+                constexpr int U = decltype(uc)::value;
                 const int b = arow & 1;
                 const int r = 2 * py0 - 1 + t;            // conv output row (may be -1: result is ignored)
                 if (t > 0) {
-#pragma unroll
-                    for (int ky = 0; ky < 5; ++ky) {
-                        ce[ky] = ce[ky + 2];
-                        co[ky] = co[ky + 2];
-                    }
-                    shift_row(nw[0], ce[5], co[5]);
-                    shift_row(nw[1], ce[6], co[6]);
+                    shift_row(nw[0], ce[(5 + 2 * U) % 7], co[(5 + 2 * U) % 7]);
+                    shift_row(nw[1], ce[(6 + 2 * U) % 7], co[(6 + 2 * U) % 7]);
                     if (t + 1 < kConvRowsPerUnit) {       // prefetch for row r+1: image rows 2(r+1)+2, 2(r+1)+3
                         load_row(2 * (r + 1) + 2, nw[0]);
                         load_row(2 * (r + 1) + 3, nw[1]);
@@ -221,11 +233,23 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                 const uint32_t tile = b * kPixTile;
 #pragma unroll
                 for (int ky = 0; ky < 7; ++ky) {
-                    st_shared_v4(off_e[ky] + tile, ce[ky].x, ce[ky].y, ce[ky].z, ce[ky].w);
-                    st_shared_v4(off_o[ky] + tile, co[ky].x, co[ky].y, co[ky].z, co[ky].w);
+                    const uint4& e = ce[(ky + 2 * U) % 7];
+                    const uint4& o = co[(ky + 2 * U) % 7];
+                    st_shared_v4(off_e[ky] + tile, e.x, e.y, e.z, e.w);
+                    st_shared_v4(off_o[ky] + tile, o.x, o.y, o.z, o.w);
                 }
                 fence_proxy_async();
                 mbar_arrive(&p_full[b]);
+                ++arow;
+            };
+            for (int t = 0; t < kConvRowsPerUnit; t += 7) {
+                conv_row(std::integral_constant<int, 0>{}, t);
+                if (t + 1 < kConvRowsPerUnit) conv_row(std::integral_constant<int, 1>{}, t + 1);
+                if (t + 2 < kConvRowsPerUnit) conv_row(std::integral_constant<int, 2>{}, t + 2);
+                if (t + 3 < kConvRowsPerUnit) conv_row(std::integral_constant<int, 3>{}, t + 3);
+                if (t + 4 < kConvRowsPerUnit) conv_row(std::integral_constant<int, 4>{}, t + 4);
+                if (t + 5 < kConvRowsPerUnit) conv_row(std::integral_constant<int, 5>{}, t + 5);
+                if (t + 6 < kConvRowsPerUnit) conv_row(std::integral_constant<int, 6>{}, t + 6);
             }
         }
     } else {
@@ -284,8 +308,8 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fused_kernel(const __grid_co
                     uint32_t hb[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float a0 = __uint_as_float(v[4 * j]), a1 = __uint_as_float(v[4 * j + 1]);
-                        const float a2 = __uint_as_float(v[4 * j + 2]), a3 = __uint_as_float(v[4 * j + 3]);
+                        const float a0 = __uint_as_float(v[pix_row(4 * j)]), a1 = __uint_as_float(v[pix_row(4 * j + 1)]);
+                        const float a2 = __uint_as_float(v[pix_row(4 * j + 2)]), a3 = __uint_as_float(v[pix_row(4 * j + 3)]);
                         const float h0 = fmax3(prev, a0, a1);             // pooled px 2j   : conv 2p-1, 2p, 2p+1
                         const float h1 = fmax3(a1, a2, a3);               // pooled px 2j+1
                         prev = a3;
