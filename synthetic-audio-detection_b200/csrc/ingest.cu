@@ -13,8 +13,8 @@
 //   `pair` kernel (every rate up to 96 kHz; mono or stereo on a 16-byte aligned base): persistent blocks, the
 //   raw PCM of the next item staged by cp.async while the current one is filtered, two adjacent outputs per thread
 //   on one window of 16-byte shared loads with the taps in registers.  Measured (B200, 25 min of stereo int16,
-//   tools/ingest_bench.py): 3.6 TB/s at 44.1 and 48 kHz (55 % of the measured HBM copy bandwidth), 3.2-3.9 TB/s at
-//   8-24 kHz, 2.3-2.4 TB/s at 88.2 / 96 kHz (one output per thread there).  ncu on the way there: the first cut was instruction-issue bound (73 % issue slots, 131 instructions per
+//   tools/ingest_bench.py): 3.8-3.9 TB/s at 44.1 and 48 kHz (58-60 % of the measured HBM copy bandwidth), 3.1-3.9 TB/s at
+//   8-24 kHz, 2.4-2.5 TB/s at 88.2 / 96 kHz (one output per thread there).  ncu on the way there: the first cut was instruction-issue bound (73 % issue slots, 131 instructions per
 //   output against 24 useful FMAs: a conversion pass with a division and two guarded stores per frame, 64-bit index
 //   arithmetic per round, the shared base address rebuilt from S2R at every use); the version below executes ~45.
 //   `phase` kernel (other channel counts, unaligned streams, 192 kHz): a block owns blockDim * R consecutive outputs,
@@ -254,6 +254,33 @@ __device__ __forceinline__ float raw_frame_to_mono(uint32_t addr) {
     }
 }
 
+// Two consecutive frames (the first one at an even index: 2 * frame-size aligned) -> two mono floats, same arithmetic.
+template <typename In, int CH>
+__device__ __forceinline__ float2 raw_two_frames_to_mono(uint32_t addr) {
+    if constexpr (sizeof(In) == 4 && CH == 2) {
+        float a, b, c, d;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
+        return make_float2((a + b) * 0.5f, (c + d) * 0.5f);
+    } else if constexpr (sizeof(In) == 4) {
+        float a, b;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(a), "=f"(b) : "r"(addr));
+        return make_float2(a, b);
+    } else if constexpr (CH == 2) {
+        int v, w;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];\n" : "=r"(v), "=r"(w) : "r"(addr));
+        return make_float2(static_cast<float>(__dp2a_lo(v, 0x0101, 0)) * (0.5f / 32768.0f),
+                           static_cast<float>(__dp2a_lo(w, 0x0101, 0)) * (0.5f / 32768.0f));
+    } else {
+        int v;
+        asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(v) : "r"(addr));
+        return make_float2(static_cast<float>(static_cast<short>(v & 0xFFFF)) * (1.0f / 32768.0f),
+                           static_cast<float>(v >> 16) * (1.0f / 32768.0f));
+    }
+}
+__device__ __forceinline__ void st_shared_f32x2(uint32_t addr, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};\n" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+
 template <typename In, int CH, int TE, int G>
 __global__ void __launch_bounds__(kPairThreads, 2) ingest_resample_pair_kernel(const In* __restrict__ pcm, long long n_frames,
                                                                                    ResamplePlan plan, PairGeometry geo,
@@ -278,7 +305,7 @@ __global__ void __launch_bounds__(kPairThreads, 2) ingest_resample_pair_kernel(c
 
     // first input frame of this block's n-th item; consecutive items of the block are ff_step frames apart
     const long long ff_step = frames_item * gridDim.x;
-    const long long ff0 = frames_item * blockIdx.x + plan.first0 - plan.width;
+    const long long ff0 = frames_item * blockIdx.x + plan.first0 - plan.width - geo.lead;
     auto issue = [&](long long ff, int slot) {                       // raw chunks of the item that starts at frame ff -> ring slot
         const long long a_lo = ff & ~static_cast<long long>(fpc - 1);
         const uint32_t dst = raw_addr + static_cast<uint32_t>(slot * geo.n_chunks) * 16u;
@@ -306,7 +333,7 @@ __global__ void __launch_bounds__(kPairThreads, 2) ingest_resample_pair_kernel(c
     for (int g = 0; g < G; ++g) {
         const int m = (G * t + g) / plan.new_f;
         ph[g] = (G * t + g) - m * plan.new_f;
-        pos[g] = m * plan.orig_f + tap_first[ph[g]] - plan.first0;
+        pos[g] = geo.lead + m * plan.orig_f + tap_first[ph[g]] - plan.first0;
     }
     const int base = pos[0] & ~3;
     float W[G][TE];
@@ -336,22 +363,44 @@ __global__ void __launch_bounds__(kPairThreads, 2) ingest_resample_pair_kernel(c
             const int skip = static_cast<int>(ff & static_cast<long long>(fpc - 1));
             const uint32_t src0 = raw_addr + static_cast<uint32_t>(slot * geo.n_chunks) * 16u + static_cast<uint32_t>(skip) * bpf;
             const uint32_t src_step = static_cast<uint32_t>(geo.round_stride) * bpf, dst_step = static_cast<uint32_t>(geo.sub_floats) * 4u;
-            for (int k = t; k < geo.sub_floats; k += nt) {
-                uint32_t src = src0 + static_cast<uint32_t>(k) * bpf, dst = span_addr + static_cast<uint32_t>(k) * 4u;
-                int i = 0;
-                for (; i + 4 <= geo.rounds; i += 4) {               // four loads in flight, then four stores
-                    float v[4];
+            if (geo.two) {
+                // even stride, even first frame: two frames per step on 8-byte (two-frame) accesses
+                for (int k = 2 * t; k < geo.sub_floats; k += 2 * nt) {
+                    uint32_t src = src0 + static_cast<uint32_t>(k) * bpf, dst = span_addr + static_cast<uint32_t>(k) * 4u;
+                    int i = 0;
+                    for (; i + 4 <= geo.rounds; i += 4) {           // four loads in flight, then four stores
+                        float2 v[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) v[u] = raw_frame_to_mono<In, CH>(src + static_cast<uint32_t>(u) * src_step);
+                        for (int u = 0; u < 4; ++u) v[u] = raw_two_frames_to_mono<In, CH>(src + static_cast<uint32_t>(u) * src_step);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) st_shared_f32(dst + static_cast<uint32_t>(u) * dst_step, v[u]);
-                    src += 4u * src_step;
-                    dst += 4u * dst_step;
+                        for (int u = 0; u < 4; ++u) st_shared_f32x2(dst + static_cast<uint32_t>(u) * dst_step, v[u]);
+                        src += 4u * src_step;
+                        dst += 4u * dst_step;
+                    }
+                    for (; i < geo.rounds; ++i) {
+                        st_shared_f32x2(dst, raw_two_frames_to_mono<In, CH>(src));
+                        src += src_step;
+                        dst += dst_step;
+                    }
                 }
-                for (; i < geo.rounds; ++i) {
-                    st_shared_f32(dst, raw_frame_to_mono<In, CH>(src));
-                    src += src_step;
-                    dst += dst_step;
+            } else {
+                for (int k = t; k < geo.sub_floats; k += nt) {
+                    uint32_t src = src0 + static_cast<uint32_t>(k) * bpf, dst = span_addr + static_cast<uint32_t>(k) * 4u;
+                    int i = 0;
+                    for (; i + 4 <= geo.rounds; i += 4) {
+                        float v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) v[u] = raw_frame_to_mono<In, CH>(src + static_cast<uint32_t>(u) * src_step);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) st_shared_f32(dst + static_cast<uint32_t>(u) * dst_step, v[u]);
+                        src += 4u * src_step;
+                        dst += 4u * dst_step;
+                    }
+                    for (; i < geo.rounds; ++i) {
+                        st_shared_f32(dst, raw_frame_to_mono<In, CH>(src));
+                        src += src_step;
+                        dst += dst_step;
+                    }
                 }
             }
         }

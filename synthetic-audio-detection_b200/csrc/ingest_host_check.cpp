@@ -18,6 +18,8 @@
 // first / after the last) and kUnset marks shared-memory floats nothing was written to.
 static const long long kOutside = -1, kUnset = -2;
 
+static int skip_of(long long ff, int fpc) { return static_cast<int>(ff & (fpc - 1)); }
+
 static int replay_pair(int sr, int bytes_per_frame, long long n_frames, int sms) {
     sad::ResamplePlan plan{};
     std::vector<int> first;
@@ -35,8 +37,8 @@ static int replay_pair(int sr, int bytes_per_frame, long long n_frames, int sms)
     }
     const sad::PairGeometry& g = c.geo;
     const int G = c.outputs, TE = c.window, nt = c.threads, fpc = 16 / bytes_per_frame;
-    printf("G %d TE %d threads %d rounds %d stride %d sub %d overlap %d chunks %d smem %zu\n", G, TE, nt, g.rounds, g.round_stride,
-           g.sub_floats, g.overlap, g.n_chunks, c.smem);
+    printf("G %d TE %d threads %d rounds %d stride %d sub %d overlap %d chunks %d smem %zu two %d lead %d\n", G, TE, nt, g.rounds,
+           g.round_stride, g.sub_floats, g.overlap, g.n_chunks, c.smem, g.two, g.lead);
     if (G * nt % plan.new_f || g.sub_floats % 4 || g.overlap != g.sub_floats - g.round_stride || c.smem > 113 * 1024) {
         printf("bad geometry\n");
         return 1;
@@ -47,7 +49,11 @@ static int replay_pair(int sr, int bytes_per_frame, long long n_frames, int sms)
     std::vector<long long> raw(static_cast<size_t>(g.n_chunks) * fpc), span(static_cast<size_t>(g.rounds) * g.sub_floats);
     long long checked = 0;
     for (long long item = 0; item < n_items; ++item) {
-        const long long ff = item * frames_item + plan.first0 - plan.width;       // first frame of the item
+        const long long ff = item * frames_item + plan.first0 - plan.width - g.lead;   // first frame staged for the item
+        if (g.two && ((ff & 1) || (g.round_stride & 1) || (skip_of(ff, fpc) & 1))) {
+            printf("two-frame conversion on an odd frame (item %lld)\n", item);
+            return 1;
+        }
         const long long a_lo = ff & ~static_cast<long long>(fpc - 1);
         const int skip = static_cast<int>(ff & (fpc - 1));
         for (int i = 0; i < g.n_chunks; ++i)                                       // issue(): 16-byte chunks, zero-filled outside
@@ -70,7 +76,7 @@ static int replay_pair(int sr, int bytes_per_frame, long long n_frames, int sms)
             for (int q = 0; q < G; ++q) {
                 const int m = (G * t + q) / plan.new_f;
                 ph[q] = (G * t + q) - m * plan.new_f;
-                pos[q] = m * plan.orig_f + first[ph[q]] - plan.first0;
+                pos[q] = g.lead + m * plan.orig_f + first[ph[q]] - plan.first0;
             }
             const int base = pos[0] & ~3;
             if (base + TE > g.sub_floats) {

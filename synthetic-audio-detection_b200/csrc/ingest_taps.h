@@ -116,6 +116,8 @@ struct PairGeometry {
     int sub_floats;      // floats per sub-span (a multiple of 4): round_stride + overlap, at least
     int overlap;         // frames of the next round a sub-span also holds
     int n_chunks;        // 16-byte chunks of raw PCM per item
+    int two;             // 1: round_stride is even, the conversion pass handles two frames per step (8-byte accesses)
+    int lead;            // 0 / 1 extra frame staged in front of every item so that its first frame has an even index
 };
 
 struct PairChoice {
@@ -145,7 +147,11 @@ inline bool choose_pair_geometry(const ResamplePlan& plan, int bytes_per_frame, 
     const int frames_round = G * threads / plan.new_f;
     PairGeometry geo{};
     geo.round_stride = frames_round * plan.orig_f;
-    const int need_round = (frames_round - 1) * plan.orig_f + plan.first_spread + TE;   // frames a round's windows reach over
+    // items start round_stride * rounds frames apart: with an even stride the parity of an item's first frame is that of
+    // first0 - width for every item, and one leading frame makes it even
+    geo.two = geo.round_stride % 2 == 0;
+    geo.lead = geo.two ? ((plan.first0 - plan.width) % 2 + 2) % 2 : 0;
+    const int need_round = geo.lead + (frames_round - 1) * plan.orig_f + plan.first_spread + TE;   // frames a round's windows reach over
     geo.sub_floats = (need_round + 3) / 4 * 4;
     if (geo.sub_floats < geo.round_stride) geo.sub_floats = (geo.round_stride + 3) / 4 * 4;
     geo.overlap = geo.sub_floats - geo.round_stride;
