@@ -97,7 +97,11 @@ int sad_frontend_image(sad_ctx* ctx, const float* pcm_dev, int B, float* image_d
  * Interleaved PCM [n_frames][n_channels] on the device -> mono (mean over channels, int16 scaled by 1/32768 as
  * torchaudio.load does) -> torchaudio.transforms.Resample(sr_in, 32000) (sinc_interp_hann, width 6, rolloff 0.99; skipped
  * when sr_in == 32000) -> zero-padded to at least one window (128000).  sad_ingest_length gives the output length
- * (torchaudio's float32 ceil rule); `out_dev` must hold that many floats.  Device -> device, ordered on `stream`. */
+ * (torchaudio's float32 ceil rule); `out_dev` must hold that many floats.  Device -> device, ordered on `stream`.
+ * No alignment is required of `pcm_dev` or `out_dev` (mono / stereo streams on a 16-byte aligned base take the faster
+ * kernel; results are the same to the bit).  Only the taps where torchaudio's window is not clamped are summed (the
+ * others are below 1e-32), so a non-finite float32 sample reaches the ~20 outputs whose band covers it, where the
+ * reference's dense kernel spreads it over its whole 2*width+orig tap window.                                        */
 #define SAD_PCM_S16 0
 #define SAD_PCM_F32 1
 long long sad_ingest_length(long long n_frames, int sr_in);
