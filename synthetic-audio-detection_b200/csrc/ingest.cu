@@ -462,8 +462,8 @@ cudaError_t launch_pair(const In* pcm, long long n_frames, const ResamplePlan& p
 // The pair kernel applies when a block of <= 320 threads holds whole periods of the phase pattern and the stream is mono
 // or stereo on a 16-byte aligned base.  Two outputs per thread when their window (alignment slack 3 + pair_shift_max +
 // taps) fits 28 floats: 44.1 / 48 kHz and every rate below.  ONE output per thread on a 40-float window for the
-// 34-37-tap rates (88.2 / 96 kHz): two tap sets of 44 would need 158 registers, one block per SM, and measured 0.91x
-// of the one-phase kernel.  SAD_INGEST_PAIR=0 turns it off.
+// 34-37-tap rates (88.2 / 96 kHz): two tap sets of 44 need 158 registers, one block per SM, and measured 0.81x of
+// the one-output instantiation (2.06 against 2.54 TB/s at 96 kHz): occupancy carries the kernel.  SAD_INGEST_PAIR=0 turns it off.
 template <typename In>
 bool try_pair(const In* pcm, long long n_frames, int channels, const ResamplePlan& plan, const int* tap_first, const float* tap_w,
               float* out, long long n_real, long long out_len, cudaStream_t stream, cudaError_t* err) {
