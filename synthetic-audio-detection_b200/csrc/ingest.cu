@@ -225,7 +225,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ float4 ld_shared_f32x4(uint32_t addr) {
     float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
 template <int N>
@@ -237,19 +237,19 @@ template <typename In, int CH>
 __device__ __forceinline__ float raw_frame_to_mono(uint32_t addr) {
     if constexpr (sizeof(In) == 4 && CH == 2) {
         float a, b;
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(a), "=f"(b) : "r"(addr));
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(a), "=f"(b) : "r"(addr) : "memory");
         return (a + b) * 0.5f;
     } else if constexpr (sizeof(In) == 4) {
         float a;
-        asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(a) : "r"(addr));
+        asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(a) : "r"(addr) : "memory");
         return a;
     } else if constexpr (CH == 2) {
         int v;
-        asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(v) : "r"(addr));
+        asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
         return static_cast<float>(__dp2a_lo(v, 0x0101, 0)) * (0.5f / 32768.0f);                 // lo + hi in one instruction
     } else {
         int v;
-        asm volatile("ld.shared.s16 %0, [%1];\n" : "=r"(v) : "r"(addr));
+        asm volatile("ld.shared.s16 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
         return static_cast<float>(v) * (1.0f / 32768.0f);
     }
 }
@@ -259,20 +259,20 @@ template <typename In, int CH>
 __device__ __forceinline__ float2 raw_two_frames_to_mono(uint32_t addr) {
     if constexpr (sizeof(In) == 4 && CH == 2) {
         float a, b, c, d;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr) : "memory");
         return make_float2((a + b) * 0.5f, (c + d) * 0.5f);
     } else if constexpr (sizeof(In) == 4) {
         float a, b;
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(a), "=f"(b) : "r"(addr));
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(a), "=f"(b) : "r"(addr) : "memory");
         return make_float2(a, b);
     } else if constexpr (CH == 2) {
         int v, w;
-        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];\n" : "=r"(v), "=r"(w) : "r"(addr));
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];\n" : "=r"(v), "=r"(w) : "r"(addr) : "memory");
         return make_float2(static_cast<float>(__dp2a_lo(v, 0x0101, 0)) * (0.5f / 32768.0f),
                            static_cast<float>(__dp2a_lo(w, 0x0101, 0)) * (0.5f / 32768.0f));
     } else {
         int v;
-        asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(v) : "r"(addr));
+        asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
         return make_float2(static_cast<float>(static_cast<short>(v & 0xFFFF)) * (1.0f / 32768.0f),
                            static_cast<float>(v >> 16) * (1.0f / 32768.0f));
     }
