@@ -234,6 +234,7 @@ struct sad_ctx {
     // ingest (f1): tap bands of the last sample rate seen
     int ingest_sr = 0;
     sad::ResamplePlan ingest_plan{};
+    sad::UniformTaps ingest_uniform{};
     int* d_tap_first = nullptr;
     float* d_tap_w = nullptr;
 
@@ -1117,9 +1118,10 @@ int sad_ingest(sad_ctx* c, const void* pcm, int sample_format, long long n_frame
         CU_OK(c, cudaMemcpy(c->d_tap_first, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice));
         CU_OK(c, cudaMemcpy(c->d_tap_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
         c->ingest_plan = plan;
+        sad::build_uniform_taps(plan, first, w, &c->ingest_uniform);   // outputs == 0 unless the ratio has one or two phases
         c->ingest_sr = sr_in;
     }
-    const sad::IngestTables tb{c->d_tap_first, c->d_tap_w};
+    const sad::IngestTables tb{c->d_tap_first, c->d_tap_w, c->ingest_uniform.outputs > 0 ? &c->ingest_uniform : nullptr};
     CU_OK(c, sad::ingest_launch(pcm, sample_format, n_frames, n_channels, &c->ingest_plan, tb, out, n_real, out_len, st,
                                 &c->launches));
     return SAD_OK;

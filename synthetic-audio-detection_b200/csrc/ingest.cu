@@ -13,8 +13,9 @@
 //   `pair` kernel (every rate up to 96 kHz; mono or stereo on a 16-byte aligned base): persistent blocks, the
 //   raw PCM of the next item staged by cp.async while the current one is filtered, two adjacent outputs per thread
 //   on one window of 16-byte shared loads with the taps in registers.  Measured (B200, 25 min of stereo int16,
-//   tools/ingest_bench.py): 3.8-3.9 TB/s at 44.1 and 48 kHz (58-60 % of the measured HBM copy bandwidth), 3.1-3.9 TB/s at
-//   8-24 kHz, 2.4-2.5 TB/s at 88.2 / 96 kHz (one output per thread there).  ncu on the way there: the first cut was instruction-issue bound (73 % issue slots, 131 instructions per
+//   tools/ingest_bench.py): 3.8 TB/s at 44.1 kHz (58 % of the measured HBM copy bandwidth), 3.1-3.9 TB/s at 8 / 22.05 /
+//   24 kHz, 2.2-2.4 TB/s at 88.2 kHz (one output per thread there); the few-phase form of the kernel (taps as kernel
+//   parameters, ingest_taps.h UniformTaps) runs 48 kHz at 4.5 (69 %), 16 kHz at 5.1 (78 %), 96 kHz at 4.0 TB/s (61 %).  ncu on the way there: the first cut was instruction-issue bound (73 % issue slots, 131 instructions per
 //   output against 24 useful FMAs: a conversion pass with a division and two guarded stores per frame, 64-bit index
 //   arithmetic per round, the shared base address rebuilt from S2R at every use); the version below executes ~45.
 //   `phase` kernel (other channel counts, unaligned streams, 192 kHz): a block owns blockDim * R consecutive outputs,
@@ -281,13 +282,17 @@ __device__ __forceinline__ void st_shared_f32x2(uint32_t addr, float2 v) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};\n" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
 
-template <typename In, int CH, int TE, int G>
-__global__ void __launch_bounds__(kPairThreads, 2) ingest_resample_pair_kernel(const In* __restrict__ pcm, long long n_frames,
+// UORIG > 0 selects the few-phase form (ingest_taps.h UniformTaps): UNEW phases, UTAPS shifted taps per phase read from
+// the kernel parameter `uni` as constant-bank operands, G outputs per thread on a window that starts at t * (G / UNEW) *
+// UORIG -- no tap registers, four blocks per SM.
+template <typename In, int CH, int TE, int G, int MINB = 2, int UORIG = 0, int UNEW = 1, int UTAPS = 0>
+__global__ void __launch_bounds__(kPairThreads, MINB) ingest_resample_pair_kernel(const In* __restrict__ pcm, long long n_frames,
                                                                                    ResamplePlan plan, PairGeometry geo,
+                                                                                   const __grid_constant__ UniformTaps uni,
                                                                                    const int* __restrict__ tap_first,
                                                                                    const float* __restrict__ tap_w, float* __restrict__ out,
                                                                                    long long n_real, long long out_len, long long n_items,
-                                                                                   bool out8) {
+                                                                                   bool out_vec) {
     constexpr int bpf = static_cast<int>(sizeof(In)) * CH;          // bytes per frame: 2, 4 or 8
     constexpr int fpc = 16 / bpf;                                   // frames per 16-byte chunk
     extern __shared__ float4 smem4[];
@@ -328,23 +333,29 @@ __global__ void __launch_bounds__(kPairThreads, 2) ingest_resample_pair_kernel(c
     }
 
     // this thread's window inside a sub-span and its G shifted tap sets
-    int pos[G], ph[G];
+    constexpr int kRegTaps = UORIG > 0 ? 1 : TE;                    // the few-phase form keeps no taps in registers
+    float W[G][kRegTaps];
+    int base;
+    if constexpr (UORIG > 0) {
+        base = t * ((G / UNEW) * UORIG);                            // a multiple of 4
+    } else {
+        int pos[G], ph[G];
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        const int m = (G * t + g) / plan.new_f;
-        ph[g] = (G * t + g) - m * plan.new_f;
-        pos[g] = geo.lead + m * plan.orig_f + tap_first[ph[g]] - plan.first0;
-    }
-    const int base = pos[0] & ~3;
-    float W[G][TE];
+        for (int g = 0; g < G; ++g) {
+            const int m = (G * t + g) / plan.new_f;
+            ph[g] = (G * t + g) - m * plan.new_f;
+            pos[g] = geo.lead + m * plan.orig_f + tap_first[ph[g]] - plan.first0;
+        }
+        base = pos[0] & ~3;
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        const int sh = pos[g] - base;
-        const float* w = tap_w + static_cast<size_t>(ph[g]) * plan.max_taps;
+        for (int g = 0; g < G; ++g) {
+            const int sh = pos[g] - base;
+            const float* w = tap_w + static_cast<size_t>(ph[g]) * plan.max_taps;
 #pragma unroll
-        for (int i = 0; i < TE; ++i) {
-            const int k = i - sh;
-            W[g][i] = (k >= 0 && k < plan.max_taps) ? w[k] : 0.f;
+            for (int i = 0; i < TE; ++i) {
+                const int k = i - sh;
+                W[g][i] = (k >= 0 && k < plan.max_taps) ? w[k] : 0.f;
+            }
         }
     }
     const uint32_t win_addr = span_addr + static_cast<uint32_t>(base) * 4u;
@@ -363,7 +374,26 @@ __global__ void __launch_bounds__(kPairThreads, 2) ingest_resample_pair_kernel(c
             const int skip = static_cast<int>(ff & static_cast<long long>(fpc - 1));
             const uint32_t src0 = raw_addr + static_cast<uint32_t>(slot * geo.n_chunks) * 16u + static_cast<uint32_t>(skip) * bpf;
             const uint32_t src_step = static_cast<uint32_t>(geo.round_stride) * bpf, dst_step = static_cast<uint32_t>(geo.sub_floats) * 4u;
-            if (geo.two) {
+            if (geo.two && geo.rounds < 4) {
+                // few rounds (the few-phase kernels, short streams): batch over the columns instead -- four loads in
+                // flight, then four stores, per round
+                for (int i = 0; i < geo.rounds; ++i) {
+                    const uint32_t src_i = src0 + static_cast<uint32_t>(i) * src_step, dst_i = span_addr + static_cast<uint32_t>(i) * dst_step;
+                    for (int k = 2 * t; k < geo.sub_floats; k += 8 * nt) {
+                        float2 v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int kk = k + u * 2 * nt;
+                            if (kk < geo.sub_floats) v[u] = raw_two_frames_to_mono<In, CH>(src_i + static_cast<uint32_t>(kk) * bpf);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int kk = k + u * 2 * nt;
+                            if (kk < geo.sub_floats) st_shared_f32x2(dst_i + static_cast<uint32_t>(kk) * 4u, v[u]);
+                        }
+                    }
+                }
+            } else if (geo.two) {
                 // even stride, even first frame: two frames per step on 8-byte (two-frame) accesses
                 for (int k = 2 * t; k < geo.sub_floats; k += 2 * nt) {
                     uint32_t src = src0 + static_cast<uint32_t>(k) * bpf, dst = span_addr + static_cast<uint32_t>(k) * 4u;
@@ -409,7 +439,7 @@ __global__ void __launch_bounds__(kPairThreads, 2) ingest_resample_pair_kernel(c
         cp_async_commit();
         slot = slot + 1 == kPairDepth ? 0 : slot + 1;
 
-        const bool whole = out8 && j_item - G * t + per_item <= n_real;   // no padding, no tail inside this item
+        const bool whole = out_vec && j_item - G * t + per_item <= n_real;   // no padding, no tail inside this item
         float* o = out + j_item;
         uint32_t xa = win_addr;
 #pragma unroll 2
@@ -424,11 +454,26 @@ __global__ void __launch_bounds__(kPairThreads, 2) ingest_resample_pair_kernel(c
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
 #pragma unroll
-                    for (int g = 0; g < G; ++g) acc[g] = fmaf(W[g][4 * c + e], x[e], acc[g]);
+                    for (int g = 0; g < G; ++g) {
+                        if constexpr (UORIG > 0) {
+                            constexpr int kDummy = 0;
+                            (void)kDummy;
+                            const int k = 4 * c + e - (g / UNEW) * UORIG;             // compile-time after unrolling
+                            if (k >= 0 && k < UTAPS) acc[g] = fmaf(uni.w[(g % UNEW) * UTAPS + k], x[e], acc[g]);
+                        } else {
+                            acc[g] = fmaf(W[g][4 * c + e], x[e], acc[g]);
+                        }
+                    }
             }
             if (whole) {
-                if constexpr (G == 2) *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1]);
-                else o[0] = acc[0];
+                if constexpr (G % 4 == 0) {
+#pragma unroll
+                    for (int g = 0; g < G; g += 4) *reinterpret_cast<float4*>(o + g) = make_float4(acc[g], acc[g + 1], acc[g + 2], acc[g + 3]);
+                } else if constexpr (G == 2) {
+                    *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1]);
+                } else {
+                    o[0] = acc[0];
+                }
             } else {
                 const long long j = j_item + static_cast<long long>(G) * nt * i;
 #pragma unroll
@@ -442,20 +487,19 @@ __global__ void __launch_bounds__(kPairThreads, 2) ingest_resample_pair_kernel(c
     cp_async_wait<0>();
 }
 
-template <typename In, int CH, int TE, int G>
-cudaError_t launch_pair(const In* pcm, long long n_frames, const ResamplePlan& plan, const PairGeometry& geo,
+template <typename In, int CH, int TE, int G, int MINB = 2, int UORIG = 0, int UNEW = 1, int UTAPS = 0>
+cudaError_t launch_pair(const In* pcm, long long n_frames, const ResamplePlan& plan, const PairGeometry& geo, const UniformTaps& uni,
                         const int* tap_first, const float* tap_w, float* out, long long n_real, long long out_len, int threads,
                         size_t smem, int sms, cudaStream_t stream) {
     const long long per_item = static_cast<long long>(G) * threads * geo.rounds;
     const long long n_items = (out_len + per_item - 1) / per_item;
-    cudaError_t e = cudaFuncSetAttribute(ingest_resample_pair_kernel<In, CH, TE, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+    auto kernel = ingest_resample_pair_kernel<In, CH, TE, G, MINB, UORIG, UNEW, UTAPS>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    const long long cap = static_cast<long long>(sms) * 2;             // two resident blocks per SM
+    const long long cap = static_cast<long long>(sms) * MINB;          // resident blocks per SM
     const unsigned grid = static_cast<unsigned>(n_items < cap ? n_items : cap);
-    const bool out8 = (reinterpret_cast<uintptr_t>(out) & 7) == 0;
-    ingest_resample_pair_kernel<In, CH, TE, G><<<grid, threads, smem, stream>>>(pcm, n_frames, plan, geo, tap_first, tap_w, out,
-                                                                                   n_real, out_len, n_items, out8);
+    const bool out_vec = (reinterpret_cast<uintptr_t>(out) & (G % 4 == 0 ? 15 : 7)) == 0;
+    kernel<<<grid, threads, smem, stream>>>(pcm, n_frames, plan, geo, uni, tap_first, tap_w, out, n_real, out_len, n_items, out_vec);
     return cudaGetLastError();
 }
 
@@ -465,23 +509,48 @@ cudaError_t launch_pair(const In* pcm, long long n_frames, const ResamplePlan& p
 // 34-37-tap rates (88.2 / 96 kHz): two tap sets of 44 need 158 registers, one block per SM, and measured 0.81x of
 // the one-output instantiation (2.06 against 2.54 TB/s at 96 kHz): occupancy carries the kernel.  SAD_INGEST_PAIR=0 turns it off.
 template <typename In>
-bool try_pair(const In* pcm, long long n_frames, int channels, const ResamplePlan& plan, const int* tap_first, const float* tap_w,
-              float* out, long long n_real, long long out_len, cudaStream_t stream, cudaError_t* err) {
+bool try_pair(const In* pcm, long long n_frames, int channels, const ResamplePlan& plan, const IngestTables& tb, float* out,
+              long long n_real, long long out_len, cudaStream_t stream, cudaError_t* err) {
     static const bool enabled = [] { const char* v = getenv("SAD_INGEST_PAIR"); return !(v && v[0] == '0'); }();
+    static const bool few_phase = [] { const char* v = getenv("SAD_INGEST_UNIFORM"); return !(v && v[0] == '0'); }();
     if (!enabled || channels > 2 || n_frames < 1 || (reinterpret_cast<uintptr_t>(pcm) & 15) != 0) return false;
     int dev = 0, sms = 0;
     if ((*err = cudaGetDevice(&dev)) != cudaSuccess || (*err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
         return true;
     PairChoice c{};
-    if (!choose_pair_geometry(plan, static_cast<int>(sizeof(In)) * channels, out_len, sms, &c)) return false;
+    if (!choose_pair_geometry(plan, static_cast<int>(sizeof(In)) * channels, out_len, sms, &c, few_phase ? tb.uniform : nullptr)) return false;
     const PairGeometry& geo = c.geo;
     const int threads = c.threads;
     const size_t smem = c.smem;
-#define SAD_PAIR_CASE(TE_, G_)                                                                                                     \
-    *err = channels == 2 ? launch_pair<In, 2, TE_, G_>(pcm, n_frames, plan, geo, tap_first, tap_w, out, n_real, out_len, threads,  \
-                                                       smem, sms, stream)                                                          \
-                         : launch_pair<In, 1, TE_, G_>(pcm, n_frames, plan, geo, tap_first, tap_w, out, n_real, out_len, threads,  \
-                                                       smem, sms, stream)
+    const int* tap_first = tb.tap_first;
+    const float* tap_w = tb.tap_w;
+    static const UniformTaps no_taps{};
+#define SAD_PAIR_CASE(TE_, G_)                                                                                                    \
+    *err = channels == 2 ? launch_pair<In, 2, TE_, G_>(pcm, n_frames, plan, geo, no_taps, tap_first, tap_w, out, n_real, out_len, \
+                                                       threads, smem, sms, stream)                                                \
+                         : launch_pair<In, 1, TE_, G_>(pcm, n_frames, plan, geo, no_taps, tap_first, tap_w, out, n_real, out_len, \
+                                                       threads, smem, sms, stream)
+#define SAD_UNIFORM_CASE(ORIG_, NEW_, G_, TAPS_)                                                                                  \
+    if (u.orig == ORIG_ && u.phases == NEW_ && u.outputs == G_ && u.taps == TAPS_) {                                             \
+        constexpr int kWin = ((G_ / NEW_ - 1) * ORIG_ + TAPS_ + 3) / 4 * 4;                                                       \
+        *err = channels == 2 ? launch_pair<In, 2, kWin, G_, 4, ORIG_, NEW_, TAPS_>(pcm, n_frames, plan, geo, u, tap_first, tap_w, \
+                                                                                   out, n_real, out_len, threads, smem, sms,      \
+                                                                                   stream)                                        \
+                             : launch_pair<In, 1, kWin, G_, 4, ORIG_, NEW_, TAPS_>(pcm, n_frames, plan, geo, u, tap_first, tap_w, \
+                                                                                   out, n_real, out_len, threads, smem, sms,      \
+                                                                                   stream);                                       \
+        return true;                                                                                                              \
+    }
+    if (c.uniform) {
+        const UniformTaps& u = *tb.uniform;                          // the rows of kUniformConfigs
+        SAD_UNIFORM_CASE(3, 1, 4, 40)
+        SAD_UNIFORM_CASE(2, 1, 4, 28)
+        SAD_UNIFORM_CASE(6, 1, 2, 76)
+        SAD_UNIFORM_CASE(3, 2, 8, 24)
+        SAD_UNIFORM_CASE(1, 2, 8, 16)
+        *err = cudaErrorInvalidValue;                                // a config without an instantiation
+        return true;
+    }
     switch (c.window) {
         case 20: SAD_PAIR_CASE(20, 2); break;
         case 24: SAD_PAIR_CASE(24, 2); break;
@@ -489,6 +558,7 @@ bool try_pair(const In* pcm, long long n_frames, int channels, const ResamplePla
         default: SAD_PAIR_CASE(40, 1); break;
     }
 #undef SAD_PAIR_CASE
+#undef SAD_UNIFORM_CASE
     return true;
 }
 
@@ -554,8 +624,8 @@ cudaError_t ingest_launch(const void* pcm, int sample_format, long long n_frames
     } else {
         cudaError_t e = cudaSuccess;
         const bool pair = sample_format == 0
-            ? try_pair(static_cast<const int16_t*>(pcm), n_frames, channels, *plan, tap_first, tap_w, out, n_real, out_len, stream, &e)
-            : try_pair(static_cast<const float*>(pcm), n_frames, channels, *plan, tap_first, tap_w, out, n_real, out_len, stream, &e);
+            ? try_pair(static_cast<const int16_t*>(pcm), n_frames, channels, *plan, tb, out, n_real, out_len, stream, &e)
+            : try_pair(static_cast<const float*>(pcm), n_frames, channels, *plan, tb, out, n_real, out_len, stream, &e);
         if (pair) {
             if (launches) *launches += 1;
             return e;

@@ -12,6 +12,7 @@ namespace sad {
 struct IngestTables {
     const int* tap_first;    // [new_f] first kept tap of each phase
     const float* tap_w;      // [new_f][max_taps]
+    const UniformTaps* uniform = nullptr;   // HOST pointer: the taps of a few-phase ratio as kernel parameters, or null
 };
 
 size_t ingest_smem_bytes(const ResamplePlan& plan);

@@ -1,7 +1,7 @@
 // CPU check of the ingest stage's host arithmetic (there is no GPU in the build container):
 //   ingest_host_check taps <sr_in>      -> "orig new width full max_taps", then per phase: first tap index and the taps
 //   ingest_host_check length <sr_in> <n_frames>...  -> output length and un-padded length per n_frames
-//   ingest_host_check pair <sr_in> <bytes_per_frame> <n_frames> <sms>
+//   ingest_host_check pair <sr_in> <bytes_per_frame> <n_frames> <sms> [few_phase = 1]
 //       -> replays the index walk of the staged (`pair`) resampling kernel of ingest.cu with the geometry the host picks
 //          (choose_pair_geometry): raw chunks of an item -> per-round float sub-spans -> per-thread windows, and checks
 //          that tap k of every output reads exactly the frame torchaudio's kernel reads; prints the geometry and "ok <n>".
@@ -20,7 +20,7 @@ static const long long kOutside = -1, kUnset = -2;
 
 static int skip_of(long long ff, int fpc) { return static_cast<int>(ff & (fpc - 1)); }
 
-static int replay_pair(int sr, int bytes_per_frame, long long n_frames, int sms) {
+static int replay_pair(int sr, int bytes_per_frame, long long n_frames, int sms, bool few_phase) {
     sad::ResamplePlan plan{};
     std::vector<int> first;
     std::vector<float> w;
@@ -31,14 +31,27 @@ static int replay_pair(int sr, int bytes_per_frame, long long n_frames, int sms)
     long long n_real = 0;
     const long long out_len = sad::ingest_length(n_frames, sr, &n_real);
     sad::PairChoice c{};
-    if (!sad::choose_pair_geometry(plan, bytes_per_frame, out_len, sms, &c)) {
+    sad::UniformTaps uni{};
+    const bool has_uni = few_phase && sad::build_uniform_taps(plan, first, w, &uni);
+    if (has_uni) {                                                                 // the parameter block holds exactly the shifted taps
+        std::vector<float> want(80, 0.f);
+        for (int p = 0; p < uni.phases; ++p)
+            for (int k = 0; k < plan.max_taps; ++k)
+                want[p * uni.taps + sad::even_lead(plan) + first[p] - plan.first0 + k] = w[static_cast<size_t>(p) * plan.max_taps + k];
+        if (uni.phases * uni.taps > 80 || memcmp(want.data(), uni.w, sizeof(uni.w)) != 0 || uni.outputs % uni.phases ||
+            (uni.outputs / uni.phases) * uni.orig % 4) {
+            printf("bad uniform taps\n");
+            return 1;
+        }
+    }
+    if (!sad::choose_pair_geometry(plan, bytes_per_frame, out_len, sms, &c, has_uni ? &uni : nullptr)) {
         printf("not a pair ratio\n");
         return 0;
     }
     const sad::PairGeometry& g = c.geo;
     const int G = c.outputs, TE = c.window, nt = c.threads, fpc = 16 / bytes_per_frame;
-    printf("G %d TE %d threads %d rounds %d stride %d sub %d overlap %d chunks %d smem %zu two %d lead %d\n", G, TE, nt, g.rounds,
-           g.round_stride, g.sub_floats, g.overlap, g.n_chunks, c.smem, g.two, g.lead);
+    printf("G %d TE %d threads %d rounds %d stride %d sub %d overlap %d chunks %d smem %zu two %d lead %d uniform %d\n", G, TE, nt,
+           g.rounds, g.round_stride, g.sub_floats, g.overlap, g.n_chunks, c.smem, g.two, g.lead, c.uniform);
     if (G * nt % plan.new_f || g.sub_floats % 4 || g.overlap != g.sub_floats - g.round_stride || c.smem > 113 * 1024) {
         printf("bad geometry\n");
         return 1;
@@ -72,13 +85,30 @@ static int replay_pair(int sr, int bytes_per_frame, long long n_frames, int sms)
                 span[static_cast<size_t>(i) * g.sub_floats + k] = raw[src];
             }
         for (int t = 0; t < nt; ++t) {                                             // filter pass
-            int pos[2], ph[2];
-            for (int q = 0; q < G; ++q) {
-                const int m = (G * t + q) / plan.new_f;
-                ph[q] = (G * t + q) - m * plan.new_f;
-                pos[q] = g.lead + m * plan.orig_f + first[ph[q]] - plan.first0;
+            int pos[16], ph[16];
+            int base;
+            if (c.uniform) {
+                base = t * (G / uni.phases) * uni.orig;
+                if (base % 4) {
+                    printf("window of thread %d is not 16-byte aligned\n", t);
+                    return 1;
+                }
+                for (int q = 0; q < G; ++q) {
+                    ph[q] = q % uni.phases;
+                    pos[q] = base + (q / uni.phases) * uni.orig + g.lead + first[ph[q]] - plan.first0;   // where w[ph][shift + k] meets x
+                    if ((G * t + q) % plan.new_f != ph[q]) {
+                        printf("phase of thread %d output %d\n", t, q);
+                        return 1;
+                    }
+                }
+            } else {
+                for (int q = 0; q < G; ++q) {
+                    const int m = (G * t + q) / plan.new_f;
+                    ph[q] = (G * t + q) - m * plan.new_f;
+                    pos[q] = g.lead + m * plan.orig_f + first[ph[q]] - plan.first0;
+                }
+                base = pos[0] & ~3;
             }
-            const int base = pos[0] & ~3;
             if (base + TE > g.sub_floats) {
                 printf("window of thread %d leaves its sub-span\n", t);
                 return 1;
@@ -145,7 +175,8 @@ int main(int argc, char** argv) {
         }
         return 0;
     }
-    if (argc >= 6 && !strcmp(argv[1], "pair")) return replay_pair(atoi(argv[2]), atoi(argv[3]), atoll(argv[4]), atoi(argv[5]));
+    if (argc >= 6 && !strcmp(argv[1], "pair"))
+        return replay_pair(atoi(argv[2]), atoi(argv[3]), atoll(argv[4]), atoi(argv[5]), argc < 7 || atoi(argv[6]) != 0);
     fprintf(stderr, "usage: ingest_host_check taps <sr> | length <sr> <frames>... | pair <sr> <bytes_per_frame> <frames> <sms>\n");
     return 2;
 }

@@ -105,6 +105,43 @@ inline bool build_resample_taps(int sr_in, ResamplePlan* plan, std::vector<int>*
     return true;
 }
 
+// ---- few-phase ratios: the taps as kernel parameters -----------------------------------------------------------------------
+// With one or two phases (96 / 64 / 192 kHz: one; 48 / 16 kHz: two) every thread of a block filters the same phases, so
+// the taps need no registers: they travel as a kernel parameter and reach the FMAs as constant-bank operands.  A thread
+// then affords `outputs` adjacent outputs on one window (eight at 48 kHz: one 16-byte shared load per output instead of
+// three).  w[p][taps] holds phase p shifted to its place in that window: w[p][lead + first[p] - first0 + k] = tap k.
+struct UniformTaps {
+    int orig, phases, outputs, taps;   // 0 outputs: not a few-phase ratio
+    float w[80];                       // [phases][taps]
+};
+
+struct UniformConfig { int orig, phases, outputs, taps; };
+// outputs: a multiple of phases with (outputs / phases) * orig % 4 == 0, so that every thread's window starts on a
+// 16-byte boundary; taps: max_taps + the largest shift, rounded up to 4
+constexpr UniformConfig kUniformConfigs[] = {{3, 1, 4, 40}, {2, 1, 4, 28}, {6, 1, 2, 76}, {3, 2, 8, 24}, {1, 2, 8, 16}};
+
+inline int even_lead(const ResamplePlan& plan) { return ((plan.first0 - plan.width) % 2 + 2) % 2; }
+
+inline bool build_uniform_taps(const ResamplePlan& plan, const std::vector<int>& first, const std::vector<float>& w, UniformTaps* u) {
+    *u = UniformTaps{};
+    if (plan.pair_shift_max < 0) return false;
+    for (const UniformConfig& cfg : kUniformConfigs) {
+        if (cfg.orig != plan.orig_f || cfg.phases != plan.new_f) continue;
+        const int lead = even_lead(plan);
+        for (int p = 0; p < cfg.phases; ++p) {
+            const int shift = lead + first[p] - plan.first0;
+            if (shift < 0 || shift + plan.max_taps > cfg.taps) return false;
+            for (int k = 0; k < plan.max_taps; ++k) u->w[p * cfg.taps + shift + k] = w[static_cast<size_t>(p) * plan.max_taps + k];
+        }
+        u->orig = cfg.orig;
+        u->phases = cfg.phases;
+        u->outputs = cfg.outputs;
+        u->taps = cfg.taps;
+        return true;
+    }
+    return false;
+}
+
 // ---- geometry of the staged (`pair`) resampling kernel of ingest.cu, chosen on the host -----------------------------------
 // Kept here, free of CUDA, so that csrc/ingest_host_check.cpp can replay the kernel's index walk on the CPU.
 constexpr int kPairDepth = 2;        // slots of the raw-PCM ring in shared memory
@@ -121,8 +158,9 @@ struct PairGeometry {
 };
 
 struct PairChoice {
-    int outputs;         // G: adjacent outputs per thread (2, or 1 for the 34-37-tap rates)
-    int window;          // TE: floats of the per-thread window (20, 24, 28 or 40)
+    int uniform;         // 1: the few-phase kernel (taps as kernel parameters, see UniformTaps)
+    int outputs;         // G: adjacent outputs per thread (2, or 1 for the 34-37-tap rates; UniformTaps::outputs)
+    int window;          // TE: floats of the per-thread window (20, 24, 28 or 40; few-phase: (outputs / phases - 1) * orig + taps)
     int threads;         // block size: whole periods of the phase pattern
     PairGeometry geo;
     size_t smem;         // dynamic shared memory per block
@@ -130,47 +168,68 @@ struct PairChoice {
 
 // False when the ratio does not fit the kernel (band starts not monotone, window > 40 floats, phase period > 320 threads).
 // bytes_per_frame: 2, 4 or 8 (mono / stereo, int16 / float32).
-inline bool choose_pair_geometry(const ResamplePlan& plan, int bytes_per_frame, long long out_len, int sms, PairChoice* c) {
+inline bool choose_pair_geometry(const ResamplePlan& plan, int bytes_per_frame, long long out_len, int sms, PairChoice* c,
+                                 const UniformTaps* uni = nullptr) {
     if (plan.pair_shift_max < 0) return false;
+    const bool uniform = uni && uni->outputs > 0;
     int G = 2, need = 3 + plan.pair_shift_max + plan.max_taps;     // alignment slack of a 16-byte window + the pair's shift + taps
-    if (need > 28) {
-        G = 1;
-        need = 3 + plan.max_taps;
-        if (need > 40) return false;
+    int TE, threads;
+    if (uniform) {
+        G = uni->outputs;
+        TE = ((G / uni->phases - 1) * uni->orig + uni->taps + 3) / 4 * 4;
+        threads = 256;
+    } else {
+        if (need > 28) {
+            G = 1;
+            need = 3 + plan.max_taps;
+            if (need > 40) return false;
+        }
+        TE = G == 1 ? 40 : need <= 20 ? 20 : need <= 24 ? 24 : 28;
+        const int period = G == 2 && plan.new_f % 2 == 0 ? plan.new_f / 2 : plan.new_f;   // threads per period of the phase pattern
+        if (period > kPairThreads) return false;
+        threads = kPairThreads / period * period;
+        if (threads < 128) return false;
     }
-    const int TE = G == 1 ? 40 : need <= 20 ? 20 : need <= 24 ? 24 : 28;
-    const int period = G == 2 && plan.new_f % 2 == 0 ? plan.new_f / 2 : plan.new_f;   // threads per period of the phase pattern
-    if (period > kPairThreads) return false;
-    const int threads = kPairThreads / period * period;
-    if (threads < 128) return false;
     const int fpc = 16 / bytes_per_frame;
-    const int frames_round = G * threads / plan.new_f;
     PairGeometry geo{};
-    geo.round_stride = frames_round * plan.orig_f;
-    // items start round_stride * rounds frames apart: with an even stride the parity of an item's first frame is that of
-    // first0 - width for every item, and one leading frame makes it even
-    geo.two = geo.round_stride % 2 == 0;
-    geo.lead = geo.two ? ((plan.first0 - plan.width) % 2 + 2) % 2 : 0;
-    const int need_round = geo.lead + (frames_round - 1) * plan.orig_f + plan.first_spread + TE;   // frames a round's windows reach over
-    geo.sub_floats = (need_round + 3) / 4 * 4;
-    if (geo.sub_floats < geo.round_stride) geo.sub_floats = (geo.round_stride + 3) / 4 * 4;
-    geo.overlap = geo.sub_floats - geo.round_stride;
     size_t smem = 0;
-    auto size_for = [&](int r) {
-        geo.rounds = r;
-        const long long need_item = static_cast<long long>(r - 1) * geo.round_stride + geo.sub_floats;
-        geo.n_chunks = static_cast<int>((need_item + fpc - 1 + fpc - 1) / fpc);     // the first chunk may start fpc - 1 frames early
-        smem = static_cast<size_t>(r) * geo.sub_floats * 4 + static_cast<size_t>(kPairDepth) * geo.n_chunks * 16;
-        return smem;
-    };
-    const size_t budget = 100 * 1024;                                // two blocks per SM
-    int rounds = 16;
-    while (rounds >= 1 && size_for(rounds) > budget) rounds >>= 1;
-    // short streams: smaller items, so that every resident block gets a few
-    const long long per_round = static_cast<long long>(G) * threads;
-    while (rounds > 1 && (out_len + per_round * rounds - 1) / (per_round * rounds) < 8LL * sms) rounds >>= 1;
-    if (rounds < 1) return false;
-    size_for(rounds);
+    int rounds = 0;
+    for (int attempt = 0; attempt < 2 && rounds < 1; ++attempt) {
+        if (attempt == 1) {
+            if (!uniform) return false;
+            threads = 128;                                           // float stereo: half the block, still four per SM
+        }
+        const int frames_round = G * threads / plan.new_f;
+        geo = PairGeometry{};
+        geo.round_stride = frames_round * plan.orig_f;
+        // items start round_stride * rounds frames apart: with an even stride the parity of an item's first frame is that
+        // of first0 - width for every item, and one leading frame makes it even
+        geo.two = geo.round_stride % 2 == 0;
+        geo.lead = geo.two ? even_lead(plan) : 0;
+        if (uniform && !geo.two) return false;                       // (cannot happen: the thread stride is a multiple of 4)
+        // frames a round's windows reach over; few-phase: thread t's window is [t * stride, + TE)
+        const int need_round = uniform ? (threads - 1) * (G / plan.new_f) * plan.orig_f + TE
+                                       : geo.lead + (frames_round - 1) * plan.orig_f + plan.first_spread + TE;
+        geo.sub_floats = (need_round + 3) / 4 * 4;
+        if (geo.sub_floats < geo.round_stride) geo.sub_floats = (geo.round_stride + 3) / 4 * 4;
+        geo.overlap = geo.sub_floats - geo.round_stride;
+        auto size_for = [&](int r) {
+            geo.rounds = r;
+            const long long need_item = static_cast<long long>(r - 1) * geo.round_stride + geo.sub_floats;
+            geo.n_chunks = static_cast<int>((need_item + fpc - 1 + fpc - 1) / fpc);   // the first chunk may start fpc - 1 frames early
+            smem = static_cast<size_t>(r) * geo.sub_floats * 4 + static_cast<size_t>(kPairDepth) * geo.n_chunks * 16;
+            return smem;
+        };
+        const size_t budget = (uniform ? 52 : 100) * 1024;           // two blocks per SM (four of the few-phase kernel)
+        rounds = 16;
+        while (rounds >= 1 && size_for(rounds) > budget) rounds >>= 1;
+        // short streams: smaller items, so that every resident block gets a few
+        const long long per_round = static_cast<long long>(G) * threads;
+        while (rounds > 1 && (out_len + per_round * rounds - 1) / (per_round * rounds) < 8LL * sms) rounds >>= 1;
+        if (rounds >= 1) size_for(rounds);
+    }
+    if (rounds < 1) return uniform ? choose_pair_geometry(plan, bytes_per_frame, out_len, sms, c) : false;
+    c->uniform = uniform ? 1 : 0;
     c->outputs = G;
     c->window = TE;
     c->threads = threads;

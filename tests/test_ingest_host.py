@@ -58,7 +58,8 @@ def test_output_length_is_torchaudios_float32_ceil(checker):
             assert total == max(want, 128000)
 
 
-PAIR_GRID = [(44100, 4, 300_000, 148), (44100, 4, 9_000_001, 148), (44100, 2, 70_001, 148), (44100, 8, 1_000_003, 132),
+PAIR_GRID = [(192000, 4, 800_000, 148), (192000, 2, 100_001, 148), (48000, 8, 2_000_001, 148), (16000, 4, 1_000_003, 148),
+             (44100, 4, 300_000, 148), (44100, 4, 9_000_001, 148), (44100, 2, 70_001, 148), (44100, 8, 1_000_003, 132),
              (48000, 2, 100_001, 148), (48000, 4, 6_000_000, 148), (22050, 8, 70_001, 148), (22050, 4, 4_000_001, 148),
              (16000, 8, 5_000_000, 148), (16000, 2, 639, 148), (8000, 2, 4_001, 148), (8000, 4, 2_000_000, 148),
              (24000, 4, 96_001, 148), (12000, 4, 50_000, 148), (25600, 4, 123_457, 148), (37800, 4, 77_777, 148),
@@ -76,14 +77,26 @@ def test_pair_kernel_geometry_reads_the_right_frames(checker, sr, bytes_per_fram
     lines = r.stdout.strip().split("\n")
     assert r.returncode == 0, r.stdout[-500:]
     geo = dict(zip(lines[0].split()[::2], map(int, lines[0].split()[1::2])))
-    assert geo["G"] == (1 if sr in (88200, 96000, 64000) else 2)
+    few_phase = {96000: 4, 64000: 4, 192000: 2, 48000: 8, 16000: 8}             # one or two phases: taps as kernel parameters
+    if sr in few_phase:
+        assert geo["uniform"] == 1 and geo["G"] == few_phase[sr] and geo["smem"] <= 52 * 1024      # four blocks per SM
+        assert geo["threads"] == (128 if bytes_per_frame == 8 and sr in (48000, 96000) else 256)
+    else:
+        assert geo["uniform"] == 0 and geo["G"] == (1 if sr in (88200, 96000) else 2)
     assert geo["threads"] % 32 == 0 or sr == 25600                 # 5 phases: 320 threads anyway
     assert geo["smem"] <= 100 * 1024                                 # two blocks per SM
     n_real = -(-32000 * frames // sr)                                # ceil; the float32 rounding of torchaudio matters only
     assert lines[1].startswith("ok ") and abs(int(lines[1].split()[1]) - n_real) <= 1   # above 2^24 samples
 
 
-@pytest.mark.parametrize("sr", [11025, 192000, 12345])
+@pytest.mark.parametrize("sr,bytes_per_frame,frames", [(48000, 4, 6_000_000), (96000, 4, 500_000), (16000, 2, 70_001)])
+def test_few_phase_ratios_also_replay_on_the_register_tap_geometry(checker, sr, bytes_per_frame, frames):
+    """SAD_INGEST_UNIFORM=0 sends the one- and two-phase ratios through the register-tap form of the kernel."""
+    r = subprocess.run([checker, "pair", str(sr), str(bytes_per_frame), str(frames), "148", "0"], capture_output=True, text=True)
+    assert r.returncode == 0 and " uniform 0" in r.stdout and "\nok " in r.stdout, r.stdout[-300:]
+
+
+@pytest.mark.parametrize("sr", [11025, 12345])
 def test_ratios_the_pair_kernel_leaves_to_the_one_phase_kernel(checker, sr):
     out = subprocess.run([checker, "pair", str(sr), "4", "100000", "148"], capture_output=True, text=True, check=True).stdout
     assert out.strip() in ("not a pair ratio", "unsupported")
