@@ -133,10 +133,11 @@ for sr, ch, frames, fmt, odd in %r:
 
 
 def test_pair_kernel_is_bit_identical_to_the_one_phase_kernel():
-    """The two-outputs-per-thread resampler (ingest.cu, `pair`) adds only products with zero weights to the sums of the
-    one-phase-per-thread kernel: the two must agree to the bit, for every kind of ratio the pair kernel takes, both
-    sample formats, mono and stereo, unaligned streams (which keep the older kernel) and lengths that end inside an
-    item.  SAD_INGEST_PAIR=0 selects the older kernel everywhere."""
+    """The staged resampler (ingest.cu, `pair`: two outputs per thread with the taps in registers; one output per thread
+    at 88.2 kHz; the few-phase form with the taps as kernel parameters at 96 / 48 / 16 kHz) adds only products with zero
+    weights to the sums of the one-phase-per-thread kernel: the two must agree to the bit, for every kind of ratio the
+    staged kernel takes, both sample formats, mono and stereo, unaligned streams (which keep the older kernel) and
+    lengths that end inside an item.  SAD_INGEST_PAIR=0 selects the older kernel everywhere."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
