@@ -374,9 +374,9 @@ __global__ void __launch_bounds__(kPairThreads, MINB) ingest_resample_pair_kerne
             const int skip = static_cast<int>(ff & static_cast<long long>(fpc - 1));
             const uint32_t src0 = raw_addr + static_cast<uint32_t>(slot * geo.n_chunks) * 16u + static_cast<uint32_t>(skip) * bpf;
             const uint32_t src_step = static_cast<uint32_t>(geo.round_stride) * bpf, dst_step = static_cast<uint32_t>(geo.sub_floats) * 4u;
-            if (geo.two && geo.rounds < 4) {
-                // few rounds (the few-phase kernels, short streams): batch over the columns instead -- four loads in
-                // flight, then four stores, per round
+            if constexpr (UORIG > 0) {
+                // the few-phase kernels run one or two rounds per item (their stride is always even): batch over the
+                // columns instead -- four loads in flight, then four stores, per round
                 for (int i = 0; i < geo.rounds; ++i) {
                     const uint32_t src_i = src0 + static_cast<uint32_t>(i) * src_step, dst_i = span_addr + static_cast<uint32_t>(i) * dst_step;
                     for (int k = 2 * t; k < geo.sub_floats; k += 8 * nt) {
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(kPairThreads, MINB) ingest_resample_pair_kerne
                     }
                 }
             } else if (geo.two) {
-                // even stride, even first frame: two frames per step on 8-byte (two-frame) accesses
+                // even stride, even first frame: two frames per step on 8-byte (two-frame) accesses; batched over the rounds
                 for (int k = 2 * t; k < geo.sub_floats; k += 2 * nt) {
                     uint32_t src = src0 + static_cast<uint32_t>(k) * bpf, dst = span_addr + static_cast<uint32_t>(k) * 4u;
                     int i = 0;
